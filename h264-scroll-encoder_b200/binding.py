@@ -1,0 +1,199 @@
+"""
+ctypes binding of libh264scroll_b200.so.  No torch, no CPU fallback: if the library is missing or no
+sm_100 device is visible, GpuComposer() raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+from . import abi
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libh264scroll_b200.so")
+
+# every symbol include/*.h declares; tests check the built library exports all of them
+GPU_SYMBOLS = [
+    "h264gpu_init", "h264gpu_shutdown", "h264gpu_device_count", "h264gpu_last_error", "h264gpu_sm_count",
+    "h264gpu_malloc", "h264gpu_free", "h264gpu_host_alloc", "h264gpu_host_free", "h264gpu_memcpy_h2d",
+    "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
+    "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
+    "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
+    "h264gpu_compose_host", "h264gpu_launch_count"]
+REFERENCE_API_SYMBOLS = [
+    # include/composer.h
+    "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
+    "composer_write_scroll_frame", "composer_get_output_size", "composer_get_output",
+    "composer_write_to_file", "composer_finish", "composer_write_scroll_frames",
+    # include/h264_writer.h
+    "composer_config_init", "composer_config_set_sps_params", "composer_config_set_pps_params",
+    "h264_generate_sps", "h264_generate_pps", "h264_rewrite_idr_frame", "h264_rewrite_as_non_idr_i_frame",
+    "h264_write_scroll_p_frame", "h264_needs_waypoint", "h264_write_waypoint_p_frame",
+    "h264_p_slice_header_bits", "h264_scroll_regions", "h264_write_scroll_sequence",
+    # include/bitwriter.h
+    "bitwriter_init", "bitwriter_write_bits", "bitwriter_write_bit", "bitwriter_write_ue", "bitwriter_write_se",
+    "bitwriter_write_trailing_bits", "bitwriter_flush", "bitwriter_get_size", "bitwriter_get_bit_position",
+    "bitwriter_is_byte_aligned", "bitreader_init", "bitreader_read_bits", "bitreader_read_bit",
+    "bitreader_read_ue", "bitreader_read_se", "bitreader_get_bit_position", "bitreader_is_byte_aligned",
+    "bitreader_get_remaining_bytes", "bitreader_get_pointer",
+    # include/nal.h, include/nal_parser.h
+    "nal_writer_init", "nal_write_unit", "nal_writer_get_size", "nal_writer_get_output", "rbsp_to_ebsp",
+    "nal_parser_init", "nal_parser_next", "ebsp_to_rbsp", "parse_sps", "parse_pps"]
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise GpuError("%s is missing - run __graft_entry__.build() (nvcc, sm_100a); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.h264gpu_last_error.restype = C.c_char_p
+    L.h264gpu_malloc.restype = vp; L.h264gpu_malloc.argtypes = [sz]
+    L.h264gpu_free.argtypes = [vp]; L.h264gpu_free.restype = None
+    L.h264gpu_host_alloc.restype = vp; L.h264gpu_host_alloc.argtypes = [sz]
+    L.h264gpu_host_free.argtypes = [vp]; L.h264gpu_host_free.restype = None
+    for f in ("h264gpu_memcpy_h2d", "h264gpu_memcpy_d2h"):
+        getattr(L, f).argtypes = [vp, vp, sz, vp]
+    L.h264gpu_memset.argtypes = [vp, ci, sz, vp]
+    L.h264gpu_stream_create.restype = vp
+    L.h264gpu_stream_destroy.argtypes = [vp]; L.h264gpu_stream_destroy.restype = None
+    L.h264gpu_stream_sync.argtypes = [vp]
+    L.h264gpu_event_create.restype = vp
+    L.h264gpu_event_destroy.argtypes = [vp]; L.h264gpu_event_destroy.restype = None
+    L.h264gpu_event_record.argtypes = [vp, vp]
+    L.h264gpu_event_elapsed_ms.argtypes = [vp, vp]; L.h264gpu_event_elapsed_ms.restype = C.c_float
+    L.h264gpu_compose_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
+    L.h264gpu_raster_regions.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+    L.h264gpu_pack_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
+    L.h264gpu_launch_count.restype = C.c_uint64
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class DeviceBuffer:
+    def __init__(self, gc, nbytes):
+        self.gc, self.nbytes = gc, int(nbytes)
+        self.ptr = gc.lib.h264gpu_malloc(max(self.nbytes, 16))
+        if not self.ptr:
+            raise GpuError("device malloc of %d bytes failed: %s" % (nbytes, gc.err()))
+
+    def upload(self, arr, stream=None):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.gc.check(self.gc.lib.h264gpu_memcpy_h2d(self.ptr, _ptr(arr), arr.nbytes, stream))
+        return self
+
+    def download(self, dtype=np.uint8, count=None, offset=0, stream=None, sync=True):
+        dtype = np.dtype(dtype)
+        count = (self.nbytes - offset) // dtype.itemsize if count is None else count
+        out = np.empty(count, dtype=dtype)
+        self.gc.check(self.gc.lib.h264gpu_memcpy_d2h(_ptr(out), self.ptr + offset, out.nbytes, stream))
+        if sync:
+            self.gc.sync(stream)
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.gc.lib.h264gpu_free(self.ptr)
+            self.ptr = None
+
+
+class GpuComposer:
+    """Thin object over the C ABI (include/composer_gpu.h)."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        rc = self.lib.h264gpu_init(device)
+        if rc != 0:
+            raise GpuError("h264gpu_init(%d) failed (%d): %s" % (device, rc, self.err()))
+        self.device = device
+
+    def err(self):
+        return (self.lib.h264gpu_last_error() or b"").decode()
+
+    def check(self, rc):
+        if rc != 0:
+            raise GpuError("libh264scroll_b200 call failed (%d): %s" % (rc, self.err()))
+
+    def sync(self, stream=None):
+        self.check(self.lib.h264gpu_stream_sync(stream))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return self.alloc(arr.nbytes).upload(arr)
+
+    # ---- host-buffer call (what tests use for parity) ------------------------------------------
+    def compose_host(self, desc, hints, dyn=None, dyn_tab=None, payload=None, out_bytes=None):
+        desc = np.ascontiguousarray(desc, dtype=abi.FRAME_DESC)
+        hints = np.ascontiguousarray(hints, dtype=abi.HINT)
+        n = len(desc)
+        if out_bytes is None:
+            out_bytes = int((desc["out_off"] + desc["out_cap"]).max()) if n else 0
+        out = np.zeros(out_bytes, np.uint8)
+        sizes = np.zeros(n, np.uint32)
+        dyn = None if dyn is None else np.ascontiguousarray(dyn, dtype=abi.DYN_DESC)
+        dyn_tab = None if dyn_tab is None else np.ascontiguousarray(dyn_tab, dtype=np.uint32)
+        payload = None if payload is None else np.ascontiguousarray(payload, dtype=np.uint8)
+        rc = self.lib.h264gpu_compose_host(_ptr(desc), n, _ptr(hints), len(hints),
+                                           _ptr(dyn), 0 if dyn is None else len(dyn),
+                                           _ptr(dyn_tab), 0 if dyn_tab is None else len(dyn_tab),
+                                           _ptr(payload), 0 if payload is None else payload.size,
+                                           _ptr(out), out.size, _ptr(sizes))
+        self.check(rc)
+        return [out[int(d["out_off"]):int(d["out_off"]) + int(s)].copy() for d, s in zip(desc, sizes)], sizes
+
+    # ---- device-pointer calls --------------------------------------------------------------------
+    def compose_batch(self, d_desc, n, d_hints, d_dyn, d_tab, d_payload, d_out, d_sizes, stream=None):
+        p = lambda b: b.ptr if b is not None else None
+        self.check(self.lib.h264gpu_compose_batch(p(d_desc), n, p(d_hints), p(d_dyn), p(d_tab), p(d_payload),
+                                                  p(d_out), p(d_sizes), stream))
+
+    def raster_regions(self, d_rdesc, n, max_mbs, d_regions, d_dyn_info, d_hints, stream=None):
+        p = lambda b: b.ptr if b is not None else None
+        self.check(self.lib.h264gpu_raster_regions(p(d_rdesc), n, max_mbs, p(d_regions), p(d_dyn_info),
+                                                   p(d_hints), stream))
+
+    def pack_frames(self, d_desc, d_sizes, n, d_slots, d_packed, d_offsets, stream=None):
+        self.check(self.lib.h264gpu_pack_frames(d_desc.ptr, d_sizes.ptr, n, d_slots.ptr, d_packed.ptr,
+                                                d_offsets.ptr, stream))
+
+    def launch_count(self):
+        return int(self.lib.h264gpu_launch_count())
+
+
+# ---- reference-shaped C API (include/h264_writer.h, nal.h) as ctypes structs ----------------------
+
+class WaypointInfo(C.Structure):
+    _fields_ = [("offset_px", C.c_int), ("long_term_idx", C.c_int), ("valid", C.c_int)]
+
+
+class ComposerConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("mb_width", C.c_int), ("mb_height", C.c_int),
+                ("log2_max_frame_num", C.c_int), ("pic_order_cnt_type", C.c_int),
+                ("log2_max_pic_order_cnt_lsb", C.c_int), ("num_ref_idx_l0_default_minus1", C.c_int),
+                ("deblocking_filter_control_present_flag", C.c_int), ("frame_num", C.c_int),
+                ("idr_pic_id", C.c_int), ("waypoints", WaypointInfo * 8), ("num_waypoints", C.c_int)]
+
+
+class NALWriter(C.Structure):
+    _fields_ = [("output", C.c_void_p), ("output_capacity", C.c_size_t), ("output_pos", C.c_size_t),
+                ("rbsp", C.c_void_p), ("rbsp_capacity", C.c_size_t)]
+
+
+class Composer(C.Structure):
+    _fields_ = [("cfg", ComposerConfig), ("parse_cfg", ComposerConfig),
+                ("ref_a_rbsp", C.c_void_p), ("ref_a_size", C.c_size_t),
+                ("ref_b_rbsp", C.c_void_p), ("ref_b_size", C.c_size_t),
+                ("orig_sps", C.c_void_p), ("orig_sps_size", C.c_size_t),
+                ("orig_pps", C.c_void_p), ("orig_pps_size", C.c_size_t),
+                ("nw", NALWriter), ("output_buffer", C.c_void_p), ("output_capacity", C.c_size_t),
+                ("rbsp_temp", C.c_void_p), ("rbsp_capacity", C.c_size_t), ("frames_written", C.c_int)]

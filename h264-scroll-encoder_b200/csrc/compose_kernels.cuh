@@ -1,0 +1,28 @@
+/* compose_kernels.cuh - launch interface between capi.cu and compose_kernels.cu */
+#ifndef H264SCROLL_COMPOSE_KERNELS_CUH
+#define H264SCROLL_COMPOSE_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "composer_gpu.h"
+
+#define COMPOSE_THREADS   256
+#define COMPOSE_MAX_MB_W  H264GPU_MAX_MB_W
+
+namespace h264scroll {
+
+cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
+                           const H264GpuMbHint *d_hints, const H264GpuDynDesc *d_dyn,
+                           const uint32_t *d_dyn_tab, const uint8_t *d_payload,
+                           uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream);
+
+cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs,
+                          const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
+                          H264GpuMbHint *d_hints, cudaStream_t stream);
+
+cudaError_t launch_pack(const H264GpuFrameDesc *d_desc, const uint32_t *d_sizes, int n_frames,
+                        const uint8_t *d_slots, uint8_t *d_packed, unsigned long long *d_offsets,
+                        cudaStream_t stream);
+
+}
+#endif

@@ -1,0 +1,293 @@
+/*
+ * mb_codec.cuh - per-macroblock arithmetic of the P-slice composer, shared by
+ * the sm_100a kernels (compose_kernels.cu) and by the CPU emulation harness in
+ * tests/emu (which compiles this header with g++ to check the bit twiddling
+ * against the oracle without a GPU).  Everything here is a pure function.
+ *
+ * Reference behaviour being reproduced (paths under /root/reference):
+ *   median3 / get_mv_prediction   src/h264_writer.c:362-432
+ *   write_p16x16_mb               src/h264_writer.c:434-453
+ *   bitwriter_write_ue / _se      src/bitwriter.c:50-101
+ *   rbsp_to_ebsp                  src/nal.c:24-50
+ */
+#ifndef H264SCROLL_MB_CODEC_CUH
+#define H264SCROLL_MB_CODEC_CUH
+
+#include <stdint.h>
+#include "composer_gpu.h"
+
+#if defined(__CUDACC__)
+#define HSD __host__ __device__ __forceinline__
+#else
+#define HSD static inline
+#endif
+
+namespace h264scroll {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+/* ---------------------------------------------------------------- bit ops */
+
+HSD int clz32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+
+/* high 32 bits of (hi:lo) << s, 0 <= s <= 31 */
+HSD u32 fshl(u32 hi, u32 lo, int s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+
+HSD u32 bswap32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
+
+/* 1 where a byte of v is zero (exact) */
+HSD u32 zero_byte_mask(u32 v) {
+    return ~((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) | 0x7F7F7F7Fu);
+}
+
+/* ------------------------------------------------------------ Exp-Golomb */
+
+/* ue(v) = (v+1) written in 2*floor(log2(v+1))+1 bits (src/bitwriter.c:50-74) */
+HSD int ue_nbits(u32 v) { return 2 * (31 - clz32(v + 1)) + 1; }
+
+/* se(v) code number: v>0 -> 2v-1, else -2v (src/bitwriter.c:91-101) */
+HSD u32 se_codenum(int v) { return v > 0 ? (u32)(2 * v - 1) : (u32)(-2 * v); }
+
+/* -------------------------------------------------------- MB table entry
+ *
+ * Every macroblock becomes one 16-byte entry plus a bit offset:
+ *   w0            mb_skip_run prefix, left aligned (ue(run), <= 29 bits)
+ *   inline MB :   w1,w2,w3   body bits left aligned (mb_type|ref|mvd|cbp, <= 85 bits);
+ *                 the low 11 bits of w3 are never body bits
+ *   spliced MB:   w1 = payload bit offset, w2 = payload bit length
+ *   w3 low bits   [5:0] prefix length, [6] spliced flag
+ */
+struct alignas(16) MbEntry { u32 w0, w1, w2, w3; };
+
+#define ENT_ULEN_MASK 0x3Fu
+#define ENT_DYN       0x40u
+#define ENT_META_MASK 0x7FFu
+
+/* append the low n (1..33) bits of v to the right-aligned accumulator hi:lo */
+HSD void acc_push(u64 &hi, u64 &lo, u64 v, int n) {
+    hi = (hi << n) | (lo >> (64 - n));
+    lo = (lo << n) | v;
+}
+
+/* neighbour-visible motion of a hint (intra: ref 255, mv 0; src/h264_writer.c:636-640) */
+struct Nbr { int mvx, mvy, ref; };
+
+HSD Nbr nbr_from_hint(u32 lo, u32 hi) {
+    Nbr n;
+    u32 kind = (hi >> 8) & 0xFF;
+    if (kind == H264GPU_MB_DYN_INTRA) { n.mvx = 0; n.mvy = 0; n.ref = 255; }
+    else {
+        n.mvx = (int)(int16_t)(lo & 0xFFFF);
+        n.mvy = (int)(int16_t)(lo >> 16);
+        n.ref = (int)(hi & 0xFF);
+    }
+    return n;
+}
+
+HSD int imin_(int a, int b) { return a < b ? a : b; }
+HSD int imax_(int a, int b) { return a > b ? a : b; }
+
+/*
+ * MV predictor.  avA/avB/avC are availability flags; unavailable neighbours
+ * must be passed with mv 0.  spec = 0 reproduces the reference including
+ * median3 == min(max(a,b),c) and the single-neighbour rule; spec = 1 is
+ * H.264 8.4.1.3.
+ */
+HSD void predict_mv(int spec, Nbr a, int avA, Nbr b, int avB, Nbr c, int avC, int ref,
+                    int &px, int &py) {
+    if (spec && !avB && !avC && avA) { b = a; c = a; avB = 1; avC = 1; }
+    int ma = avA && a.ref == ref, mb = avB && b.ref == ref, mc = avC && c.ref == ref;
+    int nav = avA + avB + avC, nm = ma + mb + mc;
+    if (!spec && nav <= 1) {
+        /* zero or one neighbour: its MV when the ref matches, else 0 (:404-417) */
+        px = ma ? a.mvx : (mb ? b.mvx : (mc ? c.mvx : 0));
+        py = ma ? a.mvy : (mb ? b.mvy : (mc ? c.mvy : 0));
+        return;
+    }
+    if (nm == 1) {
+        px = ma ? a.mvx : (mb ? b.mvx : c.mvx);
+        py = ma ? a.mvy : (mb ? b.mvy : c.mvy);
+        return;
+    }
+    int hx = imin_(imax_(a.mvx, b.mvx), c.mvx), hy = imin_(imax_(a.mvy, b.mvy), c.mvy);
+    if (spec) {
+        hx = imax_(imin_(a.mvx, b.mvx), hx);
+        hy = imax_(imin_(a.mvy, b.mvy), hy);
+    }
+    px = hx; py = hy;
+}
+
+/* H.264 8.4.1.1: inferred P_Skip MV */
+HSD void skip_infer_mv(int spec, Nbr a, int avA, Nbr b, int avB, Nbr c, int avC, int &sx, int &sy) {
+    if (!avA || !avB || (a.ref == 0 && a.mvx == 0 && a.mvy == 0) ||
+        (b.ref == 0 && b.mvx == 0 && b.mvy == 0)) { sx = 0; sy = 0; return; }
+    predict_mv(spec, a, avA, b, avB, c, avC, 0, sx, sy);
+}
+
+/*
+ * Body of a P_L0_16x16 macroblock: '1' | te(ref) | se(mvdx) | se(mvdy) | '1'
+ * (src/h264_writer.c:434-453).  Returns the bit count; body bits left aligned in
+ * e.w1..w3 (low 11 bits of w3 cleared).
+ */
+HSD int encode_p16x16_body(int ref, int mvdx, int mvdy, int num_refs, MbEntry &e) {
+    u64 hi = 0, lo = 1;          /* mb_type ue(0) */
+    int len = 1;
+    if (num_refs == 2) { acc_push(hi, lo, (u64)(1 - (ref & 1)), 1); len += 1; }
+    else if (num_refs > 2) { int n = ue_nbits((u32)ref); acc_push(hi, lo, (u64)ref + 1, n); len += n; }
+    u32 kx = se_codenum(mvdx), ky = se_codenum(mvdy);
+    int nx = ue_nbits(kx), ny = ue_nbits(ky);
+    acc_push(hi, lo, (u64)kx + 1, nx);
+    acc_push(hi, lo, (u64)ky + 1, ny);
+    acc_push(hi, lo, 1, 1);      /* coded_block_pattern ue(0) */
+    len += nx + ny + 1;
+    /* left-align the len-bit value in 96 bits */
+    int sh = 96 - len;           /* 11 .. 93 */
+    u64 h2, l2;
+    if (sh >= 64) { h2 = lo << (sh - 64); l2 = 0; }
+    else { h2 = (hi << sh) | (lo >> (64 - sh)); l2 = lo << sh; }
+    /* value now occupies bits [95:0] of h2:l2 with h2 holding bits [95:64] in its low half */
+    e.w1 = (u32)h2;
+    e.w2 = (u32)(l2 >> 32);
+    e.w3 = (u32)l2 & ~ENT_META_MASK;
+    return len;
+}
+
+/* mb_skip_run prefix: ue(run) left aligned in a word + its length */
+HSD void encode_skip_prefix(u32 run, u32 &bits, int &n) {
+    n = ue_nbits(run);
+    bits = (run + 1) << (32 - n);
+}
+
+/* ------------------------------------------------------- payload access */
+
+/* 32 payload bits starting at bit position p (MSB first), words are read big-endian */
+HSD u32 payload_bits32(const u32 *payload_words, u32 n_words, u32 p) {
+    u32 wi = p >> 5;
+    u32 a = wi < n_words ? bswap32(payload_words[wi]) : 0u;
+    u32 b = wi + 1 < n_words ? bswap32(payload_words[wi + 1]) : 0u;
+    return fshl(a, b, (int)(p & 31));
+}
+
+/*
+ * Bits that MB entry `e`, whose first bit sits at frame bit `o`, contributes to
+ * the 32-bit output word starting at frame bit `base`.
+ */
+HSD u32 entry_contrib(const MbEntry &e, u32 o, u32 base, const u32 *payload_words, u32 n_payload_words) {
+    int q = (int)(base - o);             /* position of the word inside the MB string */
+    int ulen = (int)(e.w3 & ENT_ULEN_MASK);
+    u32 acc = 0;
+    if (q < 0) { if (q > -32) acc = e.w0 >> (-q); }
+    else if (q < 32) acc = e.w0 << q;
+    int q2 = q - ulen;                   /* position inside the body */
+    if (!(e.w3 & ENT_DYN)) {
+        u32 b0 = e.w1, b1 = e.w2, b2 = e.w3 & ~ENT_META_MASK;
+        if (q2 < 0) { if (q2 > -32) acc |= b0 >> (-q2); }
+        else if (q2 < 96) {
+            int ws = q2 >> 5, sh = q2 & 31;
+            u32 x = ws == 0 ? b0 : (ws == 1 ? b1 : b2);
+            u32 y = ws == 0 ? b1 : (ws == 1 ? b2 : 0u);
+            acc |= fshl(x, y, sh);
+        }
+    } else {
+        u32 pb = e.w1, L = e.w2;
+        if (q2 < 0) {
+            if (q2 > -32 && L) {
+                u32 v = payload_bits32(payload_words, n_payload_words, pb);
+                if (L < 32) v &= ~(0xFFFFFFFFu >> L);
+                acc |= v >> (-q2);
+            }
+        } else if ((u32)q2 < L) {
+            u32 v = payload_bits32(payload_words, n_payload_words, pb + (u32)q2);
+            u32 rem = L - (u32)q2;
+            if (rem < 32) v &= ~(0xFFFFFFFFu >> rem);
+            acc |= v;
+        }
+    }
+    return acc;
+}
+
+/* --------------------------------------------------------------- header */
+
+/* 32 bits at stream bit position p of: 00 00 00 01 | nal_header | slice header bits */
+HSD u32 header_bits32(const u64 hdr[4], u32 nal_header, u32 p) {
+    /* string = 40-bit prefix followed by 256 header bits */
+    u32 acc = 0;
+    /* prefix words: bits 0..31 = 0x00000001, bits 32..39 = nal_header */
+    if (p < 32) acc |= 0x00000001u << p;                /* p == 0 keeps the word, else shifts the 1 out */
+    if (p < 40) {
+        int d = (int)p - 32;                            /* where the header byte starts relative to p */
+        u32 nh = nal_header << 24;
+        if (d >= 0) acc |= nh << d;
+        else if (d > -32) acc |= nh >> (-d);
+    }
+    /* slice header bits start at stream bit 40 */
+    int q = (int)p - 40;
+    for (int k = 0; k < 4; k++) {
+        /* hdr[k] covers header bits [64k, 64k+64) */
+        int rel = q - 64 * k;                           /* offset of p inside hdr[k] */
+        if (rel <= -32 || rel >= 64) continue;
+        u64 w = hdr[k];
+        u32 piece;
+        if (rel < 0) piece = (u32)(w >> 32) >> (-rel);
+        else if (rel <= 32) piece = (u32)(w >> (32 - rel));
+        else piece = (u32)(w << (rel - 32));
+        acc |= piece;
+    }
+    return acc;
+}
+
+/* --------------------------------------------------- emulation prevention
+ *
+ * rbsp_to_ebsp (src/nal.c:24-50) in closed form: with r = number of zero bytes
+ * immediately before RBSP byte p (continuing the automaton state zc_in carried
+ * into this chunk), 0x03 is inserted before p iff byte(p) <= 3, r >= 2, r even.
+ *
+ * words[] holds the chunk MSB-first (stream byte 4*j+k is bits [31-8k:24-8k] of
+ * words[j]); chunk_byte0 is the stream byte index of words[0]; stream bytes
+ * below 5 are the start code and NAL header and never take part.
+ */
+HSD u32 chunk_byte(const u32 *words, int b) { return (words[b >> 2] >> (24 - 8 * (b & 3))) & 0xFFu; }
+
+HSD u32 epb_insert_mask(const u32 *words, int j, u32 chunk_byte0, int zc_in, int valid_bytes) {
+    u32 mask = 0;
+    for (int k = 0; k < valid_bytes; k++) {
+        int b = 4 * j + k;
+        if (chunk_byte0 + (u32)b < 5) continue;
+        if (chunk_byte(words, b) > 3) continue;
+        int r = 0, c = b - 1;
+        while (c >= 0 && chunk_byte0 + (u32)c >= 5 && chunk_byte(words, c) == 0) { r++; c--; }
+        if (c < 0) r += zc_in;
+        if (r >= 2 && !(r & 1)) mask |= 1u << k;
+    }
+    return mask;
+}
+
+/* automaton state after a chunk whose emitted bytes are words[0 .. nbytes) */
+HSD int epb_state_after(const u32 *words, int nbytes, u32 chunk_byte0, int zc_in) {
+    int r = 0, c = nbytes - 1;
+    while (c >= 0 && chunk_byte0 + (u32)c >= 5 && chunk_byte(words, c) == 0) { r++; c--; }
+    if (c < 0) r += zc_in;
+    return r == 0 ? 0 : ((r & 1) ? 1 : 2);
+}
+
+} /* namespace h264scroll */
+#endif

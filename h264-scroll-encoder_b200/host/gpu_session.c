@@ -1,0 +1,172 @@
+/*
+ * gpu_session.c - drives the GPU path for the reference-shaped host API.
+ *
+ * A legacy scroll frame is at most two horizontal bands of constant motion
+ * (src/h264_writer.c:598-617), so the host ships 2 x 16-byte regions, a 64-byte
+ * frame descriptor and a 24-byte raster descriptor per frame; the dense hint
+ * map, the slice data and the packed Annex-B stream are produced on the device:
+ *
+ *     H2D(descs) -> raster_regions -> compose_batch -> pack_frames -> D2H(stream)
+ *
+ * Device and pinned buffers are cached and grown on demand.  Not thread safe
+ * per process by itself; callers serialise through the mutex below.
+ */
+#include "gpu_session.h"
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static struct {
+    int ready;
+    uint8_t *dev;  size_t dev_cap;
+    uint8_t *pin;  size_t pin_cap;
+} S;
+
+static size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int session_init(void) {
+    if (S.ready) return 0;
+    const char *env = getenv("H264GPU_DEVICE");
+    int dev = env ? atoi(env) : 0;
+    int rc = h264gpu_init(dev);
+    if (rc != H264GPU_OK) {
+        fprintf(stderr, "Error: GPU composer unavailable (%s); there is no CPU fallback\n",
+                h264gpu_last_error());
+        return rc;
+    }
+    S.ready = 1;
+    return 0;
+}
+
+static int ensure(size_t dev_bytes, size_t pin_bytes) {
+    if (dev_bytes > S.dev_cap) {
+        h264gpu_free(S.dev);
+        S.dev = h264gpu_malloc(dev_bytes);
+        S.dev_cap = S.dev ? dev_bytes : 0;
+        if (!S.dev) return H264GPU_ERR_NOMEM;
+    }
+    if (pin_bytes > S.pin_cap) {
+        h264gpu_host_free(S.pin);
+        S.pin = h264gpu_host_alloc(pin_bytes);
+        S.pin_cap = S.pin ? pin_bytes : 0;
+        if (!S.pin) return H264GPU_ERR_NOMEM;
+    }
+    return 0;
+}
+
+/* slot bound for a legacy frame: <= 46 bits per MB plus header, 3/2 for worst-case emulation prevention */
+static uint32_t legacy_slot_cap(int n_mbs) { return (uint32_t)up(128 + (size_t)n_mbs * 9, 16); }
+
+static int compose_chunk(const LegacyFrame *fr, int n, int mb_w, int mb_h,
+                         uint8_t *dst, size_t cap, uint32_t *sizes, size_t *written) {
+    const size_t n_mbs = (size_t)mb_w * mb_h;
+    const size_t hint_stride = up(n_mbs, 2);
+    const uint32_t slot = legacy_slot_cap((int)n_mbs);
+
+    /* pinned staging: descs | rdescs | regions  ...  sizes | offsets */
+    size_t p_desc = 0, p_rd = up(p_desc + sizeof(H264GpuFrameDesc) * n, 64);
+    size_t p_reg = up(p_rd + sizeof(H264GpuRasterDesc) * n, 64);
+    size_t p_up_end = up(p_reg + sizeof(H264GpuRegion) * 2 * n, 64);
+    size_t p_sizes = p_up_end, p_offs = up(p_sizes + 4 * (size_t)n, 64);
+    size_t p_end = p_offs + 8 * ((size_t)n + 1);
+
+    size_t d_up = 0, d_hints = up(p_up_end, 256);
+    size_t d_sizes = up(d_hints + 8 * hint_stride * n, 256);
+    size_t d_offs = up(d_sizes + 4 * (size_t)n, 256);
+    size_t d_slots = up(d_offs + 8 * ((size_t)n + 1), 256);
+    size_t d_packed = up(d_slots + (size_t)slot * n, 256);
+    size_t d_end = d_packed + (size_t)slot * n;
+
+    int rc = ensure(d_end, p_end);
+    if (rc) return rc;
+
+    H264GpuFrameDesc *desc = (H264GpuFrameDesc *)(S.pin + p_desc);
+    H264GpuRasterDesc *rd = (H264GpuRasterDesc *)(S.pin + p_rd);
+    H264GpuRegion *reg = (H264GpuRegion *)(S.pin + p_reg);
+    for (int f = 0; f < n; f++) {
+        const LegacyFrame *L = &fr[f];
+        memset(&desc[f], 0, sizeof desc[f]);
+        memcpy(desc[f].hdr_bits, L->hdr, sizeof L->hdr);
+        desc[f].hint_off = hint_stride * f;
+        desc[f].out_off = (uint64_t)slot * f;
+        desc[f].out_cap = slot;
+        desc[f].dyn_id = H264GPU_NO_DYN;
+        desc[f].mb_w = (uint16_t)mb_w;
+        desc[f].mb_h = (uint16_t)mb_h;
+        desc[f].hdr_nbits = (uint8_t)L->hdr_nbits;
+        desc[f].num_refs = (uint8_t)L->num_refs;
+        desc[f].flags = H264GPU_SKIP_OFF | H264GPU_PRED_REF;      /* bit-exact reference behaviour */
+        desc[f].nal_header = (uint8_t)L->nal_header;
+        rd[f].region_first = 2u * f;
+        rd[f].region_count = 2;
+        rd[f].hint_off = hint_stride * f;
+        rd[f].mb_w = (uint16_t)mb_w;
+        rd[f].mb_h = (uint16_t)mb_h;
+        rd[f].dyn_info_off = 0;
+        int split = L->split_row < 0 ? 0 : (L->split_row > mb_h ? mb_h : L->split_row);
+        H264GpuRegion *r = &reg[2 * f];
+        memset(r, 0, 2 * sizeof *r);
+        r[0].mb_x0 = 0; r[0].mb_y0 = 0; r[0].mb_x1 = (int16_t)mb_w; r[0].mb_y1 = (int16_t)split;
+        r[0].mv_y_qpel = (int16_t)L->mv_top_qpel; r[0].ref_idx = (uint8_t)L->ref_top;
+        r[1].mb_x0 = 0; r[1].mb_y0 = (int16_t)split; r[1].mb_x1 = (int16_t)mb_w; r[1].mb_y1 = (int16_t)mb_h;
+        r[1].mv_y_qpel = (int16_t)L->mv_bot_qpel; r[1].ref_idx = (uint8_t)L->ref_bot;
+    }
+
+    uint8_t *D = S.dev;
+    rc = h264gpu_memcpy_h2d(D + d_up, S.pin, p_up_end, NULL);
+    if (!rc) rc = h264gpu_raster_regions((const H264GpuRasterDesc *)(D + p_rd), n, (int)n_mbs,
+                                         (const H264GpuRegion *)(D + p_reg), NULL,
+                                         (H264GpuMbHint *)(D + d_hints), NULL);
+    if (!rc) rc = h264gpu_compose_batch((const H264GpuFrameDesc *)(D + p_desc), n,
+                                        (const H264GpuMbHint *)(D + d_hints), NULL, NULL, NULL,
+                                        D + d_slots, (uint32_t *)(D + d_sizes), NULL);
+    if (!rc) rc = h264gpu_pack_frames((const H264GpuFrameDesc *)(D + p_desc), (const uint32_t *)(D + d_sizes), n,
+                                      D + d_slots, D + d_packed, (uint64_t *)(D + d_offs), NULL);
+    if (!rc) rc = h264gpu_memcpy_d2h(S.pin + p_sizes, D + d_sizes, 4 * (size_t)n, NULL);
+    if (!rc) rc = h264gpu_memcpy_d2h(S.pin + p_offs, D + d_offs, 8 * ((size_t)n + 1), NULL);
+    if (!rc) rc = h264gpu_stream_sync(NULL);
+    if (rc) return rc;
+
+    const uint32_t *hs = (const uint32_t *)(S.pin + p_sizes);
+    const uint64_t *ho = (const uint64_t *)(S.pin + p_offs);
+    for (int f = 0; f < n; f++) {
+        if (hs[f] > slot) return H264GPU_ERR_OVERFLOW;
+        sizes[f] = hs[f];
+    }
+    size_t total = (size_t)ho[n];
+    if (total > cap) return H264GPU_ERR_OVERFLOW;
+    rc = h264gpu_memcpy_d2h(dst, D + d_packed, total, NULL);
+    if (!rc) rc = h264gpu_stream_sync(NULL);
+    if (rc) return rc;
+    *written = total;
+    return 0;
+}
+
+int gpu_session_compose_legacy(const LegacyFrame *frames, int n, int mb_w, int mb_h,
+                               uint8_t *dst, size_t cap, uint32_t *sizes, size_t *total) {
+    if (n <= 0) { *total = 0; return 0; }
+    if (mb_w <= 0 || mb_h <= 0 || mb_w > H264GPU_MAX_MB_W) return H264GPU_ERR_ARG;
+    pthread_mutex_lock(&g_lock);
+    int rc = session_init();
+    size_t done_bytes = 0;
+    if (!rc) {
+        /* bound device scratch to ~1 GiB per launch */
+        size_t per_frame = (size_t)mb_w * mb_h * 8 + 2 * (size_t)legacy_slot_cap(mb_w * mb_h) + 256;
+        int chunk = (int)((1ull << 30) / per_frame);
+        if (chunk < 1) chunk = 1;
+        for (int f0 = 0; f0 < n && !rc; f0 += chunk) {
+            int m = n - f0 < chunk ? n - f0 : chunk;
+            size_t w = 0;
+            rc = compose_chunk(frames + f0, m, mb_w, mb_h, dst + done_bytes, cap - done_bytes, sizes + f0, &w);
+            done_bytes += w;
+        }
+    }
+    pthread_mutex_unlock(&g_lock);
+    if (rc && rc != H264GPU_ERR_NO_DEVICE)
+        fprintf(stderr, "Error: GPU compose failed (%d: %s)\n", rc, h264gpu_last_error());
+    *total = done_bytes;
+    return rc;
+}

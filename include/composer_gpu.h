@@ -1,0 +1,195 @@
+/*
+ * composer_gpu.h - C ABI of the B200 (sm_100a) P-slice composition path.
+ *
+ * This is the drop-in boundary for the reference's per-frame hot path:
+ *
+ *   reference                                             replaced by
+ *   ---------------------------------------------------   -------------------------------
+ *   h264_write_scroll_p_frame   src/h264_writer.c:541     h264gpu_compose_batch (dense hints)
+ *   h264_write_waypoint_p_frame src/h264_writer.c:678     h264gpu_compose_batch (nal_header 0x41)
+ *   get_mv_prediction/median3   src/h264_writer.c:362-432 kernel stage "predict"
+ *   write_p16x16_mb             src/h264_writer.c:434     kernel stage "code"
+ *   bitwriter_write_{ue,se,bit} src/bitwriter.c:13-101    closed-form (code,len) + scan + pack
+ *   bitwriter_write_trailing_bits/_get_size  :103-131     kernel stage "finish"
+ *   rbsp_to_ebsp/nal_write_unit src/nal.c:24-84           kernel stage "epb" (detect+scan+compact)
+ *   per-MB region -> (ref,mv)   src/h264_writer.c:598-620 h264gpu_raster_regions (device rasteriser)
+ *
+ * The slice header, frame_num and the waypoint / long-term-reference
+ * bookkeeping stay on the host (include/h264_writer.h); the host hands the
+ * kernel the already-written slice-header bits.
+ *
+ * Plain C: pointers, sizes and PODs only.  No CPU fallback exists: every
+ * entry point returns H264GPU_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef COMPOSER_GPU_H
+#define COMPOSER_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (negative = failure) -------------------------------- */
+#define H264GPU_OK               0
+#define H264GPU_ERR_NO_DEVICE   -1   /* no CUDA device / wrong architecture  */
+#define H264GPU_ERR_CUDA        -2   /* a CUDA call failed (see last_error)  */
+#define H264GPU_ERR_ARG         -3   /* invalid argument                     */
+#define H264GPU_ERR_OVERFLOW    -4   /* a frame did not fit its output slot  */
+#define H264GPU_ERR_NOMEM       -5
+
+/* ---- per-macroblock hint (8 bytes, raster order, dense) -------------- */
+#define H264GPU_MB_INTER      0   /* P_L0_16x16 / P_Skip candidate with this MV      */
+#define H264GPU_MB_DYN_INTER  1   /* spliced pre-encoded MB, neighbours see (ref,mv) */
+#define H264GPU_MB_DYN_INTRA  2   /* spliced pre-encoded intra MB (ref -1, mv 0)     */
+
+typedef struct {
+    int16_t  mv_x_qpel;     /* quarter-pel, as coded (src/h264_writer.c:619-620) */
+    int16_t  mv_y_qpel;
+    uint8_t  ref_idx;       /* index into RefPicList0                           */
+    uint8_t  kind;          /* H264GPU_MB_*                                     */
+    uint16_t dyn_idx;       /* kind != INTER: index into the frame's dyn table  */
+} H264GpuMbHint;
+
+/* ---- frame flags ------------------------------------------------------ */
+#define H264GPU_SKIP_OFF    0x00  /* reference behaviour: mb_skip_run always 0 (src/h264_writer.c:629-631) */
+#define H264GPU_SKIP_SPEC   0x01  /* emit P_Skip where H.264 8.4.1.1 infers the hinted MV */
+#define H264GPU_PRED_REF    0x00  /* reference predictor incl. its median3 / single-neighbour quirks */
+#define H264GPU_PRED_SPEC   0x02  /* H.264 8.4.1.3 predictor                    */
+
+#define H264GPU_NO_DYN      0xFFFFFFFFu
+#define H264GPU_MAX_HDR_BITS 255
+
+/* ---- frame descriptor (64 bytes) ------------------------------------- */
+typedef struct {
+    uint64_t hdr_bits[4];   /* slice-header bits, MSB first: stream bit k is
+                               bit (63 - k%64) of hdr_bits[k/64]            */
+    uint64_t hint_off;      /* index of the frame's first hint (even)       */
+    uint64_t out_off;       /* byte offset of the output slot (16-aligned)  */
+    uint32_t out_cap;       /* slot capacity in bytes (multiple of 16)      */
+    uint32_t dyn_id;        /* index into the dyn descriptor array or NO_DYN */
+    uint16_t mb_w, mb_h;
+    uint8_t  hdr_nbits;     /* <= H264GPU_MAX_HDR_BITS                      */
+    uint8_t  num_refs;      /* active refs: selects the ref_idx te() coding */
+    uint8_t  flags;         /* H264GPU_SKIP_* | H264GPU_PRED_*              */
+    uint8_t  nal_header;    /* (nal_ref_idc<<5)|nal_unit_type, src/nal.c:74 */
+} H264GpuFrameDesc;
+
+/* ---- dynamic-region (splice) descriptor (32 bytes) -------------------- */
+typedef struct {
+    uint64_t payload_off;   /* byte offset into the payload buffer (4-aligned)   */
+    uint64_t table_off;     /* index into the bit-offset table: n_mbs+1 entries, */
+                            /* MB j owns payload bits [t[j], t[j+1])             */
+    uint32_t n_mbs;
+    uint32_t payload_bytes; /* bytes readable from payload_off (padded to 4)     */
+    uint64_t reserved;
+} H264GpuDynDesc;
+
+/* ---- region list (device rasteriser input), later regions occlude ---- */
+typedef struct {
+    int16_t  mb_x0, mb_y0, mb_x1, mb_y1;   /* half-open MB rectangle          */
+    int16_t  mv_x_qpel, mv_y_qpel;
+    uint8_t  ref_idx, kind; /* H264GPU_MB_INTER or H264GPU_REGION_DYN          */
+    uint16_t dyn_base;      /* REGION_DYN: dyn-info index of the rect's first MB */
+} H264GpuRegion;            /* 16 bytes */
+
+#define H264GPU_REGION_DYN 3  /* region.kind: copy per-MB hints from the dyn-info table
+                                 (entry = dyn_info_off + dyn_base + row-major index) */
+
+typedef struct {
+    uint32_t region_first;  /* index of the frame's first region              */
+    uint32_t region_count;  /* <= H264GPU_MAX_REGIONS                          */
+    uint64_t hint_off;      /* where to write the dense map (MB index)        */
+    uint16_t mb_w, mb_h;
+    uint32_t dyn_info_off;  /* frame's base index into the dyn-info table     */
+} H264GpuRasterDesc;        /* 24 bytes */
+
+#define H264GPU_MAX_REGIONS 512
+#define H264GPU_MAX_MB_W    1023   /* widest frame the composer stages (16368 px) */
+
+/* ---- device lifecycle -------------------------------------------------- */
+int         h264gpu_init(int device);          /* idempotent per device    */
+void        h264gpu_shutdown(void);
+int         h264gpu_device_count(void);
+const char *h264gpu_last_error(void);
+int         h264gpu_sm_count(void);
+
+/* ---- raw memory / stream plumbing (so callers need no CUDA headers) --- */
+void *h264gpu_malloc(size_t bytes);            /* device memory            */
+void  h264gpu_free(void *dptr);
+void *h264gpu_host_alloc(size_t bytes);        /* pinned host memory       */
+void  h264gpu_host_free(void *hptr);
+int   h264gpu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int   h264gpu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int   h264gpu_memset(void *dst, int value, size_t bytes, void *stream);
+void *h264gpu_stream_create(void);
+void  h264gpu_stream_destroy(void *stream);
+int   h264gpu_stream_sync(void *stream);       /* NULL = default stream    */
+void *h264gpu_event_create(void);
+void  h264gpu_event_destroy(void *ev);
+int   h264gpu_event_record(void *ev, void *stream);
+float h264gpu_event_elapsed_ms(void *ev_start, void *ev_stop); /* syncs on stop */
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/*
+ * Compose n_frames P-slices.  All pointers are DEVICE pointers.
+ *   d_desc      n_frames frame descriptors
+ *   d_hints     dense hint maps, indexed by desc.hint_off
+ *   d_dyn       dyn descriptors (may be NULL when no frame splices)
+ *   d_dyn_tab   bit-offset tables, d_payload the pre-encoded bits
+ *   d_out       output arena; frame f writes Annex-B bytes at out_off
+ *   d_sizes     per frame: bytes of "00 00 00 01 | header | EBSP" that the
+ *               frame needs; when it exceeds out_cap only out_cap bytes were
+ *               stored and the caller must treat the frame as overflowed
+ *               (the reference asserts instead, src/nal.c:34,59)
+ * Asynchronous on `stream`; returns a launch status only.
+ */
+int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
+                          const H264GpuMbHint *d_hints,
+                          const H264GpuDynDesc *d_dyn,
+                          const uint32_t *d_dyn_tab,
+                          const uint8_t *d_payload,
+                          uint8_t *d_out, uint32_t *d_sizes,
+                          void *stream);
+
+/*
+ * Expand region lists into dense hint maps on the device
+ * (replaces the per-MB region test of src/h264_writer.c:598-620).
+ */
+int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs_per_frame,
+                           const H264GpuRegion *d_regions,
+                           const H264GpuMbHint *d_dyn_info,   /* may be NULL without DYN regions */
+                           H264GpuMbHint *d_hints, void *stream);
+
+/*
+ * Exact output packing: gathers the frames' slots into one contiguous Annex-B
+ * stream in frame order (the append order of src/nal.c:55-83, src/composer.c:255-264).
+ * d_offsets receives n_frames+1 byte offsets, d_offsets[n_frames] = stream size.
+ * A frame that overflowed its slot contributes out_cap bytes.
+ */
+int h264gpu_pack_frames(const H264GpuFrameDesc *d_desc, const uint32_t *d_sizes, int n_frames,
+                        const uint8_t *d_slots, uint8_t *d_packed, uint64_t *d_offsets,
+                        void *stream);
+
+/*
+ * Host-buffer convenience: copies descriptors/hints/dyn data up, composes,
+ * copies the slots and sizes back, synchronises.  Frames are returned in
+ * their slots (h_out + out_off).  Returns H264GPU_ERR_OVERFLOW if any frame
+ * exceeded its slot.  Scratch device memory is cached between calls.
+ */
+int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
+                         const H264GpuMbHint *h_hints, size_t n_hints,
+                         const H264GpuDynDesc *h_dyn, int n_dyn,
+                         const uint32_t *h_dyn_tab, size_t n_tab,
+                         const uint8_t *h_payload, size_t payload_bytes,
+                         uint8_t *h_out, size_t out_bytes, uint32_t *h_sizes);
+
+/* Count of kernels this library has launched since init (for bench accounting). */
+uint64_t h264gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMPOSER_GPU_H */
