@@ -1,0 +1,117 @@
+"""
+GPU parity tests proper: the CUDA path, called through the C ABI (include/composer_gpu.h), against the
+oracle on the same seeded inputs.  Bit-exact: these are integer/byte computations.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from h264_scroll_encoder_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(gpu, po, chk, b, hints=None):
+    hints = helpers.dense_hints(po, b) if hints is None else hints
+    frames, sizes = gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload)
+    for f in range(b.n_frames):
+        want = helpers.checker_frame(chk, b, hints, f)
+        got = frames[f]
+        if not np.array_equal(got, want):
+            m = min(len(got), len(want))
+            k = int(np.argmax(got[:m] != want[:m])) if m and (got[:m] != want[:m]).any() else m
+            raise AssertionError("%s frame %d: GPU %d bytes vs oracle %d bytes, first difference at byte %d"
+                                 % (b.name, f, len(got), len(want), k))
+
+
+@pytest.mark.parametrize("flags", [0, abi.SKIP_SPEC, abi.PRED_SPEC, abi.SKIP_SPEC | abi.PRED_SPEC])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_frames(gpu, po, oracle, seed, flags):
+    nr = [1, 2, 3, 5, 10, 2][seed]
+    b = workloads.make_random(5 + 9 * seed, 4 + 5 * seed, 3, seed=seed, num_refs=nr, flags=flags)
+    _compare(gpu, po, oracle, b)
+
+
+@pytest.mark.parametrize("flags", [0, abi.SKIP_SPEC | abi.PRED_SPEC])
+def test_random_multi_tile_frames(gpu, po, oracle, flags):
+    # > 1024 MBs per frame: tile boundaries, halo rows, carried partial words and EPB state
+    b = workloads.make_random(120, 68, 3, seed=41, num_refs=3, flags=flags, n_regions=40)
+    _compare(gpu, po, oracle, b)
+    b = workloads.make_random(240, 135, 2, seed=42, num_refs=2, flags=flags, n_regions=60)
+    _compare(gpu, po, oracle, b)
+
+
+def test_against_reference_functions(gpu, po, ref):
+    # the reference's own median3/get_mv_prediction/write_p16x16_mb/copy_bits behind the hinted loop
+    for flags in (0, abi.SKIP_SPEC):
+        b = workloads.make_random(80, 45, 3, seed=77, num_refs=3, flags=flags, n_regions=30)
+        _compare(gpu, po, ref, b)
+
+
+def test_edge_shapes(gpu, po, oracle):
+    for (w, h) in ((1, 1), (1, 7), (7, 1), (2, 2), (33, 31), (1023, 2)):
+        for flags in (0, 3):
+            b = workloads.make_random(w, h, 2, seed=w * 100 + h, num_refs=2, flags=flags, n_regions=6)
+            _compare(gpu, po, oracle, b)
+
+
+def test_all_skipped_frame(gpu, po, oracle):
+    # static frame: every MB is P_Skip in SPEC mode; the slice is header + one trailing mb_skip_run
+    b = workloads.Batch(120, 68)
+    regs = [workloads.region(0, 0, 120, 68)]
+    b = workloads._finish(b, [workloads.p_header_bits(2)], regs, 2, abi.SKIP_SPEC | abi.PRED_SPEC, 4096)
+    _compare(gpu, po, oracle, b)
+
+
+def test_zero_heavy_payload_epb(gpu, po, oracle):
+    b = workloads.make_random(60, 40, 4, seed=5, num_refs=2, flags=0, p_dyn=0.5, zero_payload_pct=60)
+    _compare(gpu, po, oracle, b)
+
+
+def test_config_generators(gpu, po, oracle):
+    _compare(gpu, po, oracle, workloads.make_config2(6))
+    _compare(gpu, po, oracle, workloads.make_config5(2, 3))
+    _compare(gpu, po, oracle, workloads.make_config4(2))
+
+
+def test_device_rasteriser_matches_checker(gpu, po):
+    b = workloads.make_random(97, 53, 5, seed=9, num_refs=4, n_regions=50)
+    want = helpers.dense_hints(po, b)
+    d_rd, d_reg = gpu.to_device(b.rdesc), gpu.to_device(b.regions)
+    d_info = gpu.to_device(b.dyn_info) if len(b.dyn_info) else None
+    d_h = gpu.alloc(want.nbytes)
+    gpu.lib.h264gpu_memset(d_h.ptr, 0, want.nbytes, None)
+    gpu.raster_regions(d_rd, b.n_frames, b.n_mbs, d_reg, d_info, d_h)
+    got = d_h.download(abi.HINT)
+    for f in range(b.n_frames):
+        s = slice(f * b.hint_stride, f * b.hint_stride + b.n_mbs)
+        assert np.array_equal(got[s], want[s]), "rasteriser differs in frame %d" % f
+
+
+def test_pack_frames_is_append_order(gpu, po, oracle):
+    b = workloads.make_random(50, 30, 9, seed=3, num_refs=2, n_regions=20)
+    hints = helpers.dense_hints(po, b)
+    d_desc, d_h = gpu.to_device(b.desc), gpu.to_device(hints)
+    d_dyn, d_tab, d_pay = gpu.to_device(b.dyn), gpu.to_device(b.dyn_tab), gpu.to_device(
+        np.concatenate([b.payload, np.zeros(8, np.uint8)]))
+    d_out = gpu.alloc(b.slot_cap * b.n_frames)
+    d_packed = gpu.alloc(b.slot_cap * b.n_frames)
+    d_sizes, d_offs = gpu.alloc(4 * b.n_frames), gpu.alloc(8 * (b.n_frames + 1))
+    gpu.compose_batch(d_desc, b.n_frames, d_h, d_dyn, d_tab, d_pay, d_out, d_sizes)
+    gpu.pack_frames(d_desc, d_sizes, b.n_frames, d_out, d_packed, d_offs)
+    offs = d_offs.download(np.uint64)
+    want = np.concatenate([helpers.checker_frame(oracle, b, hints, f) for f in range(b.n_frames)])
+    assert int(offs[-1]) == len(want)
+    got = d_packed.download(np.uint8, count=len(want))
+    assert np.array_equal(got, want)
+
+
+def test_overflowing_slot_is_reported(gpu, po, oracle):
+    from h264_scroll_encoder_b200.binding import GpuError
+    b = workloads.make_random(40, 30, 1, seed=1, num_refs=2, n_regions=10)
+    hints = helpers.dense_hints(po, b)
+    want = helpers.checker_frame(oracle, b, hints, 0)
+    b.desc["out_cap"] = 64
+    with pytest.raises(GpuError):
+        gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload, out_bytes=4096)
+    assert len(want) > 64
