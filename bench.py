@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""
+bench.py - composed macroblocks/second of bit-exact P-frames (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a, through the C ABI)
+  python bench.py --impl reference ...                     the reference's own CPU code on the host cores
+
+Workload (config.workload): BASELINE.json configs[4] "batched 1024 independent 1080p UI streams sharded
+across 8xB200": every GPU takes 128 streams x 64 frames of the config-3 layout (static chrome, three
+carousels, a two-reference vertical grid, a 25x25-MB spliced dynamic region), so the
+8-GPU run is exactly the 1024-stream batch and per-GPU work is fixed (weak scaling, no collective).
+
+A step = one pass of the hot path over the rank's whole batch.
+  value   MB/s with all inputs resident in HBM (dense hint maps, payload, descriptors): the compose kernel
+  e2e     MB/s through the host-buffer path: pinned host region lists + payload -> H2D -> rasterise ->
+          compose -> pack -> D2H of the packed Annex-B stream, every step
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "composed_macroblocks_per_second_bit_exact_p_frames"
+UNIT = "MB/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# --------------------------------------------------------------------------------------- reference arm
+
+def cpu_sample(po, streams=2, frames=8):
+    """Bounded sample of the same workload as dense hints for the CPU code."""
+    from h264_scroll_encoder_b200 import workloads, abi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    b = workloads.make_config5(streams, frames)
+    hints = np.zeros((b.n_frames, b.n_mbs), abi.HINT)
+    for f in range(b.n_frames):
+        r0, rc = int(b.rdesc["region_first"][f]), int(b.rdesc["region_count"][f])
+        hints[f] = po.raster_regions_numpy(b.regions[r0:r0 + rc], b.mb_w, b.mb_h, b.dyn_info[int(b.rdesc["dyn_info_off"][f]):])
+    # per-frame tables re-based on one shared payload buffer
+    tab = np.zeros((b.n_frames, 626), np.uint32)
+    for f in range(b.n_frames):
+        t0 = int(b.dyn["table_off"][f])
+        tab[f] = b.dyn_tab[t0:t0 + 626] + np.uint32(8 * int(b.dyn["payload_off"][f]))
+    return b, np.ascontiguousarray(hints), np.ascontiguousarray(tab), b.payload
+
+
+def run_cpu(po, threads, target_seconds, kind=None):
+    """Time the reference's CPU path (oracle/_ref when present, else the oracle port) on `threads` threads."""
+    use_ref = po.have_ref() if kind is None else (kind == "reference")
+    chk = po.Ref() if use_ref else po.Oracle()
+    b, hints, tab, payload = cpu_sample(po)
+    hdr = b.desc["hdr_bits"][0].copy()
+    nb = int(b.desc["hdr_nbits"][0])
+    # calibrate reps on one thread
+    t1, _ = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, 2, 0, hdr, nb, payload, tab, 626, 1)
+    reps = max(1, int(target_seconds / max(t1, 1e-6)))
+    res = [None] * threads
+
+    def work(i):
+        res[i] = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, 2, 0, hdr, nb, payload, tab, 626, reps)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    mbs = threads * reps * b.n_frames * b.n_mbs
+    return {"value": mbs / wall, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": "%d threads x %d passes over %d frames (2 streams x 8 frames of the config-5 workload, "
+                      "%d MBs/frame, dense hints), %.1f s wall" % (threads, reps, b.n_frames, b.n_mbs, wall)}, wall, reps
+
+
+def main_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    po = ge.load_oracle()
+    ge.load_package()
+    threads = os.cpu_count() or 1
+    vals, walls = [], []
+    for i in range(args.warmup + args.steps):
+        r, wall, reps = run_cpu(po, threads, target_seconds=max(1.0, 20.0 / max(args.steps + args.warmup, 1)))
+        if i >= args.warmup:
+            vals.append(r["value"]); walls.append(wall)
+        last = r
+    v = float(np.mean(vals))
+    last["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args), "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "config5: batched independent 1080p UI streams, %d streams x %d frames per GPU "
+                        "(1920x1088 = 120x68 MBs, config-3 layout with a 25x25-MB spliced dynamic region, "
+                        "num_refs 2, skip OFF, reference predictor)" % (args.streams, args.frames),
+            "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "mbs_per_frame": 8160,
+            "l2_policy": "inputs larger than L2: %.0f MB of hints + payload per GPU per step vs 126 MB L2"
+                         % ((args.streams * args.frames * (8160 * 8 + 23500)) / 1e6),
+            "sharding": "streams block-partitioned over ranks, no collective"}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+
+def main_ours(args):
+    rank, local, world = dist_env()
+    ge.load_package()
+    from h264_scroll_encoder_b200 import binding, workloads, abi
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+    gc = binding.GpuComposer(local)      # raises if the CUDA library or a B200 is missing: no fallback
+    L = gc.lib
+
+    b = workloads.make_config5(args.streams, args.frames, stream0=rank * args.streams)
+    n, n_mbs = b.n_frames, b.n_mbs
+    total_mbs = n * n_mbs
+
+    # ---- device-resident inputs -------------------------------------------------------------------
+    pay_pad = np.concatenate([b.payload, np.zeros(16, np.uint8)])
+    d_desc, d_rdesc, d_reg = gc.to_device(b.desc), gc.to_device(b.rdesc), gc.to_device(b.regions)
+    d_info, d_dyn, d_tab, d_pay = gc.to_device(b.dyn_info), gc.to_device(b.dyn), gc.to_device(b.dyn_tab), gc.to_device(pay_pad)
+    d_hints = gc.alloc(8 * b.hint_stride * n)
+    d_out = gc.alloc(b.slot_cap * n)
+    d_packed = gc.alloc(b.slot_cap * n // 2)
+    d_sizes, d_offs = gc.alloc(4 * n), gc.alloc(8 * (n + 1))
+    gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
+    gc.sync()
+
+    ev0, ev1 = L.h264gpu_event_create(), L.h264gpu_event_create()
+
+    def barrier():
+        gc.sync()
+        if dist is not None:
+            dist.barrier()
+        gc.sync()
+
+    def kernel_step():
+        gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
+
+    for _ in range(args.warmup):
+        kernel_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = gc.launch_count()
+    gc.check(L.h264gpu_event_record(ev0, None))
+    for _ in range(args.steps):
+        kernel_step()
+    gc.check(L.h264gpu_event_record(ev1, None))
+    ms = L.h264gpu_event_elapsed_ms(ev0, ev1)
+    launches = gc.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop()
+
+    sizes = d_sizes.download(np.uint32)
+    assert (sizes <= b.slot_cap).all() and (sizes > 5).all(), "a frame overflowed its slot"
+    s_out = int(sizes.sum())
+    s_dyn = int(sum(int(b.dyn_tab[int(b.dyn["table_off"][f]) + 625]) for f in range(n)) // 8)
+    b_alg = 8 * total_mbs + s_dyn + 4 * 626 * n + s_out + 64 * n
+
+    # ---- end to end: host buffers in, packed Annex-B stream out, every step ------------------------
+    def pinned(a):
+        a = np.ascontiguousarray(a)
+        p = L.h264gpu_host_alloc(max(a.nbytes, 16))
+        v = np.ctypeslib.as_array((ctypes.c_uint8 * a.nbytes).from_address(p))
+        v[:] = a.view(np.uint8).reshape(-1)
+        return p, a.nbytes
+    ups = [(pinned(x), d) for x, d in ((b.desc, d_desc), (b.rdesc, d_rdesc), (b.regions, d_reg), (b.dyn_info, d_info),
+                                       (b.dyn, d_dyn), (b.dyn_tab, d_tab), (b.payload, d_pay))]
+    h2d_bytes = sum(nb for (p, nb), d in ups)
+    h_out = L.h264gpu_host_alloc(b.slot_cap * n // 2)
+    h_offs = L.h264gpu_host_alloc(8 * (n + 1))
+    offs_view = np.ctypeslib.as_array((ctypes.c_uint64 * (n + 1)).from_address(h_offs))
+    est_total = [s_out]
+
+    def e2e_step():
+        for (p, nb), d in ups:
+            gc.check(L.h264gpu_memcpy_h2d(d.ptr, p, nb, None))
+        gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
+        gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
+        gc.pack_frames(d_desc, d_sizes, n, d_out, d_packed, d_offs)
+        gc.check(L.h264gpu_memcpy_d2h(h_offs, d_offs.ptr, 8 * (n + 1), None))
+        gc.sync()
+        tot = int(offs_view[n])
+        gc.check(L.h264gpu_memcpy_d2h(h_out, d_packed.ptr, tot, None))
+        gc.sync()
+        est_total[0] = tot
+        return tot
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d2h = e2e_step()
+    gc.sync()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert d2h == s_out, "packed stream size differs from the sum of the frame sizes"
+
+    # ---- reduce over ranks (max time) ------------------------------------------------------------
+    ms_step, e2e_step_s = ms / args.steps, e2e_s
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_step, e2e_step_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_step_s = float(t[0]), float(t[1])
+        tm = torch.tensor([float(total_mbs), float(b_alg)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+        job_mbs = float(tm[0])
+    else:
+        job_mbs = float(total_mbs)
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        achieved = b_alg / (ms / args.steps * 1e-3) / 1e9      # this rank's kernel, GB/s
+        line = {
+            "metric": METRIC, "value": job_mbs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h + 8 * (n + 1)), "ms_per_step": 1e3 * e2e_step_s,
+                    "path": "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "compose_frames_kernel",
+                         "algorithmic_bytes_per_launch": int(b_alg), "bytes_per_mb": b_alg / total_mbs,
+                         "kernel_ms": ms / args.steps},
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            po = ge.load_oracle()
+            cb, _, _ = run_cpu(po, 1, target_seconds=12.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

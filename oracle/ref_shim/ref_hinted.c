@@ -90,7 +90,9 @@ size_t refhint_compose_frame(const H264GpuMbHint *hints, int mb_w, int mb_h,
                 bitwriter_write_ue(&bw, skip_count);
                 skip_count = 0;
                 uint32_t b0 = dyn_bit_off[h->dyn_idx], b1 = dyn_bit_off[h->dyn_idx + 1];
-                copy_bits(&bw, payload, payload_bytes, b0, b1 - b0);
+                /* the reference's copy_bits walks to start_bit one bit at a time, so hand it the
+                 * byte that holds the first bit: same function, same result, no O(offset) walk */
+                copy_bits(&bw, payload + (b0 >> 3), payload_bytes - (b0 >> 3), b0 & 7, b1 - b0);
                 if (h->kind == H264GPU_MB_DYN_INTRA) { ref_idx = 255; mvx = 0; mvy = 0; }
             }
 
