@@ -6,19 +6,23 @@
  *
  *   load     hints of the tile + (mb_w+1) halo -> shared memory (128-bit loads)
  *   decide   per MB: A/B/C(D) neighbours from shared memory, MV predictor, P_Skip
- *            test, mvd, closed-form Exp-Golomb -> 16-byte MbEntry + bit length
- *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
+ *            test, mvd, closed-form Exp-Golomb -> MbEntry + bit length
+ *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101);
+ *            a uniform neighbourhood (A = B = C = own hint) short-cuts to mvd = 0
  *   skiprun  SPEC mode only: ballot masks + prefix-max -> mb_skip_run per coded MB
  *   scan     block prefix sum of bit lengths -> absolute slice bit offsets
- *   pack     output-word-owned gather: each thread builds whole 32-bit words from
- *            the MbEntries overlapping them; spliced MBs are funnel-shifted in from
- *            the pre-encoded payload (semantics of copy_bits, src/h264_writer.c:228)
- *   epb      emulation prevention (src/nal.c:24-50) in closed form: detect per word,
- *            prefix-sum the insert flags, compact; untouched words are stored directly
+ *   pack     output words in which a macroblock starts are gathered by an owner
+ *            thread from the entries overlapping them; words lying wholly inside a
+ *            spliced macroblock are funnel-shifted in from the pre-encoded payload by
+ *            a whole warp with coalesced loads (semantics of copy_bits,
+ *            src/h264_writer.c:228)
+ *   epb      emulation prevention (src/nal.c:24-50) in closed form: zero-byte
+ *            detect, prefix-max of the last non-zero byte, prefix-sum of the insert
+ *            flags, compact; warps without insertions store re-aligned 32-bit words
  *
  * The Annex-B start code, the NAL header byte and the host-written slice header
- * are treated as the first bits of the same bit string, so the shared-memory
- * image is the output image.
+ * are the first bits of the same bit string, so the shared-memory image is the
+ * output image.
  */
 #include <cuda_runtime.h>
 #include "mb_codec.cuh"
@@ -32,6 +36,7 @@ constexpr int MPT = TILE / NT;           /* macroblocks per thread per tile */
 constexpr int HALO_MAX = COMPOSE_MAX_MB_W + 1;
 constexpr int CH = 1024;                 /* output words per pack chunk */
 constexpr int NW = NT / 32;
+constexpr int WPT = CH / NT;             /* output words per thread per chunk */
 
 struct FrameState {
     u32 bitpos;        /* slice bits emitted so far (incl. 40-bit Annex-B prefix) */
@@ -42,14 +47,17 @@ struct FrameState {
     u32 trailer_len;
     int last_coded_next;
     u32 carry_next;
+    u32 n_long;        /* entries of the current tile that may own interior words (spliced / > 32 bits) */
+    int zc_next;
 };
 
 struct __align__(16) ComposeSmem {
     uint2 hint[HALO_MAX + TILE];
     MbEntry ent[TILE + 1];
-    u32 off[TILE + 4];
+    u32 off[TILE + 4];                   /* lengths, then offsets; entry kind in the top two bits */
     u32 out[CH];
-    unsigned short first[CH];
+    u32 first[CH];                       /* (chunk tag << 16) | first entry starting in the word */
+    unsigned short longlist[TILE];
     u32 mask[TILE / 32];
     int prev[TILE / 32];
     u32 scan[NW + 1];
@@ -69,25 +77,46 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
     }
     if (lane == 31) s_scan[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        u32 w = lane < NW ? s_scan[lane] : 0u;
-        u32 wi = w;
+    const u32 wsum = lane < NW ? s_scan[lane] : 0u;    /* every warp scans the NW warp totals itself */
+    u32 winc = wsum;
 #pragma unroll
-        for (int d = 1; d < NW; d <<= 1) {
-            u32 t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= d) wi += t;
-        }
-        if (lane < NW) s_scan[lane] = wi - w;
-        if (lane == NW - 1) s_scan[NW] = wi;
+    for (int d = 1; d < NW; d <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+        if (lane >= d) winc += t;
     }
-    __syncthreads();
-    u32 res = s_scan[warp] + inc - v;
-    total = s_scan[NW];
-    __syncthreads();
-    return res;
+    const u32 wexc = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
+    total = __shfl_sync(0xFFFFFFFFu, winc, NW - 1);
+    __syncthreads();                                   /* s_scan may be reused by the caller */
+    return wexc + inc - v;
 }
 
-__device__ __forceinline__ uint2 ld_hint2(const uint2 *p) { return __ldg(p); }
+/* exclusive prefix max over the CTA (identity `ident`); `total` = max over all threads */
+__device__ __forceinline__ int block_excl_scan_max(int v, int ident, int *s_scan, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc = max(inc, t);
+    }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    const int wv = lane < NW ? s_scan[lane] : ident;
+    int winc = wv;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+        int t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+        if (lane >= d) winc = max(winc, t);
+    }
+    int wexc = __shfl_up_sync(0xFFFFFFFFu, winc, 1);
+    if (lane == 0) wexc = ident;
+    wexc = __shfl_sync(0xFFFFFFFFu, wexc, warp);
+    total = __shfl_sync(0xFFFFFFFFu, winc, NW - 1);
+    __syncthreads();
+    int exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) exc = ident;
+    return max(wexc, exc);
+}
 
 __global__ void __launch_bounds__(NT, 4)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
@@ -98,6 +127,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
     __shared__ ComposeSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 chunk_tag = 0;                    /* bumps per pack chunk; stale first[] entries never match */
+
+    for (int jj = tid; jj < CH; jj += NT) sm.first[jj] = 0xFFFFFFFFu;
 
     for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
         /* ---- frame setup ------------------------------------------------ */
@@ -106,6 +138,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             ((u32 *)&sm.desc)[tid] = ((const u32 *)&descs[f])[tid];
         __syncthreads();
         const int W = sm.desc.mb_w, N = W * (int)sm.desc.mb_h;
+        const u32 w_magic = 0xFFFFFFFFu / (u32)W + 1u;         /* g / W == umulhi(g, magic): exact for g < 2^20, W < 2^10 */
         const int num_refs = sm.desc.num_refs;
         const int skip_spec = (sm.desc.flags & H264GPU_SKIP_SPEC) != 0;
         const int pred_spec = (sm.desc.flags & H264GPU_PRED_SPEC) != 0;
@@ -120,6 +153,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             sm.st.last_coded = -1;
             sm.st.zc = 0;
             sm.st.ins_total = 0;
+            sm.st.n_long = 0;
         }
         __syncthreads();
         const uint2 *fh = (const uint2 *)hints + sm.desc.hint_off;
@@ -152,7 +186,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     int g = g_al + 2 * p;
                     uint4 v;
                     if (g + 1 < N) v = __ldg(src + p);
-                    else { uint2 s = ld_hint2(fh + g); v = make_uint4(s.x, s.y, 0u, 0u); }
+                    else { uint2 s2 = __ldg(fh + g); v = make_uint4(s2.x, s2.y, 0u, 0u); }
                     int idx = 2 * p - lead;
                     if (idx >= 0) sm.hint[idx] = make_uint2(v.x, v.y);
                     if (idx + 1 < cnt) sm.hint[idx + 1] = make_uint2(v.z, v.w);
@@ -166,47 +200,72 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 const int i = k * NT + tid;
                 const int g = t0 + i;
                 int coded = 0;
-                u32 len = 0;
+                u32 len = 0, kind = KIND_SHORT;
                 if (i < n_real) {
                     const uint2 h = sm.hint[halo + i];
-                    const u32 kind = (h.y >> 8) & 0xFFu;
+                    const u32 hk = (h.y >> 8) & 0xFFu;
                     MbEntry e;
                     e.w0 = 0; e.w1 = 0; e.w2 = 0; e.w3 = 0;
                     coded = 1;
-                    if (kind == H264GPU_MB_INTER) {
-                        const int y = g / W, x = g - y * W;
+                    if (hk == H264GPU_MB_INTER) {
+                        const int y = W == 1 ? g : (int)__umulhi((u32)g, w_magic), x = g - y * W;
                         const int ref = (int)(h.y & 0xFFu);
-                        Nbr a = {0, 0, 0}, b = {0, 0, 0}, c = {0, 0, 0};
                         const int avA = x > 0, avB = y > 0;
-                        int avC = 0;
-                        if (avA) { uint2 n = sm.hint[halo + i - 1]; a = nbr_from_hint(n.x, n.y); }
-                        if (avB) {
-                            uint2 n = sm.hint[halo + i - W];
-                            b = nbr_from_hint(n.x, n.y);
-                            if (x + 1 < W) { uint2 m = sm.hint[halo + i - W + 1]; c = nbr_from_hint(m.x, m.y); avC = 1; }
-                            else if (x > 0) { uint2 m = sm.hint[halo + i - W - 1]; c = nbr_from_hint(m.x, m.y); avC = 1; }
+                        const int avC = avB && (x + 1 < W || x > 0);
+                        uint2 ha = make_uint2(0u, 0u), hb = ha, hc = ha;
+                        if (avA) ha = sm.hint[halo + i - 1];
+                        if (avB) hb = sm.hint[halo + i - W];
+                        if (avC) hc = sm.hint[halo + i - W + (x + 1 < W ? 1 : -1)];
+                        const u32 own_lo = h.x, own_hi = h.y & 0xFFFFu;
+                        const bool uniform = avA && avB && avC &&
+                                             ha.x == own_lo && hb.x == own_lo && hc.x == own_lo &&
+                                             (ha.y & 0xFFFFu) == own_hi && (hb.y & 0xFFFFu) == own_hi &&
+                                             (hc.y & 0xFFFFu) == own_hi;
+                        int blen;
+                        if (uniform) {
+                            /* A = B = C = this MB: every predictor rule yields the MB's own MV -> mvd 0;
+                             * with ref 0 that is also exactly the inferred P_Skip motion */
+                            if (skip_spec && ref == 0) coded = 0;
+                            blen = encode_p16x16_body(ref, 0, 0, num_refs, e);
+                        } else {
+                            const Nbr a = nbr_from_hint(ha.x, ha.y), b = nbr_from_hint(hb.x, hb.y),
+                                      c = nbr_from_hint(hc.x, hc.y);
+                            const int mvx = (int)(int16_t)(h.x & 0xFFFFu), mvy = (int)(int16_t)(h.x >> 16);
+                            int px, py;
+                            predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
+                            if (skip_spec && ref == 0) {
+                                int sx, sy;
+                                skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
+                                if (mvx == sx && mvy == sy) coded = 0;
+                            }
+                            blen = encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
                         }
-                        const int mvx = (int)(int16_t)(h.x & 0xFFFFu), mvy = (int)(int16_t)(h.x >> 16);
-                        int px, py;
-                        predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
-                        if (skip_spec && ref == 0) {
-                            int sx, sy;
-                            skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
-                            if (mvx == sx && mvy == sy) coded = 0;
+                        if (coded) {
+                            len = (u32)blen;
+                            if (!skip_spec) { kind = finish_inline_entry(e, 0x80000000u, 1, blen); len += 1u; }  /* ue(0), :630 */
                         }
-                        if (coded) len = (u32)encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
                     } else {
                         const u32 di = h.y >> 16;
                         const u32 b0 = __ldg(tab + di), b1 = __ldg(tab + di + 1);
                         e.w1 = b0; e.w2 = b1 - b0; e.w3 = ENT_DYN;
                         len = e.w2;
+                        kind = KIND_DYN;
+                        if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }
                     }
-                    if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }   /* ue(0), :630 */
                     sm.ent[i] = e;
                 }
-                sm.off[i] = len;
+                sm.off[i] = len | (kind << OFF_KIND_SHIFT);
                 const u32 m = __ballot_sync(0xFFFFFFFFu, coded);
                 if (lane == 0) sm.mask[i >> 5] = m;
+                /* entries that can own whole output words are listed for the cooperative copy */
+                const bool listed = kind != KIND_SHORT;
+                const u32 lm = __ballot_sync(0xFFFFFFFFu, listed);
+                if (lm) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.st.n_long, (u32)__popc(lm));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (listed) sm.longlist[base + __popc(lm & ((1u << lane) - 1u))] = (unsigned short)i;
+                }
             }
             __syncthreads();
 
@@ -235,11 +294,21 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                         const u32 below = m & ((1u << (i & 31)) - 1u);
                         const int prev = below ? (t0 + (i & ~31) + 31 - __clz((int)below)) : sm.prev[i >> 5];
                         const u32 run = (u32)(t0 + i - 1 - prev);
-                        u32 bits; int n;
-                        encode_skip_prefix(run, bits, n);
-                        sm.ent[i].w0 = bits;
-                        sm.ent[i].w3 |= (u32)n;
-                        sm.off[i] += (u32)n;
+                        u32 bits; int pn;
+                        encode_skip_prefix(run, bits, pn);
+                        const u32 lk = sm.off[i];
+                        u32 kind = lk >> OFF_KIND_SHIFT;
+                        const u32 blen = lk & OFF_MASK;
+                        if (kind == KIND_DYN) {
+                            sm.ent[i].w0 = bits;
+                            sm.ent[i].w3 |= (u32)pn;
+                        } else {
+                            MbEntry e = sm.ent[i];
+                            kind = finish_inline_entry(e, bits, pn, (int)blen);
+                            sm.ent[i] = e;
+                            if (kind == KIND_LONG) sm.longlist[atomicAdd(&sm.st.n_long, 1u)] = (unsigned short)i;
+                        }
+                        sm.off[i] = (blen + (u32)pn) | (kind << OFF_KIND_SHIFT);
                     }
                 }
                 __syncthreads();
@@ -247,40 +316,43 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
             /* ---- slice trailer: trailing mb_skip_run + rbsp_stop_one_bit ---- */
             if (last && tid == 0) {
-                u32 bits = 0x80000000u; int n = 1;
+                u32 bits = 0x80000000u; int pn = 1;
                 if (skip_spec) {
                     const int lc = sm.st.last_coded_next;
                     const u32 run_end = (u32)(N - 1 - lc);
                     if (run_end > 0) {
-                        encode_skip_prefix(run_end, bits, n);
-                        bits |= 1u << (31 - n);
-                        n += 1;
+                        encode_skip_prefix(run_end, bits, pn);
+                        bits |= 1u << (31 - pn);
+                        pn += 1;
                     }
                 }
-                MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = (u32)n;
-                sm.ent[n_real] = e;
-                sm.st.trailer_len = (u32)n;
+                MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = 0;
+                sm.ent[n_real] = e;                            /* a KIND_SHORT entry */
+                sm.st.trailer_len = (u32)pn;
             }
 
             /* ---- bit offsets: prefix sum of the lengths --------------------- */
             const u32 bitpos = sm.st.bitpos;
             {
                 uint4 l = *(uint4 *)&sm.off[MPT * tid];
-                u32 s = l.x + l.y + l.z + l.w, total;
-                u32 base = bitpos + block_excl_scan(s, sm.scan, total);
+                const u32 k0 = l.x & ~OFF_MASK, k1 = l.y & ~OFF_MASK, k2 = l.z & ~OFF_MASK, k3 = l.w & ~OFF_MASK;
+                l.x &= OFF_MASK; l.y &= OFF_MASK; l.z &= OFF_MASK; l.w &= OFF_MASK;
+                u32 sum4 = l.x + l.y + l.z + l.w, total;
+                u32 base = bitpos + block_excl_scan(sum4, sm.scan, total);
                 uint4 o;
                 o.x = base; o.y = base + l.x; o.z = o.y + l.y; o.w = o.z + l.z;
+                o.x |= k0; o.y |= k1; o.z |= k2; o.w |= k3;
                 *(uint4 *)&sm.off[MPT * tid] = o;
                 __syncthreads();
                 if (tid == 0) {
                     u32 e0 = bitpos + total;
-                    sm.off[n_real] = e0;                       /* sentinel / trailer start */
+                    sm.off[n_real] = e0;                       /* sentinel / trailer start (KIND_SHORT) */
                     if (last) sm.off[n_real + 1] = e0 + sm.st.trailer_len;
                 }
                 __syncthreads();
             }
             const int n = last ? n_real + 1 : n_real;          /* entries; off[n] = end */
-            const u32 end = sm.off[n];
+            const u32 end = sm.off[n] & OFF_MASK;
             const u32 w_lo = bitpos >> 5;
             const u32 total_bytes = (end + 7u) >> 3;           /* meaningful when last */
             const u32 w_end = end >> 5;
@@ -288,86 +360,176 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end;
             const u32 cb0 = tile0 ? 0u : w_lo;
             const u32 carry_in = sm.st.carry;
+            const u32 n_long = sm.st.n_long;
 
             for (u32 cb = cb0; cb <= w_last; cb += CH) {
-                /* markers: first[j] = smallest entry index whose start is >= bit 32j */
-                for (int i = tid; i <= n; i += NT) {
-                    const u32 jhi = sm.off[i] >> 5;
-                    u32 jlo = (i == 0) ? cb0 : (sm.off[i - 1] >> 5) + 1u;
-                    if (jlo < cb) jlo = cb;
-                    const u32 jtop = min(jhi, cb + CH - 1u);
-                    for (u32 j = jlo; j <= jtop; j++) sm.first[j - cb] = (unsigned short)i;
+                chunk_tag = (chunk_tag + 1u) & 0xFFFFu;
+                if (chunk_tag == 0u) {                         /* tag wrapped: forget every stale marker */
+                    for (int jj = tid; jj < CH; jj += NT) sm.first[jj] = 0xFFFFFFFFu;
+                    chunk_tag = 1u;
+                    __syncthreads();
                 }
+                const u32 tagbits = chunk_tag << 16;
+
+                /* markers: for every word in which an entry starts, the first such entry */
+                for (int i = tid; i <= n; i += NT) {
+                    const u32 j = (sm.off[i] & OFF_MASK) >> 5;
+                    const bool first_in_word = (i == 0) || (((sm.off[i - 1] & OFF_MASK) >> 5) != j);
+                    if (first_in_word && j >= cb && j < cb + CH) sm.first[j - cb] = tagbits | (u32)i;
+                }
+                if (tile0 && cb + (u32)tid < w_lo)             /* words holding only header bits */
+                    sm.first[tid] = tagbits;
                 __syncthreads();
 
-                /* pack: one 32-bit output word per thread per step */
+                /* pack (a): words in which an entry starts -> gathered by one thread each */
                 const u32 j_hi = min(cb + CH, w_last + 1u);
                 for (u32 j = cb + tid; j < j_hi; j += NT) {
+                    const u32 fm = sm.first[j - cb];
+                    if ((fm & 0xFFFF0000u) != tagbits) continue;           /* interior word, see (b) */
                     const u32 base = j << 5;
                     u32 acc = tile0 ? (base < 40u + 256u ? header_bits32(sm.desc.hdr_bits, nal_header, base) : 0u)
                                     : (j == w_lo ? carry_in : 0u);
-                    int i = sm.first[j - cb];
-                    if (i > 0) acc |= entry_contrib(sm.ent[i - 1], sm.off[i - 1], base, pay_words, n_pay_words);
-                    while (i < n && sm.off[i] < base + 32u) {
-                        acc |= entry_contrib(sm.ent[i], sm.off[i], base, pay_words, n_pay_words);
+                    int i = (int)(fm & 0xFFFFu);
+                    if (i > 0) {
+                        const u32 o = sm.off[i - 1];
+                        if ((o >> OFF_KIND_SHIFT) == KIND_SHORT) acc |= short_contrib(sm.ent[i - 1].w0, o & OFF_MASK, base);
+                        else acc |= entry_contrib(sm.ent[i - 1], o & OFF_MASK, base, pay_words, n_pay_words);
+                    }
+                    while (i < n) {
+                        const u32 o = sm.off[i];
+                        if ((o & OFF_MASK) >= base + 32u) break;
+                        if ((o >> OFF_KIND_SHIFT) == KIND_SHORT) acc |= short_contrib(sm.ent[i].w0, o & OFF_MASK, base);
+                        else acc |= entry_contrib(sm.ent[i], o & OFF_MASK, base, pay_words, n_pay_words);
                         i++;
                     }
                     if (j < w_stop) sm.out[j - cb] = acc;
-                    else sm.st.carry_next = acc;               /* partial word, next tile */
+                    else sm.st.carry_next = acc;               /* partial word, carried into the next tile */
+                }
+                /* pack (b): words lying wholly inside one long entry -> a warp per entry, a lane per word */
+                for (u32 d = warp; d < n_long; d += NW) {
+                    const int i = sm.longlist[d];
+                    const u32 o = sm.off[i] & OFF_MASK;
+                    const u32 o_next = sm.off[i + 1] & OFF_MASK;
+                    u32 ja = (o >> 5) + 1u, jb = o_next >> 5;              /* interior words [ja, jb) */
+                    if (ja < cb) ja = cb;
+                    if (jb > cb + CH) jb = cb + CH;
+                    if (ja >= jb) continue;
+                    const MbEntry e = sm.ent[i];
+                    for (u32 j = ja + lane; j < jb; j += 32)
+                        sm.out[j - cb] = entry_contrib(e, o, j << 5, pay_words, n_pay_words);
                 }
                 __syncthreads();
 
-                /* emulation prevention + store of words [cb, e_hi) */
+                /* ---- emulation prevention + store of words [cb, e_hi) ------ */
                 const u32 e_hi = min(cb + CH, w_stop);
                 const int cw = e_hi > cb ? (int)(e_hi - cb) : 0;
                 const u32 chunk_byte0 = cb << 2;
                 const int zc_in = sm.st.zc;
                 const u32 ins_in = sm.st.ins_total;
                 const int chunk_bytes = last ? (int)(min(e_hi << 2, total_bytes) - chunk_byte0) : cw * 4;
-                u32 masks = 0;
-                for (int it = 0; it * NT < cw; it++) {
+                u32 wv[WPT];
+                bool cand = false;
+#pragma unroll
+                for (int it = 0; it < WPT; it++) {
                     const int jj = it * NT + tid;
+                    wv[it] = 0xFFFFFFFFu;
                     if (jj < cw) {
-                        const u32 j = cb + jj;
                         const u32 w = sm.out[jj];
-                        bool cand = zero_byte_mask(w) != 0u;
-                        if (jj > 0) cand = cand || zero_byte_mask(sm.out[jj - 1]) != 0u;
-                        else cand = cand || zc_in > 0;
-                        if (j == 0) cand = false;
-                        if (j == 1) cand = (zero_byte_mask(w | 0xFF000000u) != 0u);
-                        if (cand) {
-                            int vb = min(4, chunk_bytes - 4 * jj);
-                            masks |= epb_insert_mask(sm.out, jj, chunk_byte0, zc_in, vb) << (4 * it);
-                        }
+                        wv[it] = w;
+                        const u32 j = cb + jj;
+                        /* protection needs two zero bytes in a row somewhere in the chunk */
+                        bool c = zero_byte_mask(j == 1u ? (w | 0xFF000000u) : w) != 0u;
+                        if (j == 0u) c = false;
+                        cand = cand || c;
                     }
                 }
-                const int any_ins = __syncthreads_or(masks != 0u);
-                if (!any_ins && ins_in == 0u) {
-                    for (int jj = tid; jj < cw; jj += NT) {
-                        const u32 j = cb + jj;
-                        if (4u * j + 4u <= cap) fout32[j] = bswap32(sm.out[jj]);
+                if (tid == 0 && zc_in > 0) cand = true;
+                const int any_cand = __syncthreads_or(cand);
+                u32 masks = 0;
+                int any_ins = 0;
+                if (any_cand) {
+                    int running_nz = -1 - zc_in;                           /* carried automaton state */
+#pragma unroll
+                    for (int it = 0; it < WPT; it++) {
+                        if (it * NT < cw) {
+                            const int jj = it * NT + tid;
+                            const int vb = jj < cw ? min(4, chunk_bytes - 4 * jj) : 0;
+                            const int lnz = word_last_nonzero(wv[it], vb, 4 * jj);
+                            int tot;
+                            int prev_nz = block_excl_scan_max(lnz, EPB_NONE, (int *)sm.scan, tot);
+                            prev_nz = max(prev_nz, running_nz);
+                            if (vb > 0) masks |= epb_word_mask(wv[it], vb, 4 * jj, chunk_byte0, prev_nz) << (4 * it);
+                            running_nz = max(running_nz, tot);
+                        }
                     }
-                } else {
-                    u32 running = ins_in;
-                    for (int it = 0; it * NT < cw; it++) {
+                    any_ins = __syncthreads_or(masks != 0u);
+                    if (tid == 0) {
+                        const int r_end = chunk_bytes - 1 - running_nz;    /* zero bytes closing the chunk */
+                        sm.st.zc_next = r_end == 0 ? 0 : ((r_end & 1) ? 1 : 2);
+                    }
+                } else if (tid == 0) sm.st.zc_next = 0;
+
+                u32 running = ins_in;
+#pragma unroll
+                for (int it = 0; it < WPT; it++) {
+                    if (it * NT < cw) {
                         const int jj = it * NT + tid;
                         const u32 mk = (masks >> (4 * it)) & 0xFu;
-                        u32 tot;
-                        u32 before = running + block_excl_scan(jj < cw ? __popc(mk) : 0, sm.scan, tot);
-                        if (jj < cw) {
-                            const int vb = min(4, chunk_bytes - 4 * jj);
-                            u32 pos = chunk_byte0 + 4u * jj + before;
-                            for (int k = 0; k < vb; k++) {
-                                if ((mk >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                                if (pos < cap) fout[pos] = (uint8_t)chunk_byte(sm.out, 4 * jj + k);
-                                pos++;
+                        u32 before = running;
+                        if (any_ins) {
+                            u32 tot;
+                            before += block_excl_scan(jj < cw ? (u32)__popc(mk) : 0u, sm.scan, tot);
+                            running += tot;
+                        }
+                        const int vb = jj < cw ? min(4, chunk_bytes - 4 * jj) : 0;
+                        const u32 w = wv[it];
+                        /* a warp covers 32 consecutive words: without insertions (and no partial tail word)
+                         * they move as re-aligned 32-bit words, otherwise byte by byte */
+                        const bool byte_path = __any_sync(0xFFFFFFFFu, vb > 0 && (mk != 0u || vb < 4));
+                        const u32 prevw = __shfl_up_sync(0xFFFFFFFFu, w, 1);
+                        const u32 nextvb = __shfl_down_sync(0xFFFFFFFFu, (u32)vb, 1);
+                        if (vb > 0) {
+                            const u32 src_byte = chunk_byte0 + 4u * (u32)jj;
+                            if (byte_path) {
+                                u32 pos = src_byte + before;
+                                for (int k = 0; k < vb; k++) {
+                                    if ((mk >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
+                                    if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
+                                    pos++;
+                                }
+                            } else {
+                                const u32 sft = before & 3u;
+                                if (sft == 0u) {
+                                    const u32 pos = src_byte + before;
+                                    if (pos + 4u <= cap) fout32[pos >> 2] = bswap32(w);
+                                } else {
+                                    const bool head = (lane == 0);
+                                    const bool tail = (lane == 31) || (nextvb == 0u);
+                                    if (!head) {
+                                        /* out word covering source bytes [src_byte - sft, src_byte - sft + 4) */
+                                        const u32 v = (prevw << (8u * (4u - sft))) | (w >> (8u * sft));
+                                        const u32 pos = src_byte - sft + before;
+                                        if (pos + 4u <= cap) fout32[pos >> 2] = bswap32(v);
+                                    } else {
+                                        u32 pos = src_byte + before;
+                                        for (u32 k = 0; k < 4u - sft; k++, pos++)
+                                            if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
+                                    }
+                                    if (tail) {
+                                        u32 pos = src_byte + 4u - sft + before;
+                                        for (u32 k = 4u - sft; k < 4u; k++, pos++)
+                                            if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
+                                    }
+                                }
                             }
                         }
-                        running += tot;
                     }
-                    if (tid == 0) sm.st.ins_total = running;
                 }
-                if (tid == 0 && cw > 0) sm.st.zc = epb_state_after(sm.out, chunk_bytes, chunk_byte0, zc_in);
+                __syncthreads();
+                if (tid == 0) {
+                    sm.st.ins_total = running;
+                    if (cw > 0) sm.st.zc = sm.st.zc_next;
+                }
                 __syncthreads();
             }
 
@@ -375,6 +537,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 sm.st.bitpos = end;
                 sm.st.carry = sm.st.carry_next;
                 if (skip_spec) sm.st.last_coded = sm.st.last_coded_next;
+                sm.st.n_long = 0;
                 if (last) sizes[f] = total_bytes + sm.st.ins_total;
             }
             __syncthreads();
@@ -385,7 +548,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 /* ------------------------------------------------------------ rasteriser */
 
 constexpr int RASTER_THREADS = 256;
-constexpr int RASTER_MAX_REGIONS = 512;
+constexpr int RASTER_MAX_REGIONS = H264GPU_MAX_REGIONS;
 
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_regions_kernel(const H264GpuRasterDesc *__restrict__ rdescs, int n_frames,

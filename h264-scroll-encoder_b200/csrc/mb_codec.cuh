@@ -82,6 +82,19 @@ struct alignas(16) MbEntry { u32 w0, w1, w2, w3; };
 #define ENT_DYN       0x40u
 #define ENT_META_MASK 0x7FFu
 
+/*
+ * The bit-offset word of an entry carries its kind in the two top bits
+ * (slice bit offsets stay below 2^30):
+ *   KIND_SHORT  prefix+body fit one word: w0 holds the whole code, left aligned
+ *   KIND_LONG   inline MB longer than 32 bits: w0 prefix, w1..w3 body
+ *   KIND_DYN    spliced MB: w0 prefix, w1 payload bit offset, w2 payload bit length
+ */
+#define KIND_SHORT 0u
+#define KIND_LONG  1u
+#define KIND_DYN   2u
+#define OFF_KIND_SHIFT 30
+#define OFF_MASK 0x3FFFFFFFu
+
 /* append the low n (1..33) bits of v to the right-aligned accumulator hi:lo */
 HSD void acc_push(u64 &hi, u64 &lo, u64 v, int n) {
     hi = (hi << n) | (lo >> (64 - n));
@@ -149,6 +162,23 @@ HSD void skip_infer_mv(int spec, Nbr a, int avA, Nbr b, int avB, Nbr c, int avC,
  * e.w1..w3 (low 11 bits of w3 cleared).
  */
 HSD int encode_p16x16_body(int ref, int mvdx, int mvdy, int num_refs, MbEntry &e) {
+    {   /* common case: the whole body fits one word */
+        const u32 kx = se_codenum(mvdx), ky = se_codenum(mvdy);
+        const int nx = ue_nbits(kx), ny = ue_nbits(ky);
+        const int rl = num_refs == 2 ? 1 : (num_refs > 2 ? ue_nbits((u32)ref) : 0);
+        const int total = 2 + rl + nx + ny;
+        if (total <= 32) {
+            const u32 rc = num_refs == 2 ? (u32)(1 - (ref & 1)) : (u32)ref + 1u;
+            u32 v = 1u;
+            v = (v << rl) | (rl ? rc : 0u);
+            v = (v << nx) | (kx + 1u);
+            v = (v << ny) | (ky + 1u);
+            v = (v << 1) | 1u;
+            e.w1 = v << (32 - total);
+            e.w2 = 0; e.w3 = 0;
+            return total;
+        }
+    }
     u64 hi = 0, lo = 1;          /* mb_type ue(0) */
     int len = 1;
     if (num_refs == 2) { acc_push(hi, lo, (u64)(1 - (ref & 1)), 1); len += 1; }
@@ -225,6 +255,27 @@ HSD u32 entry_contrib(const MbEntry &e, u32 o, u32 base, const u32 *payload_word
     return acc;
 }
 
+/* contribution of a KIND_SHORT entry (whole code in one left-aligned word) */
+HSD u32 short_contrib(u32 code, u32 o, u32 base) {
+    int q = (int)(base - o);
+    if (q < 0) return q > -32 ? code >> (-q) : 0u;
+    return q < 32 ? code << q : 0u;
+}
+
+/*
+ * Attach the mb_skip_run prefix (pbits left aligned, pn bits) to an entry whose
+ * body (blen bits) sits left aligned in w1..w3.  Returns the kind.
+ */
+HSD u32 finish_inline_entry(MbEntry &e, u32 pbits, int pn, int blen) {
+    if (pn + blen <= 32) {
+        e.w0 = pbits | (pn < 32 ? e.w1 >> pn : 0u);
+        return KIND_SHORT;
+    }
+    e.w0 = pbits;
+    e.w3 = (e.w3 & ~ENT_META_MASK) | (u32)pn;
+    return KIND_LONG;
+}
+
 /* --------------------------------------------------------------- header */
 
 /* 32 bits at stream bit position p of: 00 00 00 01 | nal_header | slice header bits */
@@ -279,6 +330,41 @@ HSD u32 epb_insert_mask(const u32 *words, int j, u32 chunk_byte0, int zc_in, int
         if (r >= 2 && !(r & 1)) mask |= 1u << k;
     }
     return mask;
+}
+
+/*
+ * Scan form of the same rule, one output word at a time.  b0 = chunk-relative
+ * index of the word's first byte, prev_nz = chunk-relative index of the last
+ * non-zero byte before it (may be negative: -1 - zc_in continues the carried
+ * automaton state).  Returns the 4-bit insert mask and updates prev_nz.
+ */
+HSD u32 epb_word_mask(u32 w, int vb, int b0, u32 chunk_byte0, int &prev_nz) {
+    u32 mask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        if (k < vb) {
+            const u32 v = (w >> (24 - 8 * k)) & 0xFFu;
+            const int b = b0 + k;
+            const int r = b - 1 - prev_nz;
+            if (v <= 3u && r >= 2 && !(r & 1) && chunk_byte0 + (u32)b >= 5u) mask |= 1u << k;
+            if (v != 0u) prev_nz = b;
+        }
+    }
+    return mask;
+}
+
+/* chunk-relative index of the last non-zero byte of a word (first vb bytes), or EPB_NONE */
+#define EPB_NONE (-0x40000000)
+HSD int word_last_nonzero(u32 w, int vb, int b0) {
+    int r = EPB_NONE;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++)
+        if (k < vb && ((w >> (24 - 8 * k)) & 0xFFu) != 0u) r = b0 + k;
+    return r;
 }
 
 /* automaton state after a chunk whose emitted bytes are words[0 .. nbytes) */

@@ -46,6 +46,7 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
     std::vector<MbEntry> ent(TILE + 1);
     std::vector<u32> off(TILE + 4);
     std::vector<int> codedv(TILE);
+    std::vector<u32> kinds(TILE + 2, KIND_SHORT);
     std::vector<u32> outw(CH);
     std::vector<int> first(CH);
 
@@ -57,13 +58,13 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
         for (int i = 0; i < TILE; i++) {
             const int g = t0 + i;
             int coded = 0;
-            u32 len = 0;
+            u32 len = 0, kind = KIND_SHORT;
             if (i < n_real) {
                 const H2 h = fh[g];
-                const u32 kind = (h.y >> 8) & 0xFFu;
+                const u32 hk = (h.y >> 8) & 0xFFu;
                 MbEntry e; e.w0 = e.w1 = e.w2 = e.w3 = 0;
                 coded = 1;
-                if (kind == H264GPU_MB_INTER) {
+                if (hk == H264GPU_MB_INTER) {
                     const int y = g / W, x = g - y * W;
                     const int ref = (int)(h.y & 0xFFu);
                     Nbr a = {0, 0, 0}, b = {0, 0, 0}, c = {0, 0, 0};
@@ -77,22 +78,39 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                     }
                     const int mvx = (int)(int16_t)(h.x & 0xFFFFu), mvy = (int)(int16_t)(h.x >> 16);
                     int px, py;
-                    predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
-                    if (skip_spec && ref == 0) {
-                        int sx, sy;
-                        skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
-                        if (mvx == sx && mvy == sy) coded = 0;
+                    /* the kernel's uniform-neighbourhood shortcut: A = B = C = own hint */
+                    const int cidx = x + 1 < W ? g - W + 1 : g - W - 1;
+                    const bool uniform = avA && avB && avC &&
+                        fh[g - 1].x == h.x && fh[g - W].x == h.x && fh[cidx].x == h.x &&
+                        (fh[g - 1].y & 0xFFFFu) == (h.y & 0xFFFFu) && (fh[g - W].y & 0xFFFFu) == (h.y & 0xFFFFu) &&
+                        (fh[cidx].y & 0xFFFFu) == (h.y & 0xFFFFu);
+                    if (uniform) {
+                        px = mvx; py = mvy;
+                        if (skip_spec && ref == 0) coded = 0;
+                    } else {
+                        predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
+                        if (skip_spec && ref == 0) {
+                            int sx, sy;
+                            skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
+                            if (mvx == sx && mvy == sy) coded = 0;
+                        }
                     }
-                    if (coded) len = (u32)encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
+                    if (coded) {
+                        int blen = encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
+                        len = (u32)blen;
+                        if (!skip_spec) { kind = finish_inline_entry(e, 0x80000000u, 1, blen); len += 1u; }
+                    }
                 } else {
                     const u32 di = h.y >> 16;
                     e.w1 = tab[di]; e.w2 = tab[di + 1] - tab[di]; e.w3 = ENT_DYN;
                     len = e.w2;
+                    kind = KIND_DYN;
+                    if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }
                 }
-                if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }
                 ent[i] = e;
             }
             off[i] = len;
+            kinds[i] = kind;
             codedv[i] = coded;
         }
         /* mb_skip_run */
@@ -104,7 +122,9 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 const u32 run = (u32)(t0 + i - 1 - prev);
                 u32 bits; int n;
                 encode_skip_prefix(run, bits, n);
-                ent[i].w0 = bits; ent[i].w3 |= (u32)n; off[i] += (u32)n;
+                if (kinds[i] == KIND_DYN) { ent[i].w0 = bits; ent[i].w3 |= (u32)n; }
+                else kinds[i] = finish_inline_entry(ent[i], bits, n, (int)off[i]);
+                off[i] += (u32)n;
                 prev = t0 + i;
             }
             last_coded_next = prev;
@@ -116,8 +136,9 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 const u32 run_end = (u32)(N - 1 - last_coded_next);
                 if (run_end > 0) { encode_skip_prefix(run_end, bits, n); bits |= 1u << (31 - n); n += 1; }
             }
-            MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = (u32)n;
+            MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = 0;
             ent[n_real] = e;
+            kinds[n_real] = KIND_SHORT;
             trailer_len = (u32)n;
         }
         /* scan */
@@ -138,25 +159,34 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
         u32 carry_next = 0;
 
         for (u32 cb = cb0; cb <= w_last; cb += (u32)CH) {
+            std::fill(first.begin(), first.end(), -1);
             for (int i = 0; i <= n; i++) {
-                const u32 jhi = off[i] >> 5;
-                u32 jlo = (i == 0) ? cb0 : (off[i - 1] >> 5) + 1u;
-                if (jlo < cb) jlo = cb;
-                const u32 jtop = std::min(jhi, cb + (u32)CH - 1u);
-                for (u32 j = jlo; j <= jtop && jtop != 0xFFFFFFFFu; j++) first[j - cb] = i;
+                const u32 j = off[i] >> 5;
+                const bool fiw = (i == 0) || ((off[i - 1] >> 5) != j);
+                if (fiw && j >= cb && j < cb + (u32)CH) first[j - cb] = i;
             }
+            if (tile0) for (u32 t = 0; t < (u32)CH && cb + t < w_lo; t++) first[t] = 0;
             const u32 j_hi = std::min(cb + (u32)CH, w_last + 1u);
             for (u32 j = cb; j < j_hi; j++) {
+                if (first[j - cb] < 0) continue;
                 const u32 base = j << 5;
                 u32 acc = tile0 ? (base < 296u ? header_bits32(d.hdr_bits, d.nal_header, base) : 0u)
                                 : (j == w_lo ? carry : 0u);
                 int i = first[j - cb];
-                if (i > 0) acc |= entry_contrib(ent[i - 1], off[i - 1], base, pay_words, n_pay_words);
-                while (i < n && off[i] < base + 32u) {
-                    acc |= entry_contrib(ent[i], off[i], base, pay_words, n_pay_words);
-                    i++;
-                }
+                auto contrib = [&](int e) {
+                    return kinds[e] == KIND_SHORT ? short_contrib(ent[e].w0, off[e], base)
+                                                  : entry_contrib(ent[e], off[e], base, pay_words, n_pay_words);
+                };
+                if (i > 0) acc |= contrib(i - 1);
+                while (i < n && off[i] < base + 32u) { acc |= contrib(i); i++; }
                 if (j < w_stop) outw[j - cb] = acc; else carry_next = acc;
+            }
+            for (int i = 0; i < n; i++) {
+                if (kinds[i] == KIND_SHORT) continue;
+                u32 ja = (off[i] >> 5) + 1u, jb = off[i + 1] >> 5;
+                if (ja < cb) ja = cb;
+                if (jb > cb + (u32)CH) jb = cb + (u32)CH;
+                for (u32 j = ja; j < jb; j++) outw[j - cb] = entry_contrib(ent[i], off[i], j << 5, pay_words, n_pay_words);
             }
             const u32 e_hi = std::min(cb + (u32)CH, w_stop);
             const int cw = e_hi > cb ? (int)(e_hi - cb) : 0;
@@ -164,18 +194,14 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
             const int chunk_bytes = last ? (int)(std::min(e_hi << 2, total_bytes) - chunk_byte0) : cw * 4;
             std::vector<u32> masks(cw, 0);
             bool any = false;
+            int prev_nz = -1 - zc;
             for (int jj = 0; jj < cw; jj++) {
-                const u32 j = cb + jj, w = outw[jj];
-                bool cand = zero_byte_mask(w) != 0u;
-                if (jj > 0) cand = cand || zero_byte_mask(outw[jj - 1]) != 0u; else cand = cand || zc > 0;
-                if (j == 0) cand = false;
-                if (j == 1) cand = (zero_byte_mask(w | 0xFF000000u) != 0u);
-                if (cand) {
-                    int vb = std::min(4, chunk_bytes - 4 * jj);
-                    masks[jj] = epb_insert_mask(outw.data(), jj, chunk_byte0, zc, vb);
-                    any = any || masks[jj];
-                }
+                int vb = std::min(4, chunk_bytes - 4 * jj);
+                masks[jj] = epb_word_mask(outw[jj], vb, 4 * jj, chunk_byte0, prev_nz);
+                any = any || masks[jj];
             }
+            const int r_end = chunk_bytes - 1 - prev_nz;
+            const int zc_next = r_end == 0 ? 0 : ((r_end & 1) ? 1 : 2);
             if (!any && ins_total == 0) {
                 for (int jj = 0; jj < cw; jj++) {
                     const u32 j = cb + jj;
@@ -195,7 +221,7 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 }
                 ins_total = running;
             }
-            if (cw > 0) zc = epb_state_after(outw.data(), chunk_bytes, chunk_byte0, zc);
+            if (cw > 0) zc = zc_next;
         }
         bitpos = end;
         carry = carry_next;
