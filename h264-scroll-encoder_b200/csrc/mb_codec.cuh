@@ -201,6 +201,26 @@ HSD int encode_p16x16_body(int ref, int mvdx, int mvdy, int num_refs, MbEntry &e
     return len;
 }
 
+/*
+ * Body of an inline MB whose mvd is (0,0): '1' te(ref) '1' '1' '1', left aligned.
+ * This is what every MB in the interior of a uniformly moving region codes.
+ */
+HSD u32 zero_mvd_body(int ref, int num_refs, int &blen) {
+    if (num_refs == 2) { blen = 5; return (0x17u | ((u32)(1 - (ref & 1)) << 3)) << 27; }
+    if (num_refs < 2) { blen = 4; return 0xFu << 28; }
+    const int n = ue_nbits((u32)ref);
+    blen = n + 4;
+    u32 v = (1u << n) | ((u32)ref + 1u);
+    v = (v << 3) | 7u;
+    return v << (32 - blen);
+}
+
+/* 4-bit mask of the zero bytes of a word: bit k = byte k, byte 0 being the first (most significant) */
+HSD u32 zero_nibble(u32 w) {
+    const u32 z = zero_byte_mask(w);
+    return ((z >> 31) & 1u) | ((z >> 22) & 2u) | ((z >> 13) & 4u) | ((z >> 4) & 8u);
+}
+
 /* mb_skip_run prefix: ue(run) left aligned in a word + its length */
 HSD void encode_skip_prefix(u32 run, u32 &bits, int &n) {
     n = ue_nbits(run);
