@@ -1,28 +1,33 @@
 /*
  * compose_kernels.cu - sm_100a kernels of the P-slice composer.
  *
- * One CTA composes one frame at a time (persistent grid-stride over frames).
- * A frame is processed in tiles of TILE macroblocks; per tile:
+ * compose_frames_kernel: one CTA composes one frame at a time (grid-stride over
+ * frames); a frame is walked in tiles of TILE = 256 threads x 8 macroblocks.
+ * Everything per-macroblock lives in registers; shared memory only holds the
+ * slice bits of the tile (the "window") on their way out.
  *
- *   load     hints of the tile + (mb_w+1) halo -> shared memory (128-bit loads)
- *   decide   per MB: A/B/C(D) neighbours from shared memory, MV predictor, P_Skip
- *            test, mvd, closed-form Exp-Golomb -> MbEntry + bit length
- *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101);
- *            a uniform neighbourhood (A = B = C = own hint) short-cuts to mvd = 0
- *   skiprun  SPEC mode only: ballot masks + prefix-max -> mb_skip_run per coded MB
- *   scan     block prefix sum of bit lengths -> absolute slice bit offsets
- *   pack     output words in which a macroblock starts are gathered by an owner
- *            thread from the entries overlapping them; words lying wholly inside a
- *            spliced macroblock are funnel-shifted in from the pre-encoded payload by
- *            a whole warp with coalesced loads (semantics of copy_bits,
- *            src/h264_writer.c:228)
- *   epb      emulation prevention (src/nal.c:24-50) in closed form: zero-byte
- *            detect, prefix-max of the last non-zero byte, prefix-sum of the insert
- *            flags, compact; warps without insertions store re-aligned 32-bit words
+ *   load     every thread reads its 8 consecutive hints (4 x 128-bit loads) plus
+ *            the 10 hints above and the one to the left straight from global memory
+ *            (the rows above come back from L1/L2); nothing is staged
+ *   decide   per MB: A/B/C(D) neighbour views, packed int16x2 predictor, P_Skip test,
+ *            mvd, closed-form Exp-Golomb -> a <= 64-bit code + length in registers
+ *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
+ *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
+ *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
+ *   write    each thread appends its codes with a sequential bit writer: whole words
+ *            are plain stores; the partial first/last words of neighbouring threads are
+ *            merged with a segmented warp-shuffle OR, so shared-memory atomics are left
+ *            for the two words a warp shares with its neighbours
+ *   splice   whole words inside a spliced macroblock are funnel-shifted in from the
+ *            pre-encoded payload by groups of 8 lanes (semantics of copy_bits,
+ *            src/h264_writer.c:228); the partial words at both ends go through the
+ *            owner thread's bit writer
+ *   emit     emulation prevention (src/nal.c:24-50) on 16-byte groups: zero-byte masks,
+ *            a bit-parallel run-parity rule, prefix sum of the insert counts; groups
+ *            without insertions leave as re-aligned 32-bit words (one byte-permute each)
  *
- * The Annex-B start code, the NAL header byte and the host-written slice header
- * are the first bits of the same bit string, so the shared-memory image is the
- * output image.
+ * The Annex-B start code, the NAL header byte and the host-written slice header are
+ * the first bits of the same bit string, so the window image is the output image.
  */
 #include <cuda_runtime.h>
 #include "mb_codec.cuh"
@@ -31,35 +36,28 @@
 namespace h264scroll {
 
 constexpr int NT = COMPOSE_THREADS;      /* threads per CTA */
-constexpr int TILE = 1024;               /* macroblocks per tile */
-constexpr int MPT = TILE / NT;           /* macroblocks per thread per tile */
-constexpr int HALO_MAX = COMPOSE_MAX_MB_W + 1;
-constexpr int CH = 1024;                 /* output words per pack chunk */
+constexpr int MPT = 8;                   /* consecutive macroblocks per thread */
+constexpr int TILE = NT * MPT;           /* macroblocks per tile */
 constexpr int NW = NT / 32;
-constexpr int WPT = CH / NT;             /* output words per thread per chunk */
+constexpr int CH = 6144;                 /* window: slice words staged per pass (24 KB) */
+constexpr int LCAP = 512;                /* splice copy list entries per pass */
+constexpr u32 FULL = 0xFFFFFFFFu;
 
 struct FrameState {
-    u32 bitpos;        /* slice bits emitted so far (incl. 40-bit Annex-B prefix) */
-    u32 carry;         /* partial output word at bitpos>>5 */
+    u32 bitpos;        /* slice bits emitted so far (incl. the 40-bit Annex-B prefix) */
+    u32 carry;         /* partial slice word at bitpos >> 5 */
     int last_coded;    /* frame index of the last non-skipped MB, -1 if none */
-    int zc;            /* rbsp_to_ebsp automaton state (0,1,2) after the emitted bytes */
+    u32 zrun;          /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state) */
     u32 ins_total;     /* emulation-prevention bytes inserted so far */
-    u32 trailer_len;
-    int last_coded_next;
-    u32 carry_next;
-    u32 n_long;        /* entries of the current tile that may own interior words (spliced / > 32 bits) */
-    int zc_next;
+    u32 n_copy;        /* entries in the splice copy list */
+    u32 zrun_next;
 };
 
 struct __align__(16) ComposeSmem {
-    uint2 hint[HALO_MAX + TILE];
-    MbEntry ent[TILE + 1];
-    u32 off[TILE + 4];                   /* lengths, then offsets; entry kind in the top two bits */
-    u32 out[CH];
-    u32 first[CH];                       /* (chunk tag << 16) | first entry starting in the word */
-    unsigned short longlist[TILE];
-    u32 mask[TILE / 32];
-    int prev[TILE / 32];
+    u32 win[CH + 8];                     /* slice bits of the pass, MSB-first words (+ read-ahead pad) */
+    uint4 copy[LCAP];                    /* {first frame word, payload bit, words, -} */
+    u32 tr[NT];                          /* emit: zero bytes closing each 16-byte group */
+    u32 gi[NT];                          /* emit: (insert count << 8) | valid bytes of each group */
     u32 scan[NW + 1];
     H264GpuFrameDesc desc;
     H264GpuDynDesc dyn;
@@ -72,7 +70,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
     u32 inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        u32 t = __shfl_up_sync(FULL, inc, d);
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_scan[warp] = inc;
@@ -81,44 +79,52 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
     u32 winc = wsum;
 #pragma unroll
     for (int d = 1; d < NW; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+        u32 t = __shfl_up_sync(FULL, winc, d);
         if (lane >= d) winc += t;
     }
-    const u32 wexc = __shfl_sync(0xFFFFFFFFu, winc - wsum, warp);
-    total = __shfl_sync(0xFFFFFFFFu, winc, NW - 1);
+    const u32 wexc = __shfl_sync(FULL, winc - wsum, warp);
+    total = __shfl_sync(FULL, winc, NW - 1);
     __syncthreads();                                   /* s_scan may be reused by the caller */
     return wexc + inc - v;
 }
 
-/* exclusive prefix max over the CTA (identity `ident`); `total` = max over all threads */
-__device__ __forceinline__ int block_excl_scan_max(int v, int ident, int *s_scan, int &total) {
+/* exclusive prefix max over the CTA (identity -1 as int); `total` = max over all threads */
+__device__ __forceinline__ int block_excl_scan_max(int v, int *s_scan, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        int t = __shfl_up_sync(FULL, inc, d);
         if (lane >= d) inc = max(inc, t);
     }
     if (lane == 31) s_scan[warp] = inc;
     __syncthreads();
-    const int wv = lane < NW ? s_scan[lane] : ident;
+    const int wv = lane < NW ? s_scan[lane] : -1;
     int winc = wv;
 #pragma unroll
     for (int d = 1; d < NW; d <<= 1) {
-        int t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+        int t = __shfl_up_sync(FULL, winc, d);
         if (lane >= d) winc = max(winc, t);
     }
-    int wexc = __shfl_up_sync(0xFFFFFFFFu, winc, 1);
-    if (lane == 0) wexc = ident;
-    wexc = __shfl_sync(0xFFFFFFFFu, wexc, warp);
-    total = __shfl_sync(0xFFFFFFFFu, winc, NW - 1);
+    int wexc = __shfl_up_sync(FULL, winc, 1);
+    if (lane == 0) wexc = -1;
+    wexc = __shfl_sync(FULL, wexc, warp);
+    total = __shfl_sync(FULL, winc, NW - 1);
     __syncthreads();
-    int exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane == 0) exc = ident;
+    int exc = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) exc = -1;
     return max(wexc, exc);
 }
 
-__global__ void __launch_bounds__(NT, 4)
+/* 32 payload bits from bit position p (payload words are big-endian in memory) */
+__device__ __forceinline__ u32 payload_ld32(const u32 *__restrict__ pw, u32 n_words, u32 p) {
+    const u32 wi = p >> 5;
+    const u32 a = wi < n_words ? bswap32(__ldg(pw + wi)) : 0u;
+    const u32 b = wi + 1u < n_words ? bswap32(__ldg(pw + wi + 1u)) : 0u;
+    return __funnelshift_l(b, a, p & 31u);
+}
+
+__global__ void __launch_bounds__(NT, 3)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuMbHint *__restrict__ hints,
                       const H264GpuDynDesc *__restrict__ dyns,
@@ -126,10 +132,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const uint8_t *__restrict__ payload,
                       uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
     __shared__ ComposeSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    u32 chunk_tag = 0;                    /* bumps per pack chunk; stale first[] entries never match */
-
-    for (int jj = tid; jj < CH; jj += NT) sm.first[jj] = 0xFFFFFFFFu;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
         /* ---- frame setup ------------------------------------------------ */
@@ -138,22 +141,23 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             ((u32 *)&sm.desc)[tid] = ((const u32 *)&descs[f])[tid];
         __syncthreads();
         const int W = sm.desc.mb_w, N = W * (int)sm.desc.mb_h;
-        const u32 w_magic = 0xFFFFFFFFu / (u32)W + 1u;         /* g / W == umulhi(g, magic): exact for g < 2^20, W < 2^10 */
+        const u32 w_magic = 0xFFFFFFFFu / (u32)W + 1u;         /* g / W == umulhi(g, magic): exact for g < 2^20, 1 < W < 2^10 */
         const int num_refs = sm.desc.num_refs;
         const int skip_spec = (sm.desc.flags & H264GPU_SKIP_SPEC) != 0;
         const int pred_spec = (sm.desc.flags & H264GPU_PRED_SPEC) != 0;
         const u32 cap = sm.desc.out_cap;
         const u32 nal_header = sm.desc.nal_header;
+        const u32 hdr_total = 40u + sm.desc.hdr_nbits;
         const u32 dyn_id = sm.desc.dyn_id;
         if (dyn_id != H264GPU_NO_DYN && tid < (int)(sizeof(H264GpuDynDesc) / 4))
             ((u32 *)&sm.dyn)[tid] = ((const u32 *)&dyns[dyn_id])[tid];
         if (tid == 0) {
-            sm.st.bitpos = 40u + sm.desc.hdr_nbits;
+            sm.st.bitpos = hdr_total;
             sm.st.carry = 0;
             sm.st.last_coded = -1;
-            sm.st.zc = 0;
+            sm.st.zrun = 0;
             sm.st.ins_total = 0;
-            sm.st.n_long = 0;
+            sm.st.n_copy = 0;
         }
         __syncthreads();
         const uint2 *fh = (const uint2 *)hints + sm.desc.hint_off;
@@ -169,375 +173,357 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         u32 *fout32 = (u32 *)fout;
 
         for (int t0 = 0; t0 < N; t0 += TILE) {
-            const int n_real = min(TILE, N - t0);
             const bool last = (t0 + TILE >= N);
             const bool tile0 = (t0 == 0);
-            const int halo = min(t0, W + 1);
+            const int g0 = t0 + tid * MPT;
+            const int nmb = min(max(N - g0, 0), MPT);          /* real macroblocks of this thread */
 
-            /* ---- load hints: tile + halo (hint_off even => 16-byte aligned pairs) */
+            /* the window is cleared while the hint loads are in flight */
             {
-                const int first_g = t0 - halo;            /* first hint index needed */
-                const int cnt = halo + n_real;
-                const int g_al = first_g & ~1;             /* align down to a pair */
-                const int lead = first_g - g_al;           /* 0 or 1 */
-                const int pairs = (cnt + lead + 1) >> 1;
-                const uint4 *src = (const uint4 *)(fh + g_al);
-                for (int p = tid; p < pairs; p += NT) {
-                    int g = g_al + 2 * p;
-                    uint4 v;
-                    if (g + 1 < N) v = __ldg(src + p);
-                    else { uint2 s2 = __ldg(fh + g); v = make_uint4(s2.x, s2.y, 0u, 0u); }
-                    int idx = 2 * p - lead;
-                    if (idx >= 0) sm.hint[idx] = make_uint2(v.x, v.y);
-                    if (idx + 1 < cnt) sm.hint[idx + 1] = make_uint2(v.z, v.w);
-                }
+                uint4 *w4 = (uint4 *)sm.win;
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = z4;
+                if (tid == 0 && !tile0) sm.win[0] = sm.st.carry;   /* bits of the previous tile in the shared word */
             }
-            __syncthreads();
 
-            /* ---- decide + code ------------------------------------------- */
+            /* ---- load: own hints, the row above, the left neighbour ---------- */
+            uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
+            uint2 abv[MPT + 2];                                 /* abv[j] = hint g0 - W - 1 + j */
 #pragma unroll
-            for (int k = 0; k < MPT; k++) {
-                const int i = k * NT + tid;
-                const int g = t0 + i;
-                int coded = 0;
-                u32 len = 0, kind = KIND_SHORT;
-                if (i < n_real) {
-                    const uint2 h = sm.hint[halo + i];
-                    const u32 hk = (h.y >> 8) & 0xFFu;
-                    MbEntry e;
-                    e.w0 = 0; e.w1 = 0; e.w2 = 0; e.w3 = 0;
-                    coded = 1;
-                    if (hk == H264GPU_MB_INTER) {
-                        const int y = W == 1 ? g : (int)__umulhi((u32)g, w_magic), x = g - y * W;
-                        const int ref = (int)(h.y & 0xFFu);
-                        const int avA = x > 0, avB = y > 0;
-                        const int avC = avB && (x + 1 < W || x > 0);
-                        uint2 ha = make_uint2(0u, 0u), hb = ha, hc = ha;
-                        if (avA) ha = sm.hint[halo + i - 1];
-                        if (avB) hb = sm.hint[halo + i - W];
-                        if (avC) hc = sm.hint[halo + i - W + (x + 1 < W ? 1 : -1)];
-                        const u32 own_lo = h.x, own_hi = h.y & 0xFFFFu;
-                        const bool uniform = avA && avB && avC &&
-                                             ha.x == own_lo && hb.x == own_lo && hc.x == own_lo &&
-                                             (ha.y & 0xFFFFu) == own_hi && (hb.y & 0xFFFFu) == own_hi &&
-                                             (hc.y & 0xFFFFu) == own_hi;
-                        int blen;
-                        if (uniform) {
-                            /* A = B = C = this MB: every predictor rule yields the MB's own MV -> mvd 0;
-                             * with ref 0 that is also exactly the inferred P_Skip motion */
-                            if (skip_spec && ref == 0) coded = 0;
-                            blen = encode_p16x16_body(ref, 0, 0, num_refs, e);
-                        } else {
-                            const Nbr a = nbr_from_hint(ha.x, ha.y), b = nbr_from_hint(hb.x, hb.y),
-                                      c = nbr_from_hint(hc.x, hc.y);
-                            const int mvx = (int)(int16_t)(h.x & 0xFFFFu), mvy = (int)(int16_t)(h.x >> 16);
-                            int px, py;
-                            predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
-                            if (skip_spec && ref == 0) {
-                                int sx, sy;
-                                skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
-                                if (mvx == sx && mvy == sy) coded = 0;
-                            }
-                            blen = encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
-                        }
-                        if (coded) {
-                            len = (u32)blen;
-                            if (!skip_spec) { kind = finish_inline_entry(e, 0x80000000u, 1, blen); len += 1u; }  /* ue(0), :630 */
-                        }
-                    } else {
-                        const u32 di = h.y >> 16;
-                        const u32 b0 = __ldg(tab + di), b1 = __ldg(tab + di + 1);
-                        e.w1 = b0; e.w2 = b1 - b0; e.w3 = ENT_DYN;
-                        len = e.w2;
-                        kind = KIND_DYN;
-                        if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }
-                    }
-                    sm.ent[i] = e;
+            for (int k = 0; k <= MPT; k++) own[k] = make_uint2(0u, 0u);
+#pragma unroll
+            for (int j = 0; j < MPT + 2; j++) abv[j] = make_uint2(0u, 0u);
+            if (nmb == MPT) {
+                const uint4 *src = (const uint4 *)(fh + g0);    /* hint_off even, g0 % 8 == 0: 16-byte aligned */
+#pragma unroll
+                for (int k = 0; k < MPT / 2; k++) {
+                    const uint4 v = __ldg(src + k);
+                    own[1 + 2 * k] = make_uint2(v.x, v.y);
+                    own[2 + 2 * k] = make_uint2(v.z, v.w);
                 }
-                sm.off[i] = len | (kind << OFF_KIND_SHIFT);
-                const u32 m = __ballot_sync(0xFFFFFFFFu, coded);
-                if (lane == 0) sm.mask[i >> 5] = m;
-                /* entries that can own whole output words are listed for the cooperative copy */
-                const bool listed = kind != KIND_SHORT;
-                const u32 lm = __ballot_sync(0xFFFFFFFFu, listed);
-                if (lm) {
-                    u32 base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.st.n_long, (u32)__popc(lm));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (listed) sm.longlist[base + __popc(lm & ((1u << lane) - 1u))] = (unsigned short)i;
-                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < MPT; k++)
+                    if (k < nmb) own[1 + k] = __ldg(fh + g0 + k);
             }
-            __syncthreads();
-
-            /* ---- mb_skip_run (SPEC mode) ----------------------------------- */
-            if (skip_spec) {
-                if (warp == 0) {
-                    const u32 m = sm.mask[lane];
-                    int v = m ? (t0 + 32 * lane + 31 - __clz((int)m)) : -1;
-                    int inc = v;
+            if (nmb > 0) {
+                if (g0 > 0) own[0] = __ldg(fh + g0 - 1);
+                const int a0 = g0 - W - 1;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        int t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                        if (lane >= d) inc = max(inc, t);
-                    }
-                    int exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-                    if (lane == 0) exc = -1;
-                    sm.prev[lane] = max(exc, sm.st.last_coded);
-                    if (lane == 31) sm.st.last_coded_next = max(inc, sm.st.last_coded);
-                }
-                __syncthreads();
+                for (int j = 0; j < MPT + 2; j++)
+                    if (a0 + j >= 0 && a0 + j < N) abv[j] = __ldg(fh + a0 + j);
+            }
+
+            /* ---- decide + code ------------------------------------------------ */
+            u64 code[MPT];
+            u32 meta[MPT];
+            u32 dynlen = 0;                                     /* payload bits of this thread's spliced MBs */
+            {
+                int y = W == 1 ? g0 : (int)__umulhi((u32)g0, w_magic), x = g0 - y * W;
 #pragma unroll
                 for (int k = 0; k < MPT; k++) {
-                    const int i = k * NT + tid;
-                    const u32 m = sm.mask[i >> 5];
-                    if ((m >> (i & 31)) & 1u) {
-                        const u32 below = m & ((1u << (i & 31)) - 1u);
-                        const int prev = below ? (t0 + (i & ~31) + 31 - __clz((int)below)) : sm.prev[i >> 5];
-                        const u32 run = (u32)(t0 + i - 1 - prev);
-                        u32 bits; int pn;
-                        encode_skip_prefix(run, bits, pn);
-                        const u32 lk = sm.off[i];
-                        u32 kind = lk >> OFF_KIND_SHIFT;
-                        const u32 blen = lk & OFF_MASK;
-                        if (kind == KIND_DYN) {
-                            sm.ent[i].w0 = bits;
-                            sm.ent[i].w3 |= (u32)pn;
+                    code[k] = 0; meta[k] = 0;
+                    if (k < nmb) {
+                        const uint2 h = own[1 + k];
+                        const u32 hk = (h.y >> 8) & 0xFFu;
+                        if (hk == H264GPU_MB_INTER) {
+                            const int avA = x > 0, avB = y > 0;
+                            const bool hasC = x + 1 < W;
+                            const int avC = avB && (hasC || x > 0);
+                            const uint2 c = hasC ? abv[k + 2] : abv[k];     /* C, else D (:391-399) */
+                            meta[k] = decide_inter(h.x, h.y, own[k].x, own[k].y, avA, abv[k + 1].x, abv[k + 1].y, avB,
+                                                   c.x, c.y, avC, num_refs, pred_spec, skip_spec, code[k]);
                         } else {
-                            MbEntry e = sm.ent[i];
-                            kind = finish_inline_entry(e, bits, pn, (int)blen);
-                            sm.ent[i] = e;
-                            if (kind == KIND_LONG) sm.longlist[atomicAdd(&sm.st.n_long, 1u)] = (unsigned short)i;
+                            const u32 di = h.y >> 16;
+                            const u32 b0 = __ldg(tab + di), b1 = __ldg(tab + di + 1);
+                            dynlen += b1 - b0;
+                            meta[k] = META_DYN | META_CODED;
+                            code[k] = (u64)di << 48;
                         }
-                        sm.off[i] = (blen + (u32)pn) | (kind << OFF_KIND_SHIFT);
                     }
+                    if (++x == W) { x = 0; y++; }
                 }
-                __syncthreads();
             }
 
-            /* ---- slice trailer: trailing mb_skip_run + rbsp_stop_one_bit ---- */
-            if (last && tid == 0) {
-                u32 bits = 0x80000000u; int pn = 1;
-                if (skip_spec) {
-                    const int lc = sm.st.last_coded_next;
-                    const u32 run_end = (u32)(N - 1 - lc);
-                    if (run_end > 0) {
-                        encode_skip_prefix(run_end, bits, pn);
-                        bits |= 1u << (31 - pn);
-                        pn += 1;
+            /* ---- mb_skip_run prefixes ------------------------------------------ */
+            int prev_in = -1, last_coded_total = -1;
+            if (skip_spec) {
+                int lc = -1;
+#pragma unroll
+                for (int k = 0; k < MPT; k++)
+                    if (meta[k] & META_CODED) lc = g0 + k;
+                prev_in = block_excl_scan_max(lc, (int *)sm.scan, last_coded_total);
+                prev_in = max(prev_in, sm.st.last_coded);
+                last_coded_total = max(last_coded_total, sm.st.last_coded);
+                int prev = prev_in;
+#pragma unroll
+                for (int k = 0; k < MPT; k++)
+                    if (meta[k] & META_CODED) {
+                        const u32 pre = (u32)(g0 + k - prev);              /* run + 1 */
+                        attach_prefix(code[k], meta[k], pre, 63 - 2 * __clz((int)pre));
+                        prev = g0 + k;
                     }
-                }
-                MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = 0;
-                sm.ent[n_real] = e;                            /* a KIND_SHORT entry */
-                sm.st.trailer_len = (u32)pn;
+            } else {
+#pragma unroll
+                for (int k = 0; k < MPT; k++)
+                    if (meta[k] & META_CODED) attach_prefix(code[k], meta[k], 1u, 1);   /* ue(0), :630 */
             }
 
-            /* ---- bit offsets: prefix sum of the lengths --------------------- */
+            /* ---- slice trailer: trailing mb_skip_run + rbsp_stop_one_bit ---------- */
+            const bool owns_trailer = last && nmb > 0 && g0 + nmb == N;
+            u32 tr_code = 1u, tr_len = 1u;
+            if (owns_trailer && skip_spec) {
+                const u32 run_end = (u32)(N - 1 - last_coded_total);
+                if (run_end > 0u) {
+                    const int pn = 63 - 2 * __clz((int)(run_end + 1u));
+                    tr_code = ((run_end + 1u) << 1) | 1u;
+                    tr_len = (u32)pn + 1u;
+                }
+            }
+
+            /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
+            u32 L = dynlen + (owns_trailer ? tr_len : 0u);
+#pragma unroll
+            for (int k = 0; k < MPT; k++) L += meta[k] & META_LEN_MASK;
             const u32 bitpos = sm.st.bitpos;
-            {
-                uint4 l = *(uint4 *)&sm.off[MPT * tid];
-                const u32 k0 = l.x & ~OFF_MASK, k1 = l.y & ~OFF_MASK, k2 = l.z & ~OFF_MASK, k3 = l.w & ~OFF_MASK;
-                l.x &= OFF_MASK; l.y &= OFF_MASK; l.z &= OFF_MASK; l.w &= OFF_MASK;
-                u32 sum4 = l.x + l.y + l.z + l.w, total;
-                u32 base = bitpos + block_excl_scan(sum4, sm.scan, total);
-                uint4 o;
-                o.x = base; o.y = base + l.x; o.z = o.y + l.y; o.w = o.z + l.z;
-                o.x |= k0; o.y |= k1; o.z |= k2; o.w |= k3;
-                *(uint4 *)&sm.off[MPT * tid] = o;
-                __syncthreads();
-                if (tid == 0) {
-                    u32 e0 = bitpos + total;
-                    sm.off[n_real] = e0;                       /* sentinel / trailer start (KIND_SHORT) */
-                    if (last) sm.off[n_real + 1] = e0 + sm.st.trailer_len;
-                }
-                __syncthreads();
-            }
-            const int n = last ? n_real + 1 : n_real;          /* entries; off[n] = end */
-            const u32 end = sm.off[n] & OFF_MASK;
+            u32 total;
+            const u32 O = bitpos + block_excl_scan(L, sm.scan, total);     /* the scan's barriers also publish the cleared window */
+            const u32 E = O + L;
+            const u32 end = bitpos + total;
             const u32 w_lo = bitpos >> 5;
-            const u32 total_bytes = (end + 7u) >> 3;           /* meaningful when last */
+            const u32 total_bytes = (end + 7u) >> 3;                       /* meaningful when last */
             const u32 w_end = end >> 5;
             const u32 w_stop = last ? ((total_bytes + 3u) >> 2) : w_end;   /* words [.., w_stop) are emitted */
             const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end;
-            const u32 cb0 = tile0 ? 0u : w_lo;
-            const u32 carry_in = sm.st.carry;
-            const u32 n_long = sm.st.n_long;
+            const u32 warp_end = __shfl_sync(FULL, E, 31);
+            bool first_pass = true;
 
-            for (u32 cb = cb0; cb <= w_last; cb += CH) {
-                chunk_tag = (chunk_tag + 1u) & 0xFFFFu;
-                if (chunk_tag == 0u) {                         /* tag wrapped: forget every stale marker */
-                    for (int jj = tid; jj < CH; jj += NT) sm.first[jj] = 0xFFFFFFFFu;
-                    chunk_tag = 1u;
+            for (u32 wbase = tile0 ? 0u : w_lo; wbase <= w_last; wbase += CH) {
+                if (!first_pass) {
+                    __syncthreads();
+                    uint4 *w4 = (uint4 *)sm.win;
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = z4;
+                    if (tid == 0) sm.st.n_copy = 0;
                     __syncthreads();
                 }
-                const u32 tagbits = chunk_tag << 16;
+                first_pass = false;
 
-                /* markers: for every word in which an entry starts, the first such entry */
-                for (int i = tid; i <= n; i += NT) {
-                    const u32 j = (sm.off[i] & OFF_MASK) >> 5;
-                    const bool first_in_word = (i == 0) || (((sm.off[i - 1] & OFF_MASK) >> 5) != j);
-                    if (first_in_word && j >= cb && j < cb + CH) sm.first[j - cb] = tagbits | (u32)i;
-                }
-                if (tile0 && cb + (u32)tid < w_lo)             /* words holding only header bits */
-                    sm.first[tid] = tagbits;
-                __syncthreads();
-
-                /* pack (a): words in which an entry starts -> gathered by one thread each */
-                const u32 j_hi = min(cb + CH, w_last + 1u);
-                for (u32 j = cb + tid; j < j_hi; j += NT) {
-                    const u32 fm = sm.first[j - cb];
-                    if ((fm & 0xFFFF0000u) != tagbits) continue;           /* interior word, see (b) */
-                    const u32 base = j << 5;
-                    u32 acc = tile0 ? (base < 40u + 256u ? header_bits32(sm.desc.hdr_bits, nal_header, base) : 0u)
-                                    : (j == w_lo ? carry_in : 0u);
-                    int i = (int)(fm & 0xFFFFu);
-                    if (i > 0) {
-                        const u32 o = sm.off[i - 1];
-                        if ((o >> OFF_KIND_SHIFT) == KIND_SHORT) acc |= short_contrib(sm.ent[i - 1].w0, o & OFF_MASK, base);
-                        else acc |= entry_contrib(sm.ent[i - 1], o & OFF_MASK, base, pay_words, n_pay_words);
+                /* ---- write: sequential bit writer per thread ------------------------- */
+                BitPut bp;
+                bp_init(bp, (tile0 && tid == 0) ? 0u : O);
+                const u32 key = bp.j;
+                if (tile0 && tid == 0) {
+                    for (u32 p = 0; p < hdr_total; p += 32u) {
+                        const u32 n = min(32u, hdr_total - p);
+                        bp_put(bp, (u64)(header_bits32(sm.desc.hdr_bits, nal_header, p) >> (32u - n)), n, sm.win, wbase, CH);
                     }
-                    while (i < n) {
-                        const u32 o = sm.off[i];
-                        if ((o & OFF_MASK) >= base + 32u) break;
-                        if ((o >> OFF_KIND_SHIFT) == KIND_SHORT) acc |= short_contrib(sm.ent[i].w0, o & OFF_MASK, base);
-                        else acc |= entry_contrib(sm.ent[i], o & OFF_MASK, base, pay_words, n_pay_words);
-                        i++;
-                    }
-                    if (j < w_stop) sm.out[j - cb] = acc;
-                    else sm.st.carry_next = acc;               /* partial word, carried into the next tile */
                 }
-                /* pack (b): words lying wholly inside one long entry -> a warp per entry, a lane per word */
-                for (u32 d = warp; d < n_long; d += NW) {
-                    const int i = sm.longlist[d];
-                    const u32 o = sm.off[i] & OFF_MASK;
-                    const u32 o_next = sm.off[i + 1] & OFF_MASK;
-                    u32 ja = (o >> 5) + 1u, jb = o_next >> 5;              /* interior words [ja, jb) */
-                    if (ja < cb) ja = cb;
-                    if (jb > cb + CH) jb = cb + CH;
-                    if (ja >= jb) continue;
-                    const MbEntry e = sm.ent[i];
-                    for (u32 j = ja + lane; j < jb; j += 32)
-                        sm.out[j - cb] = entry_contrib(e, o, j << 5, pay_words, n_pay_words);
-                }
-                __syncthreads();
-
-                /* ---- emulation prevention + store of words [cb, e_hi) ------ */
-                const u32 e_hi = min(cb + CH, w_stop);
-                const int cw = e_hi > cb ? (int)(e_hi - cb) : 0;
-                const u32 chunk_byte0 = cb << 2;
-                const int zc_in = sm.st.zc;
-                const u32 ins_in = sm.st.ins_total;
-                const int chunk_bytes = last ? (int)(min(e_hi << 2, total_bytes) - chunk_byte0) : cw * 4;
-                u32 wv[WPT];
-                bool cand = false;
+                {
+                    int prev = prev_in;
 #pragma unroll
-                for (int it = 0; it < WPT; it++) {
-                    const int jj = it * NT + tid;
-                    wv[it] = 0xFFFFFFFFu;
-                    if (jj < cw) {
-                        const u32 w = sm.out[jj];
-                        wv[it] = w;
-                        const u32 j = cb + jj;
-                        /* protection needs two zero bytes in a row somewhere in the chunk */
-                        bool c = zero_byte_mask(j == 1u ? (w | 0xFF000000u) : w) != 0u;
-                        if (j == 0u) c = false;
-                        cand = cand || c;
-                    }
-                }
-                if (tid == 0 && zc_in > 0) cand = true;
-                const int any_cand = __syncthreads_or(cand);
-                u32 masks = 0;
-                int any_ins = 0;
-                if (any_cand) {
-                    int running_nz = -1 - zc_in;                           /* carried automaton state */
-#pragma unroll
-                    for (int it = 0; it < WPT; it++) {
-                        if (it * NT < cw) {
-                            const int jj = it * NT + tid;
-                            const int vb = jj < cw ? min(4, chunk_bytes - 4 * jj) : 0;
-                            const int lnz = word_last_nonzero(wv[it], vb, 4 * jj);
-                            int tot;
-                            int prev_nz = block_excl_scan_max(lnz, EPB_NONE, (int *)sm.scan, tot);
-                            prev_nz = max(prev_nz, running_nz);
-                            if (vb > 0) masks |= epb_word_mask(wv[it], vb, 4 * jj, chunk_byte0, prev_nz) << (4 * it);
-                            running_nz = max(running_nz, tot);
-                        }
-                    }
-                    any_ins = __syncthreads_or(masks != 0u);
-                    if (tid == 0) {
-                        const int r_end = chunk_bytes - 1 - running_nz;    /* zero bytes closing the chunk */
-                        sm.st.zc_next = r_end == 0 ? 0 : ((r_end & 1) ? 1 : 2);
-                    }
-                } else if (tid == 0) sm.st.zc_next = 0;
-
-                u32 running = ins_in;
-#pragma unroll
-                for (int it = 0; it < WPT; it++) {
-                    if (it * NT < cw) {
-                        const int jj = it * NT + tid;
-                        const u32 mk = (masks >> (4 * it)) & 0xFu;
-                        u32 before = running;
-                        if (any_ins) {
-                            u32 tot;
-                            before += block_excl_scan(jj < cw ? (u32)__popc(mk) : 0u, sm.scan, tot);
-                            running += tot;
-                        }
-                        const int vb = jj < cw ? min(4, chunk_bytes - 4 * jj) : 0;
-                        const u32 w = wv[it];
-                        /* a warp covers 32 consecutive words: without insertions (and no partial tail word)
-                         * they move as re-aligned 32-bit words, otherwise byte by byte */
-                        const bool byte_path = __any_sync(0xFFFFFFFFu, vb > 0 && (mk != 0u || vb < 4));
-                        const u32 prevw = __shfl_up_sync(0xFFFFFFFFu, w, 1);
-                        const u32 nextvb = __shfl_down_sync(0xFFFFFFFFu, (u32)vb, 1);
-                        if (vb > 0) {
-                            const u32 src_byte = chunk_byte0 + 4u * (u32)jj;
-                            if (byte_path) {
-                                u32 pos = src_byte + before;
-                                for (int k = 0; k < vb; k++) {
-                                    if ((mk >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                                    if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
-                                    pos++;
-                                }
+                    for (int k = 0; k < MPT; k++) {
+                        const u32 m = meta[k];
+                        if (m & META_CODED) {
+                            const u32 n = m & META_LEN_MASK;
+                            if (!(m & (META_DYN | META_LONG | META_SPLIT))) {
+                                bp_put(bp, code[k], n, sm.win, wbase, CH);
                             } else {
-                                const u32 sft = before & 3u;
-                                if (sft == 0u) {
-                                    const u32 pos = src_byte + before;
-                                    if (pos + 4u <= cap) fout32[pos >> 2] = bswap32(w);
+                                const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
+                                const u32 pn = 63u - 2u * (u32)__clz((int)pre);
+                                bp_put(bp, (u64)pre, pn, sm.win, wbase, CH);
+                                if (m & META_SPLIT) {
+                                    bp_put(bp, code[k], n - pn, sm.win, wbase, CH);
+                                } else if (m & META_LONG) {
+                                    MbEntry e;
+                                    int bl = encode_p16x16_body((int)(m >> META_REF_SHIFT), long_dx(code[k]), long_dy(code[k]), num_refs, e);
+                                    bp_put(bp, (u64)e.w1, 32u, sm.win, wbase, CH);
+                                    bp_put(bp, (u64)e.w2, 32u, sm.win, wbase, CH);
+                                    bl -= 64;
+                                    bp_put(bp, (u64)(e.w3 >> (32 - bl)), (u32)bl, sm.win, wbase, CH);
                                 } else {
-                                    const bool head = (lane == 0);
-                                    const bool tail = (lane == 31) || (nextvb == 0u);
-                                    if (!head) {
-                                        /* out word covering source bytes [src_byte - sft, src_byte - sft + 4) */
-                                        const u32 v = (prevw << (8u * (4u - sft))) | (w >> (8u * sft));
-                                        const u32 pos = src_byte - sft + before;
-                                        if (pos + 4u <= cap) fout32[pos >> 2] = bswap32(v);
-                                    } else {
-                                        u32 pos = src_byte + before;
-                                        for (u32 k = 0; k < 4u - sft; k++, pos++)
-                                            if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
+                                    /* spliced MB: partial words through the writer, whole words through the copy list */
+                                    const u32 di = (u32)(code[k] >> 48);
+                                    const u32 b0 = __ldg(tab + di), len = __ldg(tab + di + 1) - b0;
+                                    const u32 hb = min(len, (32u - bp.fill) & 31u);
+                                    if (hb) bp_put(bp, (u64)(payload_ld32(pay_words, n_pay_words, b0) >> (32u - hb)), hb, sm.win, wbase, CH);
+                                    const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31u;
+                                    if (nw) {
+                                        const u32 slot = atomicAdd(&sm.st.n_copy, 1u);
+                                        if (slot < (u32)LCAP) sm.copy[slot] = make_uint4(bp.j, b0 + hb, nw, 0u);
+                                        else
+                                            for (u32 i = 0; i < nw; i++)
+                                                if (bp.j + i - wbase < (u32)CH)
+                                                    sm.win[bp.j + i - wbase] = payload_ld32(pay_words, n_pay_words, b0 + hb + 32u * i);
+                                        bp.j += nw;
                                     }
-                                    if (tail) {
-                                        u32 pos = src_byte + 4u - sft + before;
-                                        for (u32 k = 4u - sft; k < 4u; k++, pos++)
-                                            if (pos < cap) fout[pos] = (uint8_t)(w >> (24 - 8 * k));
-                                    }
+                                    if (tb) bp_put(bp, (u64)(payload_ld32(pay_words, n_pay_words, b0 + len - tb) >> (32u - tb)), tb, sm.win, wbase, CH);
                                 }
                             }
+                            prev = g0 + k;
                         }
                     }
                 }
+                if (owns_trailer) bp_put(bp, (u64)tr_code, tr_len, sm.win, wbase, CH);
+                u32 T = 0, tj = 0;
+                bool has_tail = false;
+                if (bp.fill) {
+                    if (bp.head) bp.H = bp.acc;
+                    else { T = bp.acc; tj = bp.j; has_tail = true; }
+                }
+
+                /* ---- merge the partial words of neighbouring threads (segmented suffix OR) ---- */
+                {
+                    u32 X = bp.H;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u32 v = __shfl_down_sync(FULL, X, d);
+                        const u32 kk = __shfl_down_sync(FULL, key, d);
+                        if (lane + d < 32 && kk == key) X |= v;
+                    }
+                    const u32 Xn = __shfl_down_sync(FULL, X, 1);
+                    const u32 kn = __shfl_down_sync(FULL, key, 1);
+                    if (has_tail && tj - wbase < (u32)CH) {
+                        u32 v = T;
+                        if (lane < 31 && kn == tj) v |= Xn;
+                        if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps add to this word */
+                        else sm.win[tj - wbase] = v;
+                    }
+                    if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], X);
+                }
                 __syncthreads();
-                if (tid == 0) {
-                    sm.st.ins_total = running;
-                    if (cw > 0) sm.st.zc = sm.st.zc_next;
+
+                /* ---- splice: whole words of spliced MBs, 8 lanes per entry ------------------ */
+                {
+                    const u32 n_copy = min(sm.st.n_copy, (u32)LCAP);
+                    const u32 sub = (u32)tid & 7u;
+                    for (u32 d = (u32)tid >> 3; d < n_copy; d += NT / 8) {
+                        const uint4 c = sm.copy[d];
+                        for (u32 i = sub; i < c.z; i += 8u) {
+                            const u32 j = c.x + i - wbase;
+                            if (j < (u32)CH) sm.win[j] = payload_ld32(pay_words, n_pay_words, c.y + 32u * i);
+                        }
+                    }
+                    if (n_copy) __syncthreads();
+                }
+
+                /* ---- emit: emulation prevention + store of words [wbase, e_hi) -------------- */
+                const u32 e_hi = min(wbase + CH, w_stop);
+                const u32 chunk_byte0 = wbase << 2;
+                const int chunk_bytes = e_hi > wbase ? (int)((last ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+                for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NT) {
+                    const int q = q0 + tid;
+                    const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+                    const int vb_next = tid == NT - 1 ? 0 : min(max(chunk_bytes - 16 * (q + 1), 0), 16);
+                    uint4 w = make_uint4(FULL, FULL, FULL, FULL);
+                    u32 wn = 0;
+                    if (vb > 0) { w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4]; }
+                    u32 z = zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12);
+                    const u32 valid = (1u << vb) - 1u;
+                    z &= valid;
+                    u32 keep = valid;                                      /* bytes that may take an insertion */
+                    if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
+                    const bool b0_le3 = (w.x >> 26) == 0u && (keep & 1u);
+                    sm.tr[tid] = epb_group_trail(z, max(vb, 1), 0u) | (z == valid ? 0x100u : 0u);
+                    __syncthreads();
+                    /* zero bytes right before the group: walk back over all-zero groups */
+                    u32 rin = 0;
+                    const bool need = vb > 0 && (b0_le3 || (z & 1u));
+                    if (need) {
+                        int u = tid - 1;
+                        for (;;) {
+                            if (u < 0) { rin += sm.st.zrun; break; }
+                            const u32 t = sm.tr[u];
+                            rin += t & 0xFFu;
+                            if (!(t & 0x100u)) break;
+                            u--;
+                        }
+                    }
+                    u32 ins = 0;
+                    if (vb > 0 && (need || (z & (z << 1)))) {
+                        u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
+                                 (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
+                        ins = epb_group_mask(z, m3 & keep, vb, rin);
+                    }
+                    const u32 cnt = (u32)__popc(ins);
+                    /* the thread holding the last valid byte carries the zero run on */
+                    if (vb > 0 && vb_next == 0) {
+                        u32 r2 = rin;
+                        if (z == valid && !need) {                          /* all-zero group that did not need rin yet */
+                            r2 = 0;
+                            int u = tid - 1;
+                            for (;;) {
+                                if (u < 0) { r2 += sm.st.zrun; break; }
+                                const u32 t = sm.tr[u];
+                                r2 += t & 0xFFu;
+                                if (!(t & 0x100u)) break;
+                                u--;
+                            }
+                        }
+                        sm.st.zrun_next = epb_group_trail(z, vb, r2);
+                    }
+                    sm.gi[tid] = (cnt << 8) | (u32)vb;
+                    const int any_ins = __syncthreads_or(cnt != 0u);
+                    u32 before = sm.st.ins_total, pass_ins = 0;
+                    if (any_ins) before += block_excl_scan(cnt, sm.scan, pass_ins);
+                    if (vb > 0) {
+                        const u32 D = chunk_byte0 + 16u * (u32)q + before;          /* output byte of the group's first byte */
+                        const bool clean = cnt == 0u && vb == 16;
+                        bool prev_clean = tid > 0, next_clean = tid < NT - 1 && vb_next == 16;
+                        if (any_ins) {
+                            if (tid > 0) prev_clean = sm.gi[tid - 1] == 16u;
+                            if (tid < NT - 1) next_clean = sm.gi[tid + 1] == 16u;
+                        }
+                        if (clean) {
+                            const u32 s = (4u - (D & 3u)) & 3u;                     /* source bytes before the first aligned word */
+                            if (s && !prev_clean)
+                                for (u32 k = 0; k < s; k++)
+                                    if (D + k < cap) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
+                            const u32 sel = realign_selector(s);
+                            u32 *dst = fout32 + ((D + s) >> 2);
+                            const u32 o0 = __byte_perm(w.x, w.y, sel), o1 = __byte_perm(w.y, w.z, sel),
+                                      o2 = __byte_perm(w.z, w.w, sel), o3 = __byte_perm(w.w, wn, sel);
+                            if (D + s + 16u <= cap && (s == 0u || next_clean)) {
+                                dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                            } else {
+                                if (D + s + 4u <= cap) dst[0] = o0;
+                                if (D + s + 8u <= cap) dst[1] = o1;
+                                if (D + s + 12u <= cap) dst[2] = o2;
+                                /* the straddling word: own bytes only */
+                                const u32 nb = s ? 4u - s : 4u;
+                                for (u32 k = 0; k < nb; k++)
+                                    if (D + s + 12u + k < cap) fout[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
+                            }
+                        } else {
+                            u32 pos = D;
+                            const u32 ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int k = 0; k < 16; k++)
+                                if (k < vb) {
+                                    if ((ins >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
+                                    if (pos < cap) fout[pos] = (uint8_t)(ws[k >> 2] >> (24 - 8 * (k & 3)));
+                                    pos++;
+                                }
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        sm.st.ins_total += pass_ins;
+                        sm.st.zrun = sm.st.zrun_next;
+                    }
                 }
                 __syncthreads();
             }
 
+            __syncthreads();
             if (tid == 0) {
                 sm.st.bitpos = end;
-                sm.st.carry = sm.st.carry_next;
-                if (skip_spec) sm.st.last_coded = sm.st.last_coded_next;
-                sm.st.n_long = 0;
+                if (!last) {
+                    const u32 cw = (tile0 ? 0u : w_lo) + ((w_end - (tile0 ? 0u : w_lo)) / CH) * CH;   /* base of the pass holding w_end */
+                    sm.st.carry = sm.win[w_end - cw];
+                }
+                if (skip_spec) sm.st.last_coded = last_coded_total;
+                sm.st.n_copy = 0;
                 if (last) sizes[f] = total_bytes + sm.st.ins_total;
             }
             __syncthreads();

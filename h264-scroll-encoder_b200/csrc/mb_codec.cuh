@@ -395,5 +395,195 @@ HSD int epb_state_after(const u32 *words, int nbytes, u32 chunk_byte0, int zc_in
     return r == 0 ? 0 : ((r & 1) ? 1 : 2);
 }
 
+
+/* ======================================================================
+ * Register pipeline (compose kernel v3): every thread owns MPT consecutive
+ * macroblocks, keeps their codes in registers and appends them to the slice
+ * with a sequential bit writer.  Pure functions, shared with tests/emu.
+ * ==================================================================== */
+
+/* packed int16x2 max / min (mv_x in the low half, mv_y in the high half) */
+HSD u32 vmax2(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(a, b);
+#else
+    int16_t al = (int16_t)(a & 0xFFFF), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xFFFF), bh = (int16_t)(b >> 16);
+    return (u32)(uint16_t)(al > bl ? al : bl) | ((u32)(uint16_t)(ah > bh ? ah : bh) << 16);
+#endif
+}
+HSD u32 vmin2(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __vmins2(a, b);
+#else
+    int16_t al = (int16_t)(a & 0xFFFF), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xFFFF), bh = (int16_t)(b >> 16);
+    return (u32)(uint16_t)(al < bl ? al : bl) | ((u32)(uint16_t)(ah < bh ? ah : bh) << 16);
+#endif
+}
+
+/* per-MB register record: `meta` beside a 64-bit `code` */
+#define META_LEN_MASK  0x0000FFFFu   /* bits this MB appends through the bit writer (prefix + inline body) */
+#define META_DYN       0x00010000u   /* spliced MB: code = prefix, the payload follows */
+#define META_LONG      0x00020000u   /* inline body > 64 bits: code = packed (mvd_x, mvd_y), rebuilt when written */
+#define META_SPLIT     0x00040000u   /* body <= 64 bits but prefix + body > 64: code = body, prefix put separately */
+#define META_CODED     0x00080000u   /* not P_Skip */
+#define META_REF_SHIFT 24
+
+/* neighbour-visible motion of a hint: packed mv + ref key (0x100 = unavailable, never matches) */
+HSD void nbr_view(u32 lo, u32 hi, int av, u32 &mv, u32 &ref) {
+    const bool intra = ((hi >> 8) & 0xFFu) == H264GPU_MB_DYN_INTRA;
+    mv = (av && !intra) ? lo : 0u;
+    ref = av ? (intra ? 255u : (hi & 0xFFu)) : 0x100u;
+}
+
+/*
+ * MV predictor on packed int16x2 values (src/h264_writer.c:369-432; spec = H.264 8.4.1.3).
+ * Unavailable neighbours carry mv 0 / ref 0x100.  With zero or one neighbour available and no
+ * ref match the reference returns 0, which is what min(max(a,b),c) gives with the zeros in place.
+ */
+HSD u32 predict_packed(int spec, u32 mva, u32 ra, u32 mvb, u32 rb, u32 mvc, u32 rc, int only_a, u32 ref) {
+    if (spec && only_a) { mvb = mva; mvc = mva; rb = ra; rc = ra; }
+    const int ma = ra == ref, mb = rb == ref, mc = rc == ref;
+    u32 med = vmin2(vmax2(mva, mvb), mvc);                 /* the reference's median3 (:362-367) */
+    if (spec) med = vmax2(vmin2(mva, mvb), med);           /* the true median */
+    const u32 single = ma ? mva : (mb ? mvb : mvc);
+    return (ma + mb + mc == 1) ? single : med;
+}
+
+/* se(v): value written (code number + 1) and its bit count */
+HSD u32 se_codeval(int v, int &n) {
+    const u32 t = (u32)v << 1;
+    const u32 cv = v > 0 ? t : 1u - t;
+    n = 63 - 2 * clz32(cv);
+    return cv;
+}
+
+/* body '1' te(ref) se(dx) se(dy) '1' right aligned in 64 bits; returns its length (body valid when <= 64) */
+HSD int inline_body64(int ref, int dx, int dy, int num_refs, u64 &body) {
+    int nx, ny, rl = 0;
+    u32 rc = 0;
+    const u32 cx = se_codeval(dx, nx), cy = se_codeval(dy, ny);
+    if (num_refs == 2) { rc = (u32)(~ref) & 1u; rl = 1; }
+    else if (num_refs > 2) { rc = (u32)ref + 1u; rl = 63 - 2 * clz32(rc); }
+    const int blen = 2 + rl + nx + ny;
+    if (blen <= 32) {
+        u32 v = (1u << rl) | rc;
+        v = (v << nx) | cx;
+        v = (v << ny) | cy;
+        body = (u64)((v << 1) | 1u);
+    } else if (blen <= 64) {
+        u64 v = ((u64)1 << rl) | rc;
+        v = (v << nx) | cx;
+        v = (v << ny) | cy;
+        body = (v << 1) | 1u;
+    } else body = 0;
+    return blen;
+}
+
+/*
+ * One inter macroblock: neighbours -> predictor -> P_Skip test -> mvd -> body.
+ * lo/hi words of the own hint and of A, B, C(D); av* availability.
+ * Returns meta (length, flags, ref) and the 64-bit code (no mb_skip_run prefix yet).
+ */
+HSD u32 decide_inter(u32 hlo, u32 hhi, u32 alo, u32 ahi, int avA, u32 blo, u32 bhi, int avB,
+                     u32 clo, u32 chi, int avC, int num_refs, int pred_spec, int skip_spec, u64 &code) {
+    const u32 ref = hhi & 0xFFu;
+    u32 mva, ra, mvb, rb, mvc, rc;
+    nbr_view(alo, ahi, avA, mva, ra);
+    nbr_view(blo, bhi, avB, mvb, rb);
+    nbr_view(clo, chi, avC, mvc, rc);
+    const u32 pred = predict_packed(pred_spec, mva, ra, mvb, rb, mvc, rc, avA && !avB && !avC, ref);
+    if (skip_spec && ref == 0u) {
+        /* H.264 8.4.1.1: the inferred motion of P_Skip */
+        const bool zero = !avA || !avB || (ra == 0u && mva == 0u) || (rb == 0u && mvb == 0u);
+        if (hlo == (zero ? 0u : pred)) { code = 0; return 0u; }
+    }
+    const int dx = (int)(int16_t)(hlo & 0xFFFFu) - (int)(int16_t)(pred & 0xFFFFu);
+    const int dy = (int)(int16_t)(hlo >> 16) - (int)(int16_t)(pred >> 16);
+    const int blen = inline_body64((int)ref, dx, dy, num_refs, code);
+    u32 meta = (u32)blen | META_CODED | (ref << META_REF_SHIFT);
+    if (blen > 64) {
+        code = (u64)((u32)dx & 0x3FFFFu) | ((u64)((u32)dy & 0x3FFFFu) << 18);
+        meta |= META_LONG;
+    }
+    return meta;
+}
+
+HSD int long_dx(u64 code) { return ((int)((u32)code << 14)) >> 14; }
+HSD int long_dy(u64 code) { return ((int)((u32)(code >> 18) << 14)) >> 14; }
+
+/* attach the mb_skip_run prefix ue(run) (value pre = run+1 in pn bits) to a record */
+HSD void attach_prefix(u64 &code, u32 &meta, u32 pre, int pn) {
+    const u32 blen = meta & META_LEN_MASK;
+    if (!(meta & META_LONG)) {
+        if (blen + (u32)pn <= 64u) code |= (u64)pre << blen;
+        else meta |= META_SPLIT;
+    }
+    meta += (u32)pn;
+}
+
+/* ---- sequential bit writer ------------------------------------------- */
+
+struct BitPut {
+    u32 acc;      /* bits of the word being assembled, from the MSB down */
+    u32 fill;     /* bits used in acc, 0..31 */
+    u32 j;        /* frame word index of acc */
+    u32 head;     /* the string started mid-word and that first word is not complete yet */
+    u32 H;        /* head partial: this thread's bits of the word its string starts in */
+};
+
+HSD void bp_init(BitPut &p, u32 bit) {
+    p.acc = 0; p.fill = bit & 31u; p.j = bit >> 5; p.head = p.fill != 0u; p.H = 0;
+}
+
+HSD void bp_flush(BitPut &p, u32 word, u32 *win, u32 wbase, u32 wcap) {
+    if (p.head) { p.H = word; p.head = 0; }
+    else if (p.j - wbase < wcap) win[p.j - wbase] = word;
+    p.j++;
+}
+
+/* append the low n (1..64) bits of code (bits above n must be zero) */
+HSD void bp_put(BitPut &p, u64 code, u32 n, u32 *win, u32 wbase, u32 wcap) {
+    const u64 t = code << (64u - n);
+    const u64 a = ((u64)p.acc << 32) | (t >> p.fill);
+    const u32 total = p.fill + n;
+    if (total < 32u) { p.acc = (u32)(a >> 32); p.fill = total; return; }
+    bp_flush(p, (u32)(a >> 32), win, wbase, wcap);
+    if (total < 64u) { p.acc = (u32)a; p.fill = total - 32u; return; }
+    bp_flush(p, (u32)a, win, wbase, wcap);
+    p.acc = p.fill ? (u32)((t << (64u - p.fill)) >> 32) : 0u;
+    p.fill = total - 64u;
+}
+
+/* ---- emulation prevention on 16-byte groups --------------------------- */
+
+/* zero-byte flags of an MSB-first word as a nibble: bit k = k-th stream byte is zero */
+HSD u32 zero_nib(u32 w) { return ((zero_byte_mask(w) >> 7) * 0x80402010u) >> 28; }
+
+/*
+ * Insert mask of a group (src/nal.c:24-50 in closed form): z = zero-byte mask (bit i = stream
+ * byte i), m3 = bytes <= 3, vb = valid bytes (1..16), rin = zero bytes immediately before the
+ * group.  0x03 goes before byte p iff byte p <= 3 and the zero run ending at p-1 has an even
+ * length >= 2.  Runs are classified by the parity of their start with one carry-propagating add.
+ */
+HSD u32 epb_group_mask(u32 z, u32 m3, int vb, u32 rin) {
+    const u32 r = rin >= 2u ? 2u + (rin & 1u) : rin;       /* keeps ">= 2" and the parity */
+    const u32 valid = (1u << vb) - 1u;
+    const u32 ze = ((z & valid) << 4) | (((1u << r) - 1u) << (4u - r));
+    const u32 s = ze & ~(ze << 1);                          /* run starts */
+    const u32 re = ze & ~(ze + (s & 0x55555555u));          /* bytes of runs that start at an even position */
+    const u32 ro = ze & ~re;
+    const u32 e = (((re << 1) & (re << 2)) & 0x55555555u) | (((ro << 1) & (ro << 2)) & 0xAAAAAAAAu);
+    return (e >> 4) & m3 & valid;
+}
+
+/* zero bytes closing a group of vb valid bytes (rin added when the whole group is zero) */
+HSD u32 epb_group_trail(u32 z, int vb, u32 rin) {
+    const u32 t = ~z & ((1u << vb) - 1u);
+    return t ? (u32)(vb - 32 + clz32(t)) : (u32)vb + rin;
+}
+
+/* byte-permute selector: output word = stream bytes s..s+3 of the MSB-first pair (a, b) */
+HSD u32 realign_selector(u32 s) { return (u32)((0x5670670170120123ull >> (16u * s)) & 0xFFFFu); }
+
 } /* namespace h264scroll */
 #endif

@@ -1,10 +1,11 @@
 /*
  * emu_compose.cpp - TEST ONLY.  Sequential CPU emulation of the tile pipeline of
- * csrc/compose_kernels.cu (load -> decide -> skiprun -> scan -> pack -> epb),
- * built on the very same mb_codec.cuh helpers the kernel uses.  It lets the
- * CPU test-suite check the bit-level logic (entry layout, word-owned gather,
- * chunking, closed-form emulation prevention) against the oracle without a GPU,
- * and with tiny TILE / CH values that force every boundary case.
+ * csrc/compose_kernels.cu (load -> decide -> skiprun -> scan -> write -> splice -> emit),
+ * built on the very same mb_codec.cuh helpers the kernel uses (decide_inter, attach_prefix,
+ * BitPut, epb_group_mask, realign_selector ...).  "Threads" are walked one after the other;
+ * the warp-shuffle merge of partial words becomes a plain OR into the window.  It lets the
+ * CPU test-suite check the bit-level logic against the oracle without a GPU, with tiny
+ * thread counts / window sizes that force every boundary case.
  *
  * Not part of the product: nothing outside tests/ builds or loads this file.
  */
@@ -17,11 +18,21 @@
 using namespace h264scroll;
 
 struct H2 { u32 x, y; };
+static const int MPT = 8;
+
+static u32 pay32(const u32 *pw, u32 n_words, u32 p) { return payload_bits32(pw, n_words, p); }
+
+static u32 byte_perm(u32 a, u32 b, u32 sel) {
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    u32 r = 0;
+    for (int k = 0; k < 4; k++) r |= (u32)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+}
 
 extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264GpuMbHint *hints_base,
                                       const H264GpuDynDesc *dyns, const uint32_t *dyn_tab,
                                       const uint8_t *payload, uint8_t *out_base,
-                                      int TILE, int CH) {
+                                      int NTHREADS, int CH) {
     const H264GpuFrameDesc &d = *desc;
     const int W = d.mb_w, N = W * (int)d.mb_h;
     const int num_refs = d.num_refs;
@@ -38,194 +49,238 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
         n_pay_words = (dd.payload_bytes + 3u) >> 2;
     }
     uint8_t *fout = out_base + d.out_off;
+    const int TILE = NTHREADS * MPT;
+    const u32 hdr_total = 40u + d.hdr_nbits;
 
-    u32 bitpos = 40u + d.hdr_nbits, carry = 0, ins_total = 0;
-    int last_coded = -1, zc = 0;
+    u32 bitpos = hdr_total, carry = 0, ins_total = 0, zrun = 0;
+    int last_coded = -1;
     u32 size = 0;
+    const H2 zero_h = {0, 0};
+    auto H = [&](int g) -> H2 { return (g >= 0 && g < N) ? fh[g] : zero_h; };
 
-    std::vector<MbEntry> ent(TILE + 1);
-    std::vector<u32> off(TILE + 4);
-    std::vector<int> codedv(TILE);
-    std::vector<u32> kinds(TILE + 2, KIND_SHORT);
-    std::vector<u32> outw(CH);
-    std::vector<int> first(CH);
+    std::vector<u64> code(TILE);
+    std::vector<u32> meta(TILE), dynlen(NTHREADS), Lv(NTHREADS), Ov(NTHREADS);
+    std::vector<int> previn(NTHREADS);
+    std::vector<u32> win(CH + 8);
 
     for (int t0 = 0; t0 < N; t0 += TILE) {
-        const int n_real = std::min(TILE, N - t0);
         const bool last = (t0 + TILE >= N), tile0 = (t0 == 0);
-
-        /* decide + code (neighbours read straight from the frame's hint map) */
-        for (int i = 0; i < TILE; i++) {
-            const int g = t0 + i;
-            int coded = 0;
-            u32 len = 0, kind = KIND_SHORT;
-            if (i < n_real) {
-                const H2 h = fh[g];
-                const u32 hk = (h.y >> 8) & 0xFFu;
-                MbEntry e; e.w0 = e.w1 = e.w2 = e.w3 = 0;
-                coded = 1;
-                if (hk == H264GPU_MB_INTER) {
-                    const int y = g / W, x = g - y * W;
-                    const int ref = (int)(h.y & 0xFFu);
-                    Nbr a = {0, 0, 0}, b = {0, 0, 0}, c = {0, 0, 0};
-                    const int avA = x > 0, avB = y > 0;
-                    int avC = 0;
-                    if (avA) a = nbr_from_hint(fh[g - 1].x, fh[g - 1].y);
-                    if (avB) {
-                        b = nbr_from_hint(fh[g - W].x, fh[g - W].y);
-                        if (x + 1 < W) { c = nbr_from_hint(fh[g - W + 1].x, fh[g - W + 1].y); avC = 1; }
-                        else if (x > 0) { c = nbr_from_hint(fh[g - W - 1].x, fh[g - W - 1].y); avC = 1; }
-                    }
-                    const int mvx = (int)(int16_t)(h.x & 0xFFFFu), mvy = (int)(int16_t)(h.x >> 16);
-                    int px, py;
-                    /* the kernel's uniform-neighbourhood shortcut: A = B = C = own hint */
-                    const int cidx = x + 1 < W ? g - W + 1 : g - W - 1;
-                    const bool uniform = avA && avB && avC &&
-                        fh[g - 1].x == h.x && fh[g - W].x == h.x && fh[cidx].x == h.x &&
-                        (fh[g - 1].y & 0xFFFFu) == (h.y & 0xFFFFu) && (fh[g - W].y & 0xFFFFu) == (h.y & 0xFFFFu) &&
-                        (fh[cidx].y & 0xFFFFu) == (h.y & 0xFFFFu);
-                    if (uniform) {
-                        px = mvx; py = mvy;
-                        if (skip_spec && ref == 0) coded = 0;
+        /* decide */
+        for (int t = 0; t < NTHREADS; t++) {
+            const int g0 = t0 + t * MPT;
+            const int nmb = std::min(std::max(N - g0, 0), MPT);
+            dynlen[t] = 0;
+            for (int k = 0; k < MPT; k++) {
+                u64 c = 0; u32 m = 0;
+                if (k < nmb) {
+                    const int g = g0 + k, y = g / W, x = g - y * W;
+                    const H2 h = H(g);
+                    if (((h.y >> 8) & 0xFF) == H264GPU_MB_INTER) {
+                        const int avA = x > 0, avB = y > 0;
+                        const bool hasC = x + 1 < W;
+                        const int avC = avB && (hasC || x > 0);
+                        const H2 a = H(g - 1), b = H(g - W), cc = hasC ? H(g - W + 1) : H(g - W - 1);
+                        m = decide_inter(h.x, h.y, a.x, a.y, avA, b.x, b.y, avB, cc.x, cc.y, avC,
+                                         num_refs, pred_spec, skip_spec, c);
                     } else {
-                        predict_mv(pred_spec, a, avA, b, avB, c, avC, ref, px, py);
-                        if (skip_spec && ref == 0) {
-                            int sx, sy;
-                            skip_infer_mv(pred_spec, a, avA, b, avB, c, avC, sx, sy);
-                            if (mvx == sx && mvy == sy) coded = 0;
-                        }
+                        const u32 di = h.y >> 16;
+                        dynlen[t] += tab[di + 1] - tab[di];
+                        m = META_DYN | META_CODED;
+                        c = (u64)di << 48;
                     }
-                    if (coded) {
-                        int blen = encode_p16x16_body(ref, mvx - px, mvy - py, num_refs, e);
-                        len = (u32)blen;
-                        if (!skip_spec) { kind = finish_inline_entry(e, 0x80000000u, 1, blen); len += 1u; }
-                    }
-                } else {
-                    const u32 di = h.y >> 16;
-                    e.w1 = tab[di]; e.w2 = tab[di + 1] - tab[di]; e.w3 = ENT_DYN;
-                    len = e.w2;
-                    kind = KIND_DYN;
-                    if (!skip_spec) { e.w0 = 0x80000000u; e.w3 |= 1u; len += 1u; }
                 }
-                ent[i] = e;
+                code[t * MPT + k] = c; meta[t * MPT + k] = m;
             }
-            off[i] = len;
-            kinds[i] = kind;
-            codedv[i] = coded;
         }
-        /* mb_skip_run */
-        int last_coded_next = last_coded;
-        if (skip_spec) {
-            int prev = last_coded;
-            for (int i = 0; i < TILE; i++) {
-                if (!codedv[i]) continue;
-                const u32 run = (u32)(t0 + i - 1 - prev);
-                u32 bits; int n;
-                encode_skip_prefix(run, bits, n);
-                if (kinds[i] == KIND_DYN) { ent[i].w0 = bits; ent[i].w3 |= (u32)n; }
-                else kinds[i] = finish_inline_entry(ent[i], bits, n, (int)off[i]);
-                off[i] += (u32)n;
-                prev = t0 + i;
+        /* prefixes */
+        int prev = last_coded;
+        for (int t = 0; t < NTHREADS; t++) {
+            previn[t] = prev;
+            const int g0 = t0 + t * MPT;
+            for (int k = 0; k < MPT; k++) {
+                u32 &m = meta[t * MPT + k];
+                if (!(m & META_CODED)) continue;
+                const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
+                attach_prefix(code[t * MPT + k], m, pre, 63 - 2 * clz32(pre));
+                prev = g0 + k;
             }
-            last_coded_next = prev;
         }
-        u32 trailer_len = 0;
-        if (last) {
-            u32 bits = 0x80000000u; int n = 1;
-            if (skip_spec) {
-                const u32 run_end = (u32)(N - 1 - last_coded_next);
-                if (run_end > 0) { encode_skip_prefix(run_end, bits, n); bits |= 1u << (31 - n); n += 1; }
-            }
-            MbEntry e; e.w0 = bits; e.w1 = 0; e.w2 = 0; e.w3 = 0;
-            ent[n_real] = e;
-            kinds[n_real] = KIND_SHORT;
-            trailer_len = (u32)n;
+        const int last_coded_total = prev;
+        /* trailer + scan */
+        u32 tr_code = 1, tr_len = 1;
+        if (last && skip_spec) {
+            const u32 run_end = (u32)(N - 1 - last_coded_total);
+            if (run_end > 0) { const int pn = 63 - 2 * clz32(run_end + 1); tr_code = ((run_end + 1) << 1) | 1; tr_len = pn + 1; }
         }
-        /* scan */
-        {
-            u32 run = bitpos;
-            for (int i = 0; i < TILE; i++) { u32 l = off[i]; off[i] = run; run += l; }
-            off[n_real] = run;
-            if (last) off[n_real + 1] = run + trailer_len;
+        u32 run = bitpos;
+        int trailer_thread = -1;
+        for (int t = 0; t < NTHREADS; t++) {
+            const int g0 = t0 + t * MPT;
+            const int nmb = std::min(std::max(N - g0, 0), MPT);
+            const bool owns = last && nmb > 0 && g0 + nmb == N;
+            if (owns) trailer_thread = t;
+            u32 L = dynlen[t] + (owns ? tr_len : 0);
+            for (int k = 0; k < MPT; k++) L += meta[t * MPT + k] & META_LEN_MASK;
+            Lv[t] = L; Ov[t] = run; run += L;
         }
-        const int n = last ? n_real + 1 : n_real;
-        const u32 end = off[n];
+        const u32 end = run;
         const u32 w_lo = bitpos >> 5;
         const u32 total_bytes = (end + 7u) >> 3;
         const u32 w_end = end >> 5;
         const u32 w_stop = last ? ((total_bytes + 3u) >> 2) : w_end;
         const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end;
-        const u32 cb0 = tile0 ? 0u : w_lo;
-        u32 carry_next = 0;
 
-        for (u32 cb = cb0; cb <= w_last; cb += (u32)CH) {
-            std::fill(first.begin(), first.end(), -1);
-            for (int i = 0; i <= n; i++) {
-                const u32 j = off[i] >> 5;
-                const bool fiw = (i == 0) || ((off[i - 1] >> 5) != j);
-                if (fiw && j >= cb && j < cb + (u32)CH) first[j - cb] = i;
-            }
-            if (tile0) for (u32 t = 0; t < (u32)CH && cb + t < w_lo; t++) first[t] = 0;
-            const u32 j_hi = std::min(cb + (u32)CH, w_last + 1u);
-            for (u32 j = cb; j < j_hi; j++) {
-                if (first[j - cb] < 0) continue;
-                const u32 base = j << 5;
-                u32 acc = tile0 ? (base < 296u ? header_bits32(d.hdr_bits, d.nal_header, base) : 0u)
-                                : (j == w_lo ? carry : 0u);
-                int i = first[j - cb];
-                auto contrib = [&](int e) {
-                    return kinds[e] == KIND_SHORT ? short_contrib(ent[e].w0, off[e], base)
-                                                  : entry_contrib(ent[e], off[e], base, pay_words, n_pay_words);
-                };
-                if (i > 0) acc |= contrib(i - 1);
-                while (i < n && off[i] < base + 32u) { acc |= contrib(i); i++; }
-                if (j < w_stop) outw[j - cb] = acc; else carry_next = acc;
-            }
-            for (int i = 0; i < n; i++) {
-                if (kinds[i] == KIND_SHORT) continue;
-                u32 ja = (off[i] >> 5) + 1u, jb = off[i + 1] >> 5;
-                if (ja < cb) ja = cb;
-                if (jb > cb + (u32)CH) jb = cb + (u32)CH;
-                for (u32 j = ja; j < jb; j++) outw[j - cb] = entry_contrib(ent[i], off[i], j << 5, pay_words, n_pay_words);
-            }
-            const u32 e_hi = std::min(cb + (u32)CH, w_stop);
-            const int cw = e_hi > cb ? (int)(e_hi - cb) : 0;
-            const u32 chunk_byte0 = cb << 2;
-            const int chunk_bytes = last ? (int)(std::min(e_hi << 2, total_bytes) - chunk_byte0) : cw * 4;
-            std::vector<u32> masks(cw, 0);
-            bool any = false;
-            int prev_nz = -1 - zc;
-            for (int jj = 0; jj < cw; jj++) {
-                int vb = std::min(4, chunk_bytes - 4 * jj);
-                masks[jj] = epb_word_mask(outw[jj], vb, 4 * jj, chunk_byte0, prev_nz);
-                any = any || masks[jj];
-            }
-            const int r_end = chunk_bytes - 1 - prev_nz;
-            const int zc_next = r_end == 0 ? 0 : ((r_end & 1) ? 1 : 2);
-            if (!any && ins_total == 0) {
-                for (int jj = 0; jj < cw; jj++) {
-                    const u32 j = cb + jj;
-                    if (4u * j + 4u <= cap) { u32 v = bswap32(outw[jj]); memcpy(fout + 4 * j, &v, 4); }
-                }
-            } else {
-                u32 running = ins_total;
-                for (int jj = 0; jj < cw; jj++) {
-                    const int vb = std::min(4, chunk_bytes - 4 * jj);
-                    u32 pos = chunk_byte0 + 4u * jj + running;
-                    for (int k = 0; k < vb; k++) {
-                        if ((masks[jj] >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                        if (pos < cap) fout[pos] = (uint8_t)chunk_byte(outw.data(), 4 * jj + k);
-                        pos++;
+        bool first_pass = true;
+        u32 wbase_last = 0;
+        for (u32 wbase = tile0 ? 0u : w_lo; wbase <= w_last; wbase += CH) {
+            std::fill(win.begin(), win.end(), 0u);
+            if (first_pass && !tile0) win[0] = carry;
+            first_pass = false;
+            wbase_last = wbase;
+            struct Copy { u32 j, src, n; };
+            std::vector<Copy> copies;
+            for (int t = 0; t < NTHREADS; t++) {
+                const int g0 = t0 + t * MPT;
+                BitPut bp;
+                bp_init(bp, (tile0 && t == 0) ? 0u : Ov[t]);
+                const u32 key = bp.j;
+                if (tile0 && t == 0)
+                    for (u32 p = 0; p < hdr_total; p += 32) {
+                        const u32 n = std::min(32u, hdr_total - p);
+                        bp_put(bp, (u64)(header_bits32(d.hdr_bits, d.nal_header, p) >> (32 - n)), n, win.data(), wbase, CH);
                     }
-                    running += (u32)__builtin_popcount(masks[jj]);
+                int pv = previn[t];
+                for (int k = 0; k < MPT; k++) {
+                    const u32 m = meta[t * MPT + k];
+                    const u64 c = code[t * MPT + k];
+                    if (!(m & META_CODED)) continue;
+                    const u32 n = m & META_LEN_MASK;
+                    if (!(m & (META_DYN | META_LONG | META_SPLIT))) bp_put(bp, c, n, win.data(), wbase, CH);
+                    else {
+                        const u32 pre = skip_spec ? (u32)(g0 + k - pv) : 1u;
+                        const u32 pn = 63 - 2 * clz32(pre);
+                        bp_put(bp, pre, pn, win.data(), wbase, CH);
+                        if (m & META_SPLIT) bp_put(bp, c, n - pn, win.data(), wbase, CH);
+                        else if (m & META_LONG) {
+                            MbEntry e;
+                            int bl = encode_p16x16_body((int)(m >> META_REF_SHIFT), long_dx(c), long_dy(c), num_refs, e);
+                            bp_put(bp, e.w1, 32, win.data(), wbase, CH);
+                            bp_put(bp, e.w2, 32, win.data(), wbase, CH);
+                            bl -= 64;
+                            bp_put(bp, e.w3 >> (32 - bl), bl, win.data(), wbase, CH);
+                        } else {
+                            const u32 di = (u32)(c >> 48);
+                            const u32 b0 = tab[di], len = tab[di + 1] - b0;
+                            const u32 hb = std::min(len, (32u - bp.fill) & 31u);
+                            if (hb) bp_put(bp, pay32(pay_words, n_pay_words, b0) >> (32 - hb), hb, win.data(), wbase, CH);
+                            const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31;
+                            if (nw) { copies.push_back({bp.j, b0 + hb, nw}); bp.j += nw; }
+                            if (tb) bp_put(bp, pay32(pay_words, n_pay_words, b0 + len - tb) >> (32 - tb), tb, win.data(), wbase, CH);
+                        }
+                    }
+                    pv = g0 + k;
                 }
-                ins_total = running;
+                if (t == trailer_thread) bp_put(bp, tr_code, tr_len, win.data(), wbase, CH);
+                if (bp.fill) {
+                    if (bp.head) bp.H = bp.acc;
+                    else if (bp.j - wbase < (u32)CH) win[bp.j - wbase] |= bp.acc;
+                }
+                if (bp.H && key - wbase < (u32)CH) win[key - wbase] |= bp.H;
             }
-            if (cw > 0) zc = zc_next;
+            for (auto &c : copies)
+                for (u32 i = 0; i < c.n; i++)
+                    if (c.j + i - wbase < (u32)CH) win[c.j + i - wbase] = pay32(pay_words, n_pay_words, c.src + 32 * i);
+
+            /* emit */
+            const u32 e_hi = std::min(wbase + (u32)CH, w_stop);
+            const u32 chunk_byte0 = wbase << 2;
+            const int chunk_bytes = e_hi > wbase ? (int)((last ? std::min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+            for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NTHREADS) {
+                std::vector<u32> tr(NTHREADS), zs(NTHREADS), insv(NTHREADS), rins(NTHREADS);
+                std::vector<int> vbs(NTHREADS);
+                for (int t = 0; t < NTHREADS; t++) {
+                    const int q = q0 + t;
+                    const int vb = std::min(std::max(chunk_bytes - 16 * q, 0), 16);
+                    u32 w[4] = {~0u, ~0u, ~0u, ~0u};
+                    if (vb > 0) for (int i = 0; i < 4; i++) w[i] = win[4 * q + i];
+                    u32 z = zero_nib(w[0]) | (zero_nib(w[1]) << 4) | (zero_nib(w[2]) << 8) | (zero_nib(w[3]) << 12);
+                    const u32 valid = (1u << vb) - 1u;
+                    z &= valid;
+                    if (chunk_byte0 == 0 && q == 0) z &= ~0x1Fu;
+                    zs[t] = z; vbs[t] = vb;
+                    tr[t] = epb_group_trail(z, std::max(vb, 1), 0) | (z == valid ? 0x100u : 0u);
+                }
+                u32 pass_ins = 0, zrun_next = zrun;
+                for (int t = 0; t < NTHREADS; t++) {
+                    const int q = q0 + t, vb = vbs[t];
+                    if (vb == 0) continue;
+                    u32 w[5];
+                    for (int i = 0; i < 5; i++) w[i] = win[4 * q + i];
+                    const u32 valid = (1u << vb) - 1u, z = zs[t];
+                    u32 keep = valid;
+                    if (chunk_byte0 == 0 && q == 0) keep &= ~0x1Fu;
+                    const bool b0_le3 = (w[0] >> 26) == 0 && (keep & 1);
+                    const bool need = b0_le3 || (z & 1);
+                    u32 rin = 0;
+                    if (need) {
+                        int u = t - 1;
+                        for (;;) {
+                            if (u < 0) { rin += zrun; break; }
+                            rin += tr[u] & 0xFF;
+                            if (!(tr[u] & 0x100)) break;
+                            u--;
+                        }
+                    }
+                    u32 ins = 0;
+                    if (need || (z & (z << 1))) {
+                        u32 m3 = zero_nib(w[0] & 0xFCFCFCFCu) | (zero_nib(w[1] & 0xFCFCFCFCu) << 4) |
+                                 (zero_nib(w[2] & 0xFCFCFCFCu) << 8) | (zero_nib(w[3] & 0xFCFCFCFCu) << 12);
+                        ins = epb_group_mask(z, m3 & keep, vb, rin);
+                    }
+                    insv[t] = ins; rins[t] = rin;
+                    const int vb_next = t == NTHREADS - 1 ? 0 : std::min(std::max(chunk_bytes - 16 * (q + 1), 0), 16);
+                    if (vb_next == 0) zrun_next = epb_group_trail(z, vb, rin);
+                }
+                u32 before = ins_total;
+                for (int t = 0; t < NTHREADS; t++) {
+                    const int q = q0 + t, vb = vbs[t];
+                    if (vb == 0) continue;
+                    const u32 cnt = (u32)__builtin_popcount(insv[t]);
+                    const u32 D = chunk_byte0 + 16u * q + before;
+                    auto is_clean = [&](int u) { return u >= 0 && u < NTHREADS && vbs[u] == 16 && insv[u] == 0; };
+                    const bool clean = is_clean(t), prev_clean = is_clean(t - 1), next_clean = is_clean(t + 1);
+                    u32 w[5];
+                    for (int i = 0; i < 5; i++) w[i] = win[4 * q + i];
+                    if (clean) {
+                        const u32 s = (4u - (D & 3u)) & 3u;
+                        if (s && !prev_clean)
+                            for (u32 k = 0; k < s; k++) if (D + k < cap) fout[D + k] = (uint8_t)(w[0] >> (24 - 8 * k));
+                        const u32 sel = realign_selector(s);
+                        u32 o[4];
+                        for (int i = 0; i < 4; i++) o[i] = byte_perm(w[i], w[i + 1], sel);
+                        const u32 nfull = (s == 0 || next_clean) ? 4 : 3;
+                        for (u32 i = 0; i < nfull; i++)
+                            if (D + s + 4 * i + 4 <= cap) memcpy(fout + D + s + 4 * i, &o[i], 4);
+                            else for (u32 k = 0; k < 4; k++) if (D + s + 4 * i + k < cap) fout[D + s + 4 * i + k] = (uint8_t)(o[i] >> (8 * k));
+                        if (nfull == 3)
+                            for (u32 k = 0; k < 4u - s; k++) if (D + s + 12 + k < cap) fout[D + s + 12 + k] = (uint8_t)(o[3] >> (8 * k));
+                    } else {
+                        u32 pos = D;
+                        for (int k = 0; k < vb; k++) {
+                            if ((insv[t] >> k) & 1) { if (pos < cap) fout[pos] = 3; pos++; }
+                            if (pos < cap) fout[pos] = (uint8_t)(w[k >> 2] >> (24 - 8 * (k & 3)));
+                            pos++;
+                        }
+                    }
+                    before += cnt; pass_ins += cnt;
+                }
+                ins_total += pass_ins;
+                zrun = zrun_next;
+            }
         }
         bitpos = end;
-        carry = carry_next;
-        last_coded = last_coded_next;
+        if (!last) carry = win[w_end - wbase_last];
+        last_coded = last_coded_total;
         if (last) size = total_bytes + ins_total;
     }
     return size;

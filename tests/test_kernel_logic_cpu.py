@@ -2,7 +2,8 @@
 The bit-level logic of the CUDA kernels, checked on the CPU: tests/emu/emu_compose.cpp walks the same tile
 pipeline as csrc/compose_kernels.cu with the very same helpers (csrc/mb_codec.cuh compiled by g++), so entry
 layout, word-owned gather, chunk carries and the closed-form emulation prevention are compared with the
-oracle without a GPU - with tiny TILE / CH values that force every boundary case.
+oracle without a GPU - with tiny thread counts (8 macroblocks each) and window sizes that force every boundary case.
+`tile` below is the number of emulated threads per tile, `ch` the window size in words.
 """
 import numpy as np
 import pytest
@@ -25,7 +26,7 @@ def _check(emu, po, oracle, b, tile, ch):
 
 
 @pytest.mark.parametrize("flags", [0, abi.SKIP_SPEC, abi.PRED_SPEC, abi.SKIP_SPEC | abi.PRED_SPEC])
-@pytest.mark.parametrize("tile,ch", [(1024, 1024), (64, 32), (32, 8), (96, 1)])
+@pytest.mark.parametrize("tile,ch", [(256, 6144), (16, 64), (4, 8), (2, 3), (3, 1)])
 def test_emulated_pipeline_matches_oracle(emu, po, oracle, tile, ch, flags):
     for seed, (w, h, nr) in enumerate(((7, 5, 2), (33, 17, 3), (64, 9, 10), (1, 40, 1), (50, 1, 2))):
         b = workloads.make_random(w, h, 2, seed=200 + seed, num_refs=nr, flags=flags, n_regions=10,
@@ -35,11 +36,12 @@ def test_emulated_pipeline_matches_oracle(emu, po, oracle, tile, ch, flags):
 
 def test_emulated_pipeline_zero_heavy(emu, po, oracle):
     b = workloads.make_random(40, 24, 3, seed=5, num_refs=2, flags=0, p_dyn=0.5, zero_payload_pct=70)
-    for tile, ch in ((1024, 1024), (128, 16), (32, 4)):
+    for tile, ch in ((256, 6144), (16, 16), (4, 4), (1, 5)):
         _check(emu, po, oracle, b, tile, ch)
 
 
 def test_emulated_pipeline_config_generators(emu, po, oracle):
-    _check(emu, po, oracle, workloads.make_config2(2), 1024, 1024)
-    _check(emu, po, oracle, workloads.make_config5(1, 2), 1024, 1024)
-    _check(emu, po, oracle, workloads.make_config4(1), 1024, 1024)
+    _check(emu, po, oracle, workloads.make_config2(2), 256, 6144)
+    _check(emu, po, oracle, workloads.make_config5(1, 2), 256, 6144)
+    _check(emu, po, oracle, workloads.make_config5(1, 1), 256, 512)
+    _check(emu, po, oracle, workloads.make_config4(1), 256, 6144)
