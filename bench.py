@@ -232,8 +232,15 @@ def main_ours(args):
     barrier()
     clocks = sampler.stop()
 
+    if hasattr(L, "h264gpu_debug_stage_cycles"):                  # timing-instrumented experiment build only
+        cyc = (ctypes.c_uint64 * 8)()
+        L.h264gpu_debug_stage_cycles(cyc)
+        tot = float(sum(cyc)) or 1.0
+        sys.stderr.write("stage cycles (thread 0 of every CTA, warm-up + timed): " +
+                         " ".join("%d:%.1f%%" % (i, 100.0 * c / tot) for i, c in enumerate(cyc)) + "\n")
     sizes = d_sizes.download(np.uint32)
-    assert (sizes <= b.slot_cap).all() and (sizes > 5).all(), "a frame overflowed its slot"
+    ablate = bool(os.environ.get("H264SCROLL_BENCH_NOCHECK"))      # timing experiments on deliberately incomplete kernels
+    assert ablate or ((sizes <= b.slot_cap).all() and (sizes > 5).all()), "a frame overflowed its slot"
     s_out = int(sizes.sum())
     s_dyn = int(sum(int(b.dyn_tab[int(b.dyn["table_off"][f]) + 625]) for f in range(n)) // 8)
     b_alg = 8 * total_mbs + s_dyn + 4 * 626 * n + s_out + 64 * n
@@ -276,7 +283,7 @@ def main_ours(args):
         d2h = e2e_step()
     gc.sync()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    assert d2h == s_out, "packed stream size differs from the sum of the frame sizes"
+    assert ablate or d2h == s_out, "packed stream size differs from the sum of the frame sizes"
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------
     ms_step, e2e_step_s = ms / args.steps, e2e_s

@@ -13,6 +13,8 @@ OBJ = os.path.join(PKG, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# experiment knobs (e.g. H264SCROLL_NVCC_EXTRA="-DCOMPOSE_MPT=4 -DCOMPOSE_MIN_CTAS=4"); empty for the shipped build
+NVCC_FLAGS += os.environ.get("H264SCROLL_NVCC_EXTRA", "").split()
 CFLAGS = ["-std=c99", "-O2", "-g", "-Wall", "-Wextra", "-fPIC"]
 
 

@@ -15,6 +15,10 @@
 #include "composer_gpu.h"
 #include "compose_kernels.cuh"
 
+#if defined(COMPOSE_TIMING) && COMPOSE_TIMING
+namespace h264scroll { cudaError_t read_stage_cycles(unsigned long long *h8); }
+#endif
+
 namespace {
 
 std::mutex g_mu;
@@ -236,5 +240,12 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
         if (h_sizes[f] > h_desc[f].out_cap) return fail(H264GPU_ERR_OVERFLOW, "a frame exceeded its output slot");
     return H264GPU_OK;
 }
+
+#if defined(COMPOSE_TIMING) && COMPOSE_TIMING
+/* experiments only: per-stage clock64() sums of thread 0 of every CTA since the last call */
+int h264gpu_debug_stage_cycles(unsigned long long *h8) {
+    return h264scroll::read_stage_cycles(h8) == cudaSuccess ? H264GPU_OK : H264GPU_ERR_CUDA;
+}
+#endif
 
 }  /* extern "C" */

@@ -36,36 +36,45 @@
 namespace h264scroll {
 
 constexpr int NT = COMPOSE_THREADS;      /* threads per CTA */
-constexpr int MPT = 8;                   /* consecutive macroblocks per thread */
+constexpr int MPT = COMPOSE_MPT;         /* consecutive macroblocks per thread */
 constexpr int TILE = NT * MPT;           /* macroblocks per tile */
 constexpr int NW = NT / 32;
-constexpr int CH = 6144;                 /* window: slice words staged per pass (24 KB) */
-constexpr int LCAP = 512;                /* splice copy list entries per pass */
+constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass */
+constexpr int LCAP = COMPOSE_COPY_SLOTS; /* splice copy list entries per pass */
 constexpr u32 FULL = 0xFFFFFFFFu;
-
-struct FrameState {
-    u32 bitpos;        /* slice bits emitted so far (incl. the 40-bit Annex-B prefix) */
-    u32 carry;         /* partial slice word at bitpos >> 5 */
-    int last_coded;    /* frame index of the last non-skipped MB, -1 if none */
-    u32 zrun;          /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state) */
-    u32 ins_total;     /* emulation-prevention bytes inserted so far */
-    u32 n_copy;        /* entries in the splice copy list */
-    u32 zrun_next;
-};
+#ifndef COMPOSE_ABLATE
+#define COMPOSE_ABLATE 0                 /* timing experiments only (scripts/variant.sh); 0 in the shipped build */
+#endif
+#ifndef COMPOSE_TIMING
+#define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
+#endif
+#if COMPOSE_TIMING
+__device__ unsigned long long g_stage_cycles[8];
+#define STAGE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); stage_acc[i] += t_ - stage_t; stage_t = t_; } } while (0)
+#else
+#define STAGE_MARK(i) do { } while (0)
+#endif
 
 struct __align__(16) ComposeSmem {
-    u32 win[CH + 8];                     /* slice bits of the pass, MSB-first words (+ read-ahead pad) */
-    uint4 copy[LCAP];                    /* {first frame word, payload bit, words, -} */
-    u32 tr[NT];                          /* emit: zero bytes closing each 16-byte group */
+    u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
+    uint4 copy[LCAP];                    /* {first window word, payload bit, words, -} */
     u32 gi[NT];                          /* emit: (insert count << 8) | valid bytes of each group */
-    u32 scan[NW + 1];
-    H264GpuFrameDesc desc;
-    H264GpuDynDesc dyn;
-    FrameState st;
+    u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
+    u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
+    u32 n_copy[2];                       /* queued splice runs, double buffered per tile */
+    /* per-frame constants only the splice and emit stages need: kept out of the register file */
+    const u32 *tab;                      /* the frame's payload bit-offset table */
+    const u32 *pay_words;                /* the frame's payload */
+    u32 n_pay_words;
+    u32 cap;                             /* output slot capacity */
+    uint8_t *fout;                       /* output slot */
 };
 
-/* exclusive prefix sum over the CTA; every thread gets its offset and the total */
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
+/*
+ * Exclusive prefix sum over the CTA; every thread gets its offset and the total.  One barrier:
+ * consecutive scans must alternate between the two s_scan buffers.
+ */
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total, int pred, int &any_pred) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 inc = v;
 #pragma unroll
@@ -74,7 +83,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
+    any_pred = __syncthreads_or(pred);                 /* the scan's barrier doubles as a block-wide vote */
     const u32 wsum = lane < NW ? s_scan[lane] : 0u;    /* every warp scans the NW warp totals itself */
     u32 winc = wsum;
 #pragma unroll
@@ -84,12 +93,11 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
     }
     const u32 wexc = __shfl_sync(FULL, winc - wsum, warp);
     total = __shfl_sync(FULL, winc, NW - 1);
-    __syncthreads();                                   /* s_scan may be reused by the caller */
     return wexc + inc - v;
 }
 
 /* exclusive prefix max over the CTA (identity -1 as int); `total` = max over all threads */
-__device__ __forceinline__ int block_excl_scan_max(int v, int *s_scan, int &total) {
+__device__ __noinline__ int block_excl_scan_max(int v, int *s_scan, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
@@ -110,21 +118,110 @@ __device__ __forceinline__ int block_excl_scan_max(int v, int *s_scan, int &tota
     if (lane == 0) wexc = -1;
     wexc = __shfl_sync(FULL, wexc, warp);
     total = __shfl_sync(FULL, winc, NW - 1);
-    __syncthreads();
     int exc = __shfl_up_sync(FULL, inc, 1);
     if (lane == 0) exc = -1;
     return max(wexc, exc);
 }
 
-/* 32 payload bits from bit position p (payload words are big-endian in memory) */
-__device__ __forceinline__ u32 payload_ld32(const u32 *__restrict__ pw, u32 n_words, u32 p) {
-    const u32 wi = p >> 5;
-    const u32 a = wi < n_words ? bswap32(__ldg(pw + wi)) : 0u;
-    const u32 b = wi + 1u < n_words ? bswap32(__ldg(pw + wi + 1u)) : 0u;
-    return __funnelshift_l(b, a, p & 31u);
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+/* payload word wi as an MSB-first word (payload bytes are a bit stream, so big-endian in memory) */
+__device__ __forceinline__ u32 payload_word(const u32 *__restrict__ pw, u32 n_words, u32 wi) {
+    return wi < n_words ? __byte_perm(__ldg(pw + wi), 0u, 0x0123u) : 0u;
 }
 
-__global__ void __launch_bounds__(NT, 3)
+/* 32 payload bits from bit position p */
+__device__ __forceinline__ u32 payload_ld32(const u32 *__restrict__ pw, u32 n_words, u32 p) {
+    const u32 wi = p >> 5;
+    return __funnelshift_l(payload_word(pw, n_words, wi + 1u), payload_word(pw, n_words, wi), p & 31u);
+}
+
+/* n whole slice words of a spliced macroblock: window word j.. <- payload bits p.. (copy_bits, src/h264_writer.c:228) */
+__device__ __forceinline__ void splice_words(u32 *win, u32 j, u32 n, const u32 *__restrict__ pw, u32 n_words, u32 p) {
+    u32 wi = p >> 5;
+    const u32 sh = p & 31u;
+    u32 a = payload_word(pw, n_words, wi);
+    u32 i = 0;
+    for (; i + 4u <= n; i += 4u) {                          /* four independent loads in flight */
+        const u32 b0 = payload_word(pw, n_words, wi + 1u), b1 = payload_word(pw, n_words, wi + 2u),
+                  b2 = payload_word(pw, n_words, wi + 3u), b3 = payload_word(pw, n_words, wi + 4u);
+        if (j + i < (u32)CH) win[j + i] = __funnelshift_l(b0, a, sh);
+        if (j + i + 1u < (u32)CH) win[j + i + 1u] = __funnelshift_l(b1, b0, sh);
+        if (j + i + 2u < (u32)CH) win[j + i + 2u] = __funnelshift_l(b2, b1, sh);
+        if (j + i + 3u < (u32)CH) win[j + i + 3u] = __funnelshift_l(b3, b2, sh);
+        a = b3;
+        wi += 4u;
+    }
+    for (; i < n; i++) {
+        const u32 b = payload_word(pw, n_words, ++wi);
+        if (j + i < (u32)CH) win[j + i] = __funnelshift_l(b, a, sh);
+        a = b;
+    }
+}
+
+/* the rare inline macroblock whose code may exceed 64 bits: prefix, then the body word by word */
+__device__ __noinline__ void put_long(BitPut &bp, u64 code, u32 meta, int num_refs, u32 *win, u32 wbase) {
+    const u32 pre = long_prefix(code);
+    bp_put(bp, (u64)pre, 63u - 2u * (u32)__clz((int)pre), win, wbase, CH);
+    MbEntry e;
+    int bl = encode_p16x16_body((int)(meta >> META_REF_SHIFT), long_dx(code), long_dy(code), num_refs, e);
+    const u32 ws[3] = {e.w1, e.w2, e.w3};
+    for (int i = 0; i < 3 && bl > 0; i++, bl -= 32) {
+        const u32 n = (u32)min(bl, 32);
+        bp_put(bp, (u64)(ws[i] >> (32u - n)), n, win, wbase, CH);
+    }
+}
+
+/*
+ * A spliced macroblock: mb_skip_run prefix, then its pre-encoded bits.  The partial words at both
+ * ends go through the bit writer, the whole words in between are queued for the copy stage.
+ */
+__device__ __noinline__ void put_spliced(BitPut &bp, u64 code, ComposeSmem &sm, u32 wbase, u32 *n_copy) {
+    const u32 *__restrict__ tab = sm.tab;
+    const u32 *__restrict__ pw = sm.pay_words;
+    const u32 n_words = sm.n_pay_words;
+    u32 *win = sm.win;
+    const u32 pre = dyn_prefix(code);
+    bp_put(bp, (u64)pre, 63u - 2u * (u32)__clz((int)pre), win, wbase, CH);
+    const u32 di = dyn_index(code);
+    const u32 b0 = __ldg(tab + di), len = __ldg(tab + di + 1) - b0;
+    const u32 hb = min(len, (32u - bp.fill) & 31u);
+    if (hb) bp_put(bp, (u64)(payload_ld32(pw, n_words, b0) >> (32u - hb)), hb, win, wbase, CH);
+    const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31u;
+    if (nw) {
+        const u32 slot = atomicAdd(n_copy, 1u);
+        if (slot < (u32)LCAP) sm.copy[slot] = make_uint4(bp.j - wbase, b0 + hb, nw, 0u);
+        else splice_words(win, bp.j - wbase, nw, pw, n_words, b0 + hb);      /* list full: copy it here */
+        bp.j += nw;
+    }
+    if (tb) bp_put(bp, (u64)(payload_ld32(pw, n_words, b0 + len - tb) >> (32u - tb)), tb, win, wbase, CH);
+}
+
+/* the copy stage: one lane per queued run */
+__device__ __noinline__ void splice_queued(ComposeSmem &sm, u32 n_copy) {
+    const u32 *__restrict__ pw = sm.pay_words;
+    const u32 n_words = sm.n_pay_words;
+    for (u32 d = threadIdx.x; d < n_copy; d += NT) {
+        const uint4 c = sm.copy[d];
+        splice_words(sm.win, c.x, c.z, pw, n_words, c.y);
+    }
+}
+
+/* out of line: the backward scan is rare */
+__device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in) { return zeros_before(win, b, zrun_in); }
+
+/* a group with insertions, the frame's last bytes, or one next to the slot's end: byte by byte */
+__device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w, u32 ins, int vb) {
+    const u32 ws[4] = {w.x, w.y, w.z, w.w};
+    for (int k = 0; k < vb; k++) {
+        if ((ins >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
+        if (pos < cap) fout[pos] = (uint8_t)(ws[k >> 2] >> (24 - 8 * (k & 3)));
+        pos++;
+    }
+}
+
+__global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuMbHint *__restrict__ hints,
                       const H264GpuDynDesc *__restrict__ dyns,
@@ -134,57 +231,59 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
     __shared__ ComposeSmem sm;
     const int tid = threadIdx.x, lane = tid & 31;
 
+    {   /* the window is zero wherever nothing was written: cleared once here, then every flush clears what it used */
+        uint4 *w4 = (uint4 *)sm.win;
+        for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) { sm.n_copy[0] = 0; sm.n_copy[1] = 0; }
+    }
+    u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
+    u32 cpar = 0;                      /* which sm.n_copy counter the current tile uses */
+#if COMPOSE_TIMING
+    long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
+#endif
+
     for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        /* ---- frame setup ------------------------------------------------ */
-        __syncthreads();
-        if (tid < (int)(sizeof(H264GpuFrameDesc) / 4))
-            ((u32 *)&sm.desc)[tid] = ((const u32 *)&descs[f])[tid];
-        __syncthreads();
-        const int W = sm.desc.mb_w, N = W * (int)sm.desc.mb_h;
+        /* ---- frame setup: the descriptor is read by every thread (one broadcast line) ------ */
+        const uint4 *dq = (const uint4 *)(descs + f);
+        const uint4 d2 = __ldg(dq + 2), d3 = __ldg(dq + 3);
+        const u64 hint_off = (u64)d2.x | ((u64)d2.y << 32), out_off = (u64)d2.z | ((u64)d2.w << 32);
+        const u32 cap = d3.x, dyn_id = d3.y;
+        const int W = (int)(d3.z & 0xFFFFu), N = W * (int)(d3.z >> 16);
+        const u32 hdr_total = 40u + (d3.w & 0xFFu);
+        const int num_refs = (int)((d3.w >> 8) & 0xFFu);
+        const int skip_spec = ((d3.w >> 16) & H264GPU_SKIP_SPEC) != 0;
+        const int pred_spec = ((d3.w >> 16) & H264GPU_PRED_SPEC) != 0;
+        const u32 nal_header = d3.w >> 24;
         const u32 w_magic = 0xFFFFFFFFu / (u32)W + 1u;         /* g / W == umulhi(g, magic): exact for g < 2^20, 1 < W < 2^10 */
-        const int num_refs = sm.desc.num_refs;
-        const int skip_spec = (sm.desc.flags & H264GPU_SKIP_SPEC) != 0;
-        const int pred_spec = (sm.desc.flags & H264GPU_PRED_SPEC) != 0;
-        const u32 cap = sm.desc.out_cap;
-        const u32 nal_header = sm.desc.nal_header;
-        const u32 hdr_total = 40u + sm.desc.hdr_nbits;
-        const u32 dyn_id = sm.desc.dyn_id;
-        if (dyn_id != H264GPU_NO_DYN && tid < (int)(sizeof(H264GpuDynDesc) / 4))
-            ((u32 *)&sm.dyn)[tid] = ((const u32 *)&dyns[dyn_id])[tid];
-        if (tid == 0) {
-            sm.st.bitpos = hdr_total;
-            sm.st.carry = 0;
-            sm.st.last_coded = -1;
-            sm.st.zrun = 0;
-            sm.st.ins_total = 0;
-            sm.st.n_copy = 0;
-        }
-        __syncthreads();
-        const uint2 *fh = (const uint2 *)hints + sm.desc.hint_off;
+        const uint2 *fh = (const uint2 *)hints + hint_off;
         const u32 *tab = nullptr;
         const u32 *pay_words = nullptr;
         u32 n_pay_words = 0;
         if (dyn_id != H264GPU_NO_DYN) {
-            tab = dyn_tab + sm.dyn.table_off;
-            pay_words = (const u32 *)(payload + sm.dyn.payload_off);
-            n_pay_words = (sm.dyn.payload_bytes + 3u) >> 2;
+            const uint4 *yq = (const uint4 *)(dyns + dyn_id);
+            const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
+            tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
+            pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
+            n_pay_words = (y1.y + 3u) >> 2;
         }
-        uint8_t *fout = out + sm.desc.out_off;
-        u32 *fout32 = (u32 *)fout;
+        if (tid == 0) {                                        /* read again only after this frame's first barrier */
+            sm.zrun[0] = 0; sm.zrun[1] = 0;
+            sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
+            sm.cap = cap; sm.fout = out + out_off;
+        }
+
+        /* frame state every thread tracks identically (all of it follows from block-wide totals) */
+        u32 bitpos = hdr_total;        /* slice bits composed so far (incl. the 40-bit Annex-B prefix) */
+        int last_coded = -1;           /* frame index of the last non-skipped MB */
+        u32 ins_total = 0;             /* emulation-prevention bytes inserted so far */
+        u32 zpar = 0;                  /* which sm.zrun slot holds the current state */
+        u32 wbase = 0;                 /* frame word held by window word 0; words below it have left for global memory */
 
         for (int t0 = 0; t0 < N; t0 += TILE) {
             const bool last = (t0 + TILE >= N);
             const bool tile0 = (t0 == 0);
             const int g0 = t0 + tid * MPT;
             const int nmb = min(max(N - g0, 0), MPT);          /* real macroblocks of this thread */
-
-            /* the window is cleared while the hint loads are in flight */
-            {
-                uint4 *w4 = (uint4 *)sm.win;
-                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = z4;
-                if (tid == 0 && !tile0) sm.win[0] = sm.st.carry;   /* bits of the previous tile in the shared word */
-            }
 
             /* ---- load: own hints, the row above, the left neighbour ---------- */
             uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
@@ -194,7 +293,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #pragma unroll
             for (int j = 0; j < MPT + 2; j++) abv[j] = make_uint2(0u, 0u);
             if (nmb == MPT) {
-                const uint4 *src = (const uint4 *)(fh + g0);    /* hint_off even, g0 % 8 == 0: 16-byte aligned */
+                const uint4 *src = (const uint4 *)(fh + g0);    /* hint_off even, g0 % MPT == 0: 16-byte aligned */
 #pragma unroll
                 for (int k = 0; k < MPT / 2; k++) {
                     const uint4 v = __ldg(src + k);
@@ -209,9 +308,14 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             if (nmb > 0) {
                 if (g0 > 0) own[0] = __ldg(fh + g0 - 1);
                 const int a0 = g0 - W - 1;
+                if (a0 >= 0 && a0 + MPT + 2 <= N) {
 #pragma unroll
-                for (int j = 0; j < MPT + 2; j++)
-                    if (a0 + j >= 0 && a0 + j < N) abv[j] = __ldg(fh + a0 + j);
+                    for (int j = 0; j < MPT + 2; j++) abv[j] = __ldg(fh + a0 + j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < MPT + 2; j++)
+                        if (a0 + j >= 0 && a0 + j < N) abv[j] = __ldg(fh + a0 + j);
+                }
             }
 
             /* ---- decide + code ------------------------------------------------ */
@@ -223,20 +327,30 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #pragma unroll
                 for (int k = 0; k < MPT; k++) {
                     code[k] = 0; meta[k] = 0;
-                    if (k < nmb) {
-                        const uint2 h = own[1 + k];
-                        const u32 hk = (h.y >> 8) & 0xFFu;
-                        if (hk == H264GPU_MB_INTER) {
-                            const int avA = x > 0, avB = y > 0;
-                            const bool hasC = x + 1 < W;
-                            const int avC = avB && (hasC || x > 0);
-                            const uint2 c = hasC ? abv[k + 2] : abv[k];     /* C, else D (:391-399) */
+                    const uint2 h = own[1 + k];
+                    const bool present = k < nmb;
+                    const bool inter = ((h.y >> 8) & 0xFFu) == H264GPU_MB_INTER;
+                    const int avA = x > 0, avB = y > 0;
+                    const bool hasC = x + 1 < W;
+                    const int avC = avB && (hasC || x > 0);
+                    const uint2 c = hasC ? abv[k + 2] : abv[k];             /* C, else D (:391-399) */
+                    /* uniform neighbourhood: A, B, C available and equal to this MB's (mv, ref, kind) */
+                    const u32 hkey = h.y & 0xFFFFu;
+                    const bool uni = inter && avA && avC &&
+                                     own[k].x == h.x && abv[k + 1].x == h.x && c.x == h.x &&
+                                     (own[k].y & 0xFFFFu) == hkey && (abv[k + 1].y & 0xFFFFu) == hkey && (c.y & 0xFFFFu) == hkey;
+                    if (__all_sync(FULL, uni || !present)) {
+                        if (present) meta[k] = decide_uniform(h.y, num_refs, skip_spec, code[k]);
+                    } else if (present) {
+                        if (inter) {
                             meta[k] = decide_inter(h.x, h.y, own[k].x, own[k].y, avA, abv[k + 1].x, abv[k + 1].y, avB,
                                                    c.x, c.y, avC, num_refs, pred_spec, skip_spec, code[k]);
                         } else {
                             const u32 di = h.y >> 16;
                             const u32 b0 = __ldg(tab + di), b1 = __ldg(tab + di + 1);
                             dynlen += b1 - b0;
+                            prefetch_l1((const uint8_t *)pay_words + (b0 >> 3));      /* the payload is first touched here: */
+                            prefetch_l1((const uint8_t *)pay_words + (b1 >> 3));      /* have it on its way before the splice */
                             meta[k] = META_DYN | META_CODED;
                             code[k] = (u64)di << 48;
                         }
@@ -245,17 +359,20 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 }
             }
 
+            STAGE_MARK(0);                                      /* load + decide */
+            if (g0 + TILE < N && (tid & 3) == 0) prefetch_l2(fh + g0 + TILE);   /* next tile's hints: one 128-byte line per 4 threads */
+
             /* ---- mb_skip_run prefixes ------------------------------------------ */
-            int prev_in = -1, last_coded_total = -1;
+            int last_coded_total = last_coded;
             if (skip_spec) {
                 int lc = -1;
 #pragma unroll
                 for (int k = 0; k < MPT; k++)
                     if (meta[k] & META_CODED) lc = g0 + k;
-                prev_in = block_excl_scan_max(lc, (int *)sm.scan, last_coded_total);
-                prev_in = max(prev_in, sm.st.last_coded);
-                last_coded_total = max(last_coded_total, sm.st.last_coded);
-                int prev = prev_in;
+                int blk_max;
+                int prev = max(block_excl_scan_max(lc, (int *)sm.scan[spar], blk_max), last_coded);
+                spar ^= 1u;
+                last_coded_total = max(blk_max, last_coded);
 #pragma unroll
                 for (int k = 0; k < MPT; k++)
                     if (meta[k] & META_CODED) {
@@ -269,6 +386,29 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     if (meta[k] & META_CODED) attach_prefix(code[k], meta[k], 1u, 1);   /* ue(0), :630 */
             }
 
+            /* ---- merge: consecutive plain codes -> one <= 64-bit item per run, bit count of the thread ---- */
+            u32 L = dynlen;
+            {
+                u64 acc = 0;
+                u32 accn = 0;
+#pragma unroll
+                for (int k = 0; k < MPT; k++) {
+                    const u64 c = code[k];
+                    const u32 m = meta[k];
+                    L += m & META_LEN_MASK;
+                    code[k] = 0; meta[k] = 0;
+                    if (m & (META_DYN | META_LONG)) {
+                        if (k > 0 && accn) { code[k - 1] = acc; meta[k - 1] = accn; acc = 0; accn = 0; }
+                        code[k] = c; meta[k] = m;
+                    } else if (m & META_CODED) {
+                        u64 sc = 0; u32 sn = 0;
+                        const bool seal = merge_plain(acc, accn, c, m & META_LEN_MASK, sc, sn);
+                        if (k > 0 && seal) { code[k - 1] = sc; meta[k - 1] = sn; }
+                    }
+                }
+                if (accn) { code[MPT - 1] = acc; meta[MPT - 1] = accn; }
+            }
+
             /* ---- slice trailer: trailing mb_skip_run + rbsp_stop_one_bit ---------- */
             const bool owns_trailer = last && nmb > 0 && g0 + nmb == N;
             u32 tr_code = 1u, tr_len = 1u;
@@ -280,88 +420,53 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     tr_len = (u32)pn + 1u;
                 }
             }
+            if (owns_trailer) L += tr_len;
 
             /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
-            u32 L = dynlen + (owns_trailer ? tr_len : 0u);
-#pragma unroll
-            for (int k = 0; k < MPT; k++) L += meta[k] & META_LEN_MASK;
-            const u32 bitpos = sm.st.bitpos;
             u32 total;
-            const u32 O = bitpos + block_excl_scan(L, sm.scan, total);     /* the scan's barriers also publish the cleared window */
+            int tile_has_dyn;
+            const u32 O = bitpos + block_excl_scan(L, sm.scan[spar], total, dynlen != 0u, tile_has_dyn);
+            spar ^= 1u;
             const u32 E = O + L;
             const u32 end = bitpos + total;
-            const u32 w_lo = bitpos >> 5;
             const u32 total_bytes = (end + 7u) >> 3;                       /* meaningful when last */
             const u32 w_end = end >> 5;
-            const u32 w_stop = last ? ((total_bytes + 3u) >> 2) : w_end;   /* words [.., w_stop) are emitted */
-            const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end;
+            const u32 w_stop = last ? ((total_bytes + 3u) >> 2) : w_end;   /* frame words [.., w_stop) are complete after this tile */
+            const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end; /* last word this tile writes to */
             const u32 warp_end = __shfl_sync(FULL, E, 31);
-            bool first_pass = true;
+            STAGE_MARK(1);                                      /* prefixes + merge + scan (incl. its barrier) */
+#if COMPOSE_ABLATE == 1                                                     /* timing experiment: stop after decide + scan */
+            {
+                u32 x = O;
+#pragma unroll
+                for (int k = 0; k < MPT; k++) x ^= (u32)code[k] ^ (u32)(code[k] >> 32) ^ meta[k];
+                if (x == 0x12345u) sizes[f] = x;
+                bitpos = end; last_coded = last_coded_total;
+                continue;
+            }
+#endif
 
-            for (u32 wbase = tile0 ? 0u : w_lo; wbase <= w_last; wbase += CH) {
-                if (!first_pass) {
-                    __syncthreads();
-                    uint4 *w4 = (uint4 *)sm.win;
-                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                    for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = z4;
-                    if (tid == 0) sm.st.n_copy = 0;
-                    __syncthreads();
-                }
-                first_pass = false;
-
-                /* ---- write: sequential bit writer per thread ------------------------- */
+            for (;;) {
+                /* ---- write: sequential bit writer per thread, clipped to the window ---------- */
                 BitPut bp;
                 bp_init(bp, (tile0 && tid == 0) ? 0u : O);
                 const u32 key = bp.j;
                 if (tile0 && tid == 0) {
+                    const uint4 h0 = __ldg(dq), h1 = __ldg(dq + 1);
+                    const u64 hdr[4] = {(u64)h0.x | ((u64)h0.y << 32), (u64)h0.z | ((u64)h0.w << 32),
+                                        (u64)h1.x | ((u64)h1.y << 32), (u64)h1.z | ((u64)h1.w << 32)};
                     for (u32 p = 0; p < hdr_total; p += 32u) {
                         const u32 n = min(32u, hdr_total - p);
-                        bp_put(bp, (u64)(header_bits32(sm.desc.hdr_bits, nal_header, p) >> (32u - n)), n, sm.win, wbase, CH);
+                        bp_put(bp, (u64)(header_bits32(hdr, nal_header, p) >> (32u - n)), n, sm.win, wbase, CH);
                     }
                 }
-                {
-                    int prev = prev_in;
 #pragma unroll
-                    for (int k = 0; k < MPT; k++) {
-                        const u32 m = meta[k];
-                        if (m & META_CODED) {
-                            const u32 n = m & META_LEN_MASK;
-                            if (!(m & (META_DYN | META_LONG | META_SPLIT))) {
-                                bp_put(bp, code[k], n, sm.win, wbase, CH);
-                            } else {
-                                const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
-                                const u32 pn = 63u - 2u * (u32)__clz((int)pre);
-                                bp_put(bp, (u64)pre, pn, sm.win, wbase, CH);
-                                if (m & META_SPLIT) {
-                                    bp_put(bp, code[k], n - pn, sm.win, wbase, CH);
-                                } else if (m & META_LONG) {
-                                    MbEntry e;
-                                    int bl = encode_p16x16_body((int)(m >> META_REF_SHIFT), long_dx(code[k]), long_dy(code[k]), num_refs, e);
-                                    bp_put(bp, (u64)e.w1, 32u, sm.win, wbase, CH);
-                                    bp_put(bp, (u64)e.w2, 32u, sm.win, wbase, CH);
-                                    bl -= 64;
-                                    bp_put(bp, (u64)(e.w3 >> (32 - bl)), (u32)bl, sm.win, wbase, CH);
-                                } else {
-                                    /* spliced MB: partial words through the writer, whole words through the copy list */
-                                    const u32 di = (u32)(code[k] >> 48);
-                                    const u32 b0 = __ldg(tab + di), len = __ldg(tab + di + 1) - b0;
-                                    const u32 hb = min(len, (32u - bp.fill) & 31u);
-                                    if (hb) bp_put(bp, (u64)(payload_ld32(pay_words, n_pay_words, b0) >> (32u - hb)), hb, sm.win, wbase, CH);
-                                    const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31u;
-                                    if (nw) {
-                                        const u32 slot = atomicAdd(&sm.st.n_copy, 1u);
-                                        if (slot < (u32)LCAP) sm.copy[slot] = make_uint4(bp.j, b0 + hb, nw, 0u);
-                                        else
-                                            for (u32 i = 0; i < nw; i++)
-                                                if (bp.j + i - wbase < (u32)CH)
-                                                    sm.win[bp.j + i - wbase] = payload_ld32(pay_words, n_pay_words, b0 + hb + 32u * i);
-                                        bp.j += nw;
-                                    }
-                                    if (tb) bp_put(bp, (u64)(payload_ld32(pay_words, n_pay_words, b0 + len - tb) >> (32u - tb)), tb, sm.win, wbase, CH);
-                                }
-                            }
-                            prev = g0 + k;
-                        }
+                for (int k = 0; k < MPT; k++) {
+                    const u32 m = meta[k];
+                    if (m) {
+                        if (!(m & (META_DYN | META_LONG))) bp_put(bp, code[k], m, sm.win, wbase, CH);
+                        else if (m & META_DYN) put_spliced(bp, code[k], sm, wbase, &sm.n_copy[cpar]);
+                        else put_long(bp, code[k], m, num_refs, sm.win, wbase);
                     }
                 }
                 if (owns_trailer) bp_put(bp, (u64)tr_code, tr_len, sm.win, wbase, CH);
@@ -386,150 +491,153 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     if (has_tail && tj - wbase < (u32)CH) {
                         u32 v = T;
                         if (lane < 31 && kn == tj) v |= Xn;
-                        if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps add to this word */
+                        if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps (or the next tile) add to this word */
                         else sm.win[tj - wbase] = v;
                     }
                     if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], X);
                 }
+
+#if COMPOSE_ABLATE == 2                                                     /* timing experiment: stop after the bit writer */
                 __syncthreads();
-
-                /* ---- splice: whole words of spliced MBs, 8 lanes per entry ------------------ */
+                if (sm.win[(tid * 7) % CH] == 0x12345u) sizes[f] = 1;
                 {
-                    const u32 n_copy = min(sm.st.n_copy, (u32)LCAP);
-                    const u32 sub = (u32)tid & 7u;
-                    for (u32 d = (u32)tid >> 3; d < n_copy; d += NT / 8) {
-                        const uint4 c = sm.copy[d];
-                        for (u32 i = sub; i < c.z; i += 8u) {
-                            const u32 j = c.x + i - wbase;
-                            if (j < (u32)CH) sm.win[j] = payload_ld32(pay_words, n_pay_words, c.y + 32u * i);
-                        }
-                    }
-                    if (n_copy) __syncthreads();
+                    uint4 *w4 = (uint4 *)sm.win;
+                    for (u32 i = (u32)tid; i < (CH + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
+                if (tid == 0) { sm.n_copy[0] = 0; sm.n_copy[1] = 0; }
+                __syncthreads();
+                break;
+#endif
+                STAGE_MARK(2);                                  /* bit writer + partial-word merge */
+                const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
+                const bool flush = last || !fits;
+                bool synced = false;
 
-                /* ---- emit: emulation prevention + store of words [wbase, e_hi) -------------- */
-                const u32 e_hi = min(wbase + CH, w_stop);
+                /* ---- splice: whole words of spliced MBs, one lane per queued run ----------- */
+                if (tile_has_dyn) {
+                    __syncthreads();
+                    synced = true;
+                    splice_queued(sm, min(sm.n_copy[cpar], (u32)LCAP));
+                    cpar ^= 1u;
+                    if (tid == 0) sm.n_copy[cpar] = 0;                     /* nobody reads that one before the next tile's barrier */
+                }
+                STAGE_MARK(3);                                  /* splice copy (incl. its barrier) */
+                if (!flush) break;                                         /* keep filling the window with the next tile */
+
+                /* ---- emit: emulation prevention + store of frame words [wbase, e_hi) --------- */
+                if (!synced || tile_has_dyn) __syncthreads();
+                STAGE_MARK(4);                                  /* barrier before emit */
+                const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
-                const int chunk_bytes = e_hi > wbase ? (int)((last ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+                const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+                const u32 zrun_in = sm.zrun[zpar];
+                const u32 cap = sm.cap;
+                uint8_t *fout = sm.fout;
+                u32 *fout32 = (u32 *)fout;
                 for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NT) {
                     const int q = q0 + tid;
                     const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
                     const int vb_next = tid == NT - 1 ? 0 : min(max(chunk_bytes - 16 * (q + 1), 0), 16);
                     uint4 w = make_uint4(FULL, FULL, FULL, FULL);
-                    u32 wn = 0;
-                    if (vb > 0) { w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4]; }
-                    u32 z = zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12);
-                    const u32 valid = (1u << vb) - 1u;
-                    z &= valid;
-                    u32 keep = valid;                                      /* bytes that may take an insertion */
-                    if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
-                    const bool b0_le3 = (w.x >> 26) == 0u && (keep & 1u);
-                    sm.tr[tid] = epb_group_trail(z, max(vb, 1), 0u) | (z == valid ? 0x100u : 0u);
-                    __syncthreads();
-                    /* zero bytes right before the group: walk back over all-zero groups */
-                    u32 rin = 0;
-                    const bool need = vb > 0 && (b0_le3 || (z & 1u));
-                    if (need) {
-                        int u = tid - 1;
-                        for (;;) {
-                            if (u < 0) { rin += sm.st.zrun; break; }
-                            const u32 t = sm.tr[u];
-                            rin += t & 0xFFu;
-                            if (!(t & 0x100u)) break;
-                            u--;
-                        }
-                    }
-                    u32 ins = 0;
-                    if (vb > 0 && (need || (z & (z << 1)))) {
-                        u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
-                                 (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
-                        ins = epb_group_mask(z, m3 & keep, vb, rin);
-                    }
-                    const u32 cnt = (u32)__popc(ins);
-                    /* the thread holding the last valid byte carries the zero run on */
-                    if (vb > 0 && vb_next == 0) {
-                        u32 r2 = rin;
-                        if (z == valid && !need) {                          /* all-zero group that did not need rin yet */
-                            r2 = 0;
-                            int u = tid - 1;
-                            for (;;) {
-                                if (u < 0) { r2 += sm.st.zrun; break; }
-                                const u32 t = sm.tr[u];
-                                r2 += t & 0xFFu;
-                                if (!(t & 0x100u)) break;
-                                u--;
+                    u32 wn = 0, ins = 0;
+                    if (vb > 0) {
+                        w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4];
+                        const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                                       ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+                        if ((hz & 0x80808080u) || (w.x >> 26) == 0u) {
+                            /* a zero byte, or a first byte <= 3 that may close a zero run of the bytes before */
+                            const u32 valid = (1u << vb) - 1u;
+                            u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
+                            u32 keep = valid;
+                            if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
+                            const bool need = ((w.x >> 26) == 0u) && (keep & 1u);
+                            if (need || (z & (z << 1))) {
+                                u32 rin = 0;
+                                if (need && (q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(sm.win, 16u * (u32)q, zrun_in);
+                                const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
+                                               (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
+                                ins = epb_group_mask(z, m3 & keep, vb, rin);
                             }
                         }
-                        sm.st.zrun_next = epb_group_trail(z, vb, r2);
+                        /* the holder of the window's last byte hands the zero run to the next window */
+                        if (16 * (q + 1) >= chunk_bytes)
+                            sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
                     }
+                    const u32 cnt = (u32)__popc(ins);
                     sm.gi[tid] = (cnt << 8) | (u32)vb;
-                    const int any_ins = __syncthreads_or(cnt != 0u);
-                    u32 before = sm.st.ins_total, pass_ins = 0;
-                    if (any_ins) before += block_excl_scan(cnt, sm.scan, pass_ins);
+                    u32 before = ins_total, pass_ins = 0;
+                    int any_ins;
+                    before += block_excl_scan(cnt, sm.scan[spar], pass_ins, 0, any_ins);
+                    spar ^= 1u;
+                    /* the whole pass stays clear of the slot's end, else everybody goes byte by byte */
+                    const bool roomy = chunk_byte0 + 16u * (u32)(q0 + NT) + ins_total + pass_ins + 4u <= cap;
                     if (vb > 0) {
-                        const u32 D = chunk_byte0 + 16u * (u32)q + before;          /* output byte of the group's first byte */
-                        const bool clean = cnt == 0u && vb == 16;
-                        bool prev_clean = tid > 0, next_clean = tid < NT - 1 && vb_next == 16;
-                        if (any_ins) {
-                            if (tid > 0) prev_clean = sm.gi[tid - 1] == 16u;
-                            if (tid < NT - 1) next_clean = sm.gi[tid + 1] == 16u;
+                        const u32 D = chunk_byte0 + 16u * (u32)q + before;      /* output byte of the group's first byte */
+                        const bool clean = cnt == 0u && (vb & 3) == 0 && roomy;
+                        bool prev_clean = tid > 0 && roomy, next_clean = tid < NT - 1 && vb_next == 16 && roomy;
+                        if (pass_ins) {
+                            if (tid > 0) prev_clean = prev_clean && sm.gi[tid - 1] == 16u;
+                            if (tid < NT - 1) next_clean = next_clean && sm.gi[tid + 1] == 16u;
                         }
                         if (clean) {
-                            const u32 s = (4u - (D & 3u)) & 3u;                     /* source bytes before the first aligned word */
-                            if (s && !prev_clean)
-                                for (u32 k = 0; k < s; k++)
-                                    if (D + k < cap) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
+                            /* vb / 4 whole source words leave as re-aligned 32-bit words */
+                            const u32 s = (4u - (D & 3u)) & 3u;                 /* source bytes before the first aligned word */
                             const u32 sel = realign_selector(s);
+                            const int nw = vb >> 2;
                             u32 *dst = fout32 + ((D + s) >> 2);
                             const u32 o0 = __byte_perm(w.x, w.y, sel), o1 = __byte_perm(w.y, w.z, sel),
                                       o2 = __byte_perm(w.z, w.w, sel), o3 = __byte_perm(w.w, wn, sel);
-                            if (D + s + 16u <= cap && (s == 0u || next_clean)) {
-                                dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
-                            } else {
-                                if (D + s + 4u <= cap) dst[0] = o0;
-                                if (D + s + 8u <= cap) dst[1] = o1;
-                                if (D + s + 12u <= cap) dst[2] = o2;
-                                /* the straddling word: own bytes only */
-                                const u32 nb = s ? 4u - s : 4u;
-                                for (u32 k = 0; k < nb; k++)
-                                    if (D + s + 12u + k < cap) fout[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
+                            const bool whole_last = s == 0u || (vb == 16 && next_clean);   /* else the last word keeps to its own bytes */
+                            if (nw > 1 || whole_last) dst[0] = o0;
+                            if (nw > 2 || (nw == 2 && whole_last)) dst[1] = o1;
+                            if (nw > 3 || (nw == 3 && whole_last)) dst[2] = o2;
+                            if (nw == 4 && whole_last) dst[3] = o3;
+                            if (!whole_last) {
+                                const u32 ol = nw == 4 ? o3 : nw == 3 ? o2 : nw == 2 ? o1 : o0;
+                                const u32 base = D + s + 4u * (u32)(nw - 1);
+                                for (u32 k = 0; k < 4u - s; k++) fout[base + k] = (uint8_t)(ol >> (8u * k));
                             }
+                            if (s && (!prev_clean || vb < 16))                  /* nobody else covers the bytes before the first aligned word */
+                                for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
                         } else {
-                            u32 pos = D;
-                            const u32 ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                            for (int k = 0; k < 16; k++)
-                                if (k < vb) {
-                                    if ((ins >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                                    if (pos < cap) fout[pos] = (uint8_t)(ws[k >> 2] >> (24 - 8 * (k & 3)));
-                                    pos++;
-                                }
+                            emit_bytes(fout, cap, D, w, ins, vb);
                         }
                     }
-                    __syncthreads();
-                    if (tid == 0) {
-                        sm.st.ins_total += pass_ins;
-                        sm.st.zrun = sm.st.zrun_next;
-                    }
+                    ins_total += pass_ins;
                 }
+                if (chunk_bytes > 0) zpar ^= 1u;
+                STAGE_MARK(5);                                  /* emit passes */
+                __syncthreads();                                               /* window fully consumed */
+                {   /* clear the words this window used */
+                    const u32 used = min((u32)CH, w_last - wbase + 1u);
+                    uint4 *w4 = (uint4 *)sm.win;
+                    for (u32 i = (u32)tid; i < (used + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                STAGE_MARK(6);                                  /* barrier + window clear */
+                if (fits) break;                                               /* (frame done) */
+                wbase += CH;                                                   /* a full window has left; the tile goes on in the next one */
                 __syncthreads();
             }
 
-            __syncthreads();
-            if (tid == 0) {
-                sm.st.bitpos = end;
-                if (!last) {
-                    const u32 cw = (tile0 ? 0u : w_lo) + ((w_end - (tile0 ? 0u : w_lo)) / CH) * CH;   /* base of the pass holding w_end */
-                    sm.st.carry = sm.win[w_end - cw];
-                }
-                if (skip_spec) sm.st.last_coded = last_coded_total;
-                sm.st.n_copy = 0;
-                if (last) sizes[f] = total_bytes + sm.st.ins_total;
-            }
-            __syncthreads();
+            bitpos = end;
+            last_coded = last_coded_total;
+            if (last && tid == 0) sizes[f] = total_bytes + ins_total;
         }
     }
+#if COMPOSE_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(&g_stage_cycles[i], (unsigned long long)stage_acc[i]);
+#endif
 }
+
+#if COMPOSE_TIMING
+cudaError_t read_stage_cycles(unsigned long long *h8) {
+    cudaError_t e = cudaMemcpyFromSymbol(h8, g_stage_cycles, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof z);
+    return e;
+}
+#endif
 
 /* ------------------------------------------------------------ rasteriser */
 
@@ -653,7 +761,14 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
                            const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    int grid = n_frames < sm_count * 4 ? n_frames : sm_count * 4;
+    static int ctas_per_sm = 0;           /* resident CTAs per SM for this build (registers / shared memory) */
+    if (ctas_per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel, NT, 0) != cudaSuccess || n < 1) n = 1;
+        ctas_per_sm = n;
+    }
+    const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
+    int grid = n_frames < resident ? n_frames : resident;
     compose_frames_kernel<<<grid, NT, 0, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab,
                                                    d_payload, d_out, d_sizes);
     return cudaGetLastError();

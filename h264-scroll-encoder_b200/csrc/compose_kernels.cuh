@@ -6,7 +6,21 @@
 #include <stdint.h>
 #include "composer_gpu.h"
 
-#define COMPOSE_THREADS   256
+#ifndef COMPOSE_THREADS
+#define COMPOSE_THREADS      256     /* threads per CTA */
+#endif
+#ifndef COMPOSE_MPT
+#define COMPOSE_MPT          8       /* consecutive macroblocks per thread (even) */
+#endif
+#ifndef COMPOSE_MIN_CTAS
+#define COMPOSE_MIN_CTAS     3       /* resident CTAs per SM the register budget is sized for */
+#endif
+#ifndef COMPOSE_WINDOW_WORDS
+#define COMPOSE_WINDOW_WORDS 6144    /* slice words staged in shared memory per pass (multiple of 4) */
+#endif
+#ifndef COMPOSE_COPY_SLOTS
+#define COMPOSE_COPY_SLOTS   512     /* queued splice runs per pass */
+#endif
 #define COMPOSE_MAX_MB_W  H264GPU_MAX_MB_W
 
 namespace h264scroll {

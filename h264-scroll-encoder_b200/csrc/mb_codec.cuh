@@ -421,12 +421,14 @@ HSD u32 vmin2(u32 a, u32 b) {
 }
 
 /* per-MB register record: `meta` beside a 64-bit `code` */
-#define META_LEN_MASK  0x0000FFFFu   /* bits this MB appends through the bit writer (prefix + inline body) */
-#define META_DYN       0x00010000u   /* spliced MB: code = prefix, the payload follows */
-#define META_LONG      0x00020000u   /* inline body > 64 bits: code = packed (mvd_x, mvd_y), rebuilt when written */
-#define META_SPLIT     0x00040000u   /* body <= 64 bits but prefix + body > 64: code = body, prefix put separately */
+#define META_LEN_MASK  0x0000FFFFu   /* bits this item appends through the bit writer (prefix + inline body) */
+#define META_DYN       0x00010000u   /* spliced MB: code = (dyn index << 48) | prefix value; the payload follows */
+#define META_LONG      0x00020000u   /* inline MB that may not fit 64 bits with its prefix:
+                                        code = mvd_x (18 bits) | mvd_y << 18 | prefix value << 36, rebuilt when written */
 #define META_CODED     0x00080000u   /* not P_Skip */
 #define META_REF_SHIFT 24
+#define PREFIX_MAX_OFF   1           /* mb_skip_run is always ue(0) with skip OFF (src/h264_writer.c:629-631) */
+#define PREFIX_MAX_SPEC 41           /* ue(run), run < 2^20 */
 
 /* neighbour-visible motion of a hint: packed mv + ref key (0x100 = unavailable, never matches) */
 HSD void nbr_view(u32 lo, u32 hi, int av, u32 &mv, u32 &ref) {
@@ -483,6 +485,7 @@ HSD int inline_body64(int ref, int dx, int dy, int num_refs, u64 &body) {
  * One inter macroblock: neighbours -> predictor -> P_Skip test -> mvd -> body.
  * lo/hi words of the own hint and of A, B, C(D); av* availability.
  * Returns meta (length, flags, ref) and the 64-bit code (no mb_skip_run prefix yet).
+ * Bodies longer than 64 - prefix_max bits become META_LONG records.
  */
 HSD u32 decide_inter(u32 hlo, u32 hhi, u32 alo, u32 ahi, int avA, u32 blo, u32 bhi, int avB,
                      u32 clo, u32 chi, int avC, int num_refs, int pred_spec, int skip_spec, u64 &code) {
@@ -501,24 +504,52 @@ HSD u32 decide_inter(u32 hlo, u32 hhi, u32 alo, u32 ahi, int avA, u32 blo, u32 b
     const int dy = (int)(int16_t)(hlo >> 16) - (int)(int16_t)(pred >> 16);
     const int blen = inline_body64((int)ref, dx, dy, num_refs, code);
     u32 meta = (u32)blen | META_CODED | (ref << META_REF_SHIFT);
-    if (blen > 64) {
+    if (blen > 64 - (skip_spec ? PREFIX_MAX_SPEC : PREFIX_MAX_OFF)) {
         code = (u64)((u32)dx & 0x3FFFFu) | ((u64)((u32)dy & 0x3FFFFu) << 18);
         meta |= META_LONG;
     }
     return meta;
 }
 
+/*
+ * The same for a macroblock whose neighbourhood is uniform (A, B and C available and equal to
+ * the MB's own hint): every predictor rule yields the MB's own MV, so mvd = 0; with ref 0 that
+ * is also exactly the inferred P_Skip motion.
+ */
+HSD u32 decide_uniform(u32 hhi, int num_refs, int skip_spec, u64 &code) {
+    const u32 ref = hhi & 0xFFu;
+    if (skip_spec && ref == 0u) { code = 0; return 0u; }
+    int blen;
+    code = (u64)(zero_mvd_body((int)ref, num_refs, blen) >> (32 - blen));
+    return (u32)blen | META_CODED | (ref << META_REF_SHIFT);
+}
+
 HSD int long_dx(u64 code) { return ((int)((u32)code << 14)) >> 14; }
 HSD int long_dy(u64 code) { return ((int)((u32)(code >> 18) << 14)) >> 14; }
+HSD u32 long_prefix(u64 code) { return (u32)(code >> 36); }
+HSD u32 dyn_prefix(u64 code) { return (u32)code; }
+HSD u32 dyn_index(u64 code) { return (u32)(code >> 48); }
 
-/* attach the mb_skip_run prefix ue(run) (value pre = run+1 in pn bits) to a record */
+/* attach the mb_skip_run prefix ue(run) (value pre = run + 1 < 2^21, in pn bits) to a coded record */
 HSD void attach_prefix(u64 &code, u32 &meta, u32 pre, int pn) {
-    const u32 blen = meta & META_LEN_MASK;
-    if (!(meta & META_LONG)) {
-        if (blen + (u32)pn <= 64u) code |= (u64)pre << blen;
-        else meta |= META_SPLIT;
-    }
+    if (meta & META_LONG) code |= (u64)pre << 36;
+    else if (meta & META_DYN) code |= (u64)pre;
+    else code |= (u64)pre << (meta & META_LEN_MASK);      /* body length <= 64 - prefix_max */
     meta += (u32)pn;
+}
+
+/*
+ * Merge step: consecutive plain codes of a thread are concatenated into one <= 64-bit item so
+ * that the bit writer runs once per item instead of once per macroblock.  (acc, accn) is the
+ * running item; `seal` tells the caller to store it (at the previous index) before this code
+ * starts a new one.
+ */
+HSD bool merge_plain(u64 &acc, u32 &accn, u64 code, u32 n, u64 &sealed, u32 &sealed_n) {
+    bool seal = accn + n > 64u;
+    if (seal) { sealed = acc; sealed_n = accn; acc = 0; accn = 0; }
+    acc = n < 64u ? ((acc << n) | code) : code;              /* n == 64 only ever follows a seal (acc == 0) */
+    accn += n;
+    return seal;
 }
 
 /* ---- sequential bit writer ------------------------------------------- */
@@ -580,6 +611,30 @@ HSD u32 epb_group_mask(u32 z, u32 m3, int vb, u32 rin) {
 HSD u32 epb_group_trail(u32 z, int vb, u32 rin) {
     const u32 t = ~z & ((1u << vb) - 1u);
     return t ? (u32)(vb - 32 + clz32(t)) : (u32)vb + rin;
+}
+
+/*
+ * Zero bytes immediately before window byte b (the run that rbsp_to_ebsp's zero_count has seen,
+ * src/nal.c:29-47): scans the window backwards; a run reaching the window start continues with
+ * the state carried over from the bytes emitted before (zrun_in).
+ */
+HSD u32 zeros_before(const u32 *win, u32 b, u32 zrun_in) {
+    u32 r = 0;
+    int i = (int)(b >> 2);
+    const u32 k = b & 3u;
+    if (k) {
+        u32 v = win[i] >> (8u * (4u - k));
+        for (u32 t = 0; t < k; t++, v >>= 8) {
+            if (v & 0xFFu) return r;
+            r++;
+        }
+    }
+    for (i--; i >= 0; i--) {
+        const u32 v = win[i];
+        if (v) return r + ((v & 0xFFu) ? 0u : (v & 0xFF00u) ? 1u : (v & 0xFF0000u) ? 2u : 3u);
+        r += 4u;
+    }
+    return r + zrun_in;
 }
 
 /* byte-permute selector: output word = stream bytes s..s+3 of the MSB-first pair (a, b) */

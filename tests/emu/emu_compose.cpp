@@ -33,6 +33,7 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                                       const H264GpuDynDesc *dyns, const uint32_t *dyn_tab,
                                       const uint8_t *payload, uint8_t *out_base,
                                       int NTHREADS, int CH) {
+    const int uniform_mode = 1;      /* take the kernel's uniform-neighbourhood shortcut where it applies */
     const H264GpuFrameDesc &d = *desc;
     const int W = d.mb_w, N = W * (int)d.mb_h;
     const int num_refs = d.num_refs;
@@ -60,7 +61,6 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
 
     std::vector<u64> code(TILE);
     std::vector<u32> meta(TILE), dynlen(NTHREADS), Lv(NTHREADS), Ov(NTHREADS);
-    std::vector<int> previn(NTHREADS);
     std::vector<u32> win(CH + 8);
 
     for (int t0 = 0; t0 < N; t0 += TILE) {
@@ -80,8 +80,12 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                         const bool hasC = x + 1 < W;
                         const int avC = avB && (hasC || x > 0);
                         const H2 a = H(g - 1), b = H(g - W), cc = hasC ? H(g - W + 1) : H(g - W - 1);
-                        m = decide_inter(h.x, h.y, a.x, a.y, avA, b.x, b.y, avB, cc.x, cc.y, avC,
-                                         num_refs, pred_spec, skip_spec, c);
+                        const u32 hkey = h.y & 0xFFFFu;
+                        const bool uni = avA && avC && a.x == h.x && b.x == h.x && cc.x == h.x &&
+                                         (a.y & 0xFFFFu) == hkey && (b.y & 0xFFFFu) == hkey && (cc.y & 0xFFFFu) == hkey;
+                        if (uni && (uniform_mode & 1)) m = decide_uniform(h.y, num_refs, skip_spec, c);
+                        else m = decide_inter(h.x, h.y, a.x, a.y, avA, b.x, b.y, avB, cc.x, cc.y, avC,
+                                              num_refs, pred_spec, skip_spec, c);
                     } else {
                         const u32 di = h.y >> 16;
                         dynlen[t] += tab[di + 1] - tab[di];
@@ -95,7 +99,6 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
         /* prefixes */
         int prev = last_coded;
         for (int t = 0; t < NTHREADS; t++) {
-            previn[t] = prev;
             const int g0 = t0 + t * MPT;
             for (int k = 0; k < MPT; k++) {
                 u32 &m = meta[t * MPT + k];
@@ -106,6 +109,26 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
             }
         }
         const int last_coded_total = prev;
+        /* merge runs of plain codes into <= 64-bit items; thread bit counts */
+        for (int t = 0; t < NTHREADS; t++) {
+            u64 acc = 0; u32 accn = 0, L = dynlen[t];
+            u64 *cd = &code[t * MPT]; u32 *mt = &meta[t * MPT];
+            for (int k = 0; k < MPT; k++) {
+                const u64 c = cd[k]; const u32 m = mt[k];
+                L += m & META_LEN_MASK;
+                cd[k] = 0; mt[k] = 0;
+                if (m & (META_DYN | META_LONG)) {
+                    if (k > 0 && accn) { cd[k - 1] = acc; mt[k - 1] = accn; acc = 0; accn = 0; }
+                    cd[k] = c; mt[k] = m;
+                } else if (m & META_CODED) {
+                    u64 sc = 0; u32 sn = 0;
+                    const bool seal = merge_plain(acc, accn, c, m & META_LEN_MASK, sc, sn);
+                    if (k > 0 && seal) { cd[k - 1] = sc; mt[k - 1] = sn; }
+                }
+            }
+            if (accn) { cd[MPT - 1] = acc; mt[MPT - 1] = accn; }
+            Lv[t] = L;
+        }
         /* trailer + scan */
         u32 tr_code = 1, tr_len = 1;
         if (last && skip_spec) {
@@ -119,9 +142,8 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
             const int nmb = std::min(std::max(N - g0, 0), MPT);
             const bool owns = last && nmb > 0 && g0 + nmb == N;
             if (owns) trailer_thread = t;
-            u32 L = dynlen[t] + (owns ? tr_len : 0);
-            for (int k = 0; k < MPT; k++) L += meta[t * MPT + k] & META_LEN_MASK;
-            Lv[t] = L; Ov[t] = run; run += L;
+            Lv[t] += owns ? tr_len : 0;
+            Ov[t] = run; run += Lv[t];
         }
         const u32 end = run;
         const u32 w_lo = bitpos >> 5;
@@ -149,36 +171,32 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                         const u32 n = std::min(32u, hdr_total - p);
                         bp_put(bp, (u64)(header_bits32(d.hdr_bits, d.nal_header, p) >> (32 - n)), n, win.data(), wbase, CH);
                     }
-                int pv = previn[t];
                 for (int k = 0; k < MPT; k++) {
                     const u32 m = meta[t * MPT + k];
                     const u64 c = code[t * MPT + k];
-                    if (!(m & META_CODED)) continue;
-                    const u32 n = m & META_LEN_MASK;
-                    if (!(m & (META_DYN | META_LONG | META_SPLIT))) bp_put(bp, c, n, win.data(), wbase, CH);
-                    else {
-                        const u32 pre = skip_spec ? (u32)(g0 + k - pv) : 1u;
-                        const u32 pn = 63 - 2 * clz32(pre);
-                        bp_put(bp, pre, pn, win.data(), wbase, CH);
-                        if (m & META_SPLIT) bp_put(bp, c, n - pn, win.data(), wbase, CH);
-                        else if (m & META_LONG) {
-                            MbEntry e;
-                            int bl = encode_p16x16_body((int)(m >> META_REF_SHIFT), long_dx(c), long_dy(c), num_refs, e);
-                            bp_put(bp, e.w1, 32, win.data(), wbase, CH);
-                            bp_put(bp, e.w2, 32, win.data(), wbase, CH);
-                            bl -= 64;
-                            bp_put(bp, e.w3 >> (32 - bl), bl, win.data(), wbase, CH);
-                        } else {
-                            const u32 di = (u32)(c >> 48);
-                            const u32 b0 = tab[di], len = tab[di + 1] - b0;
-                            const u32 hb = std::min(len, (32u - bp.fill) & 31u);
-                            if (hb) bp_put(bp, pay32(pay_words, n_pay_words, b0) >> (32 - hb), hb, win.data(), wbase, CH);
-                            const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31;
-                            if (nw) { copies.push_back({bp.j, b0 + hb, nw}); bp.j += nw; }
-                            if (tb) bp_put(bp, pay32(pay_words, n_pay_words, b0 + len - tb) >> (32 - tb), tb, win.data(), wbase, CH);
+                    if (!m) continue;
+                    if (!(m & (META_DYN | META_LONG))) bp_put(bp, c, m, win.data(), wbase, CH);
+                    else if (m & META_LONG) {
+                        const u32 pre = long_prefix(c);
+                        bp_put(bp, pre, 63 - 2 * clz32(pre), win.data(), wbase, CH);
+                        MbEntry e;
+                        int bl = encode_p16x16_body((int)(m >> META_REF_SHIFT), long_dx(c), long_dy(c), num_refs, e);
+                        const u32 ws[3] = {e.w1, e.w2, e.w3};
+                        for (int i = 0; i < 3 && bl > 0; i++, bl -= 32) {
+                            const u32 n = (u32)std::min(bl, 32);
+                            bp_put(bp, ws[i] >> (32 - n), n, win.data(), wbase, CH);
                         }
+                    } else {
+                        const u32 pre = dyn_prefix(c);
+                        bp_put(bp, pre, 63 - 2 * clz32(pre), win.data(), wbase, CH);
+                        const u32 di = dyn_index(c);
+                        const u32 b0 = tab[di], len = tab[di + 1] - b0;
+                        const u32 hb = std::min(len, (32u - bp.fill) & 31u);
+                        if (hb) bp_put(bp, pay32(pay_words, n_pay_words, b0) >> (32 - hb), hb, win.data(), wbase, CH);
+                        const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31;
+                        if (nw) { copies.push_back({bp.j, b0 + hb, nw}); bp.j += nw; }
+                        if (tb) bp_put(bp, pay32(pay_words, n_pay_words, b0 + len - tb) >> (32 - tb), tb, win.data(), wbase, CH);
                     }
-                    pv = g0 + k;
                 }
                 if (t == trailer_thread) bp_put(bp, tr_code, tr_len, win.data(), wbase, CH);
                 if (bp.fill) {
@@ -195,75 +213,62 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
             const u32 e_hi = std::min(wbase + (u32)CH, w_stop);
             const u32 chunk_byte0 = wbase << 2;
             const int chunk_bytes = e_hi > wbase ? (int)((last ? std::min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+            const u32 zrun_in = zrun;
             for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NTHREADS) {
-                std::vector<u32> tr(NTHREADS), zs(NTHREADS), insv(NTHREADS), rins(NTHREADS);
-                std::vector<int> vbs(NTHREADS);
+                std::vector<u32> insv(NTHREADS, 0);
+                std::vector<int> vbs(NTHREADS, 0);
                 for (int t = 0; t < NTHREADS; t++) {
                     const int q = q0 + t;
                     const int vb = std::min(std::max(chunk_bytes - 16 * q, 0), 16);
-                    u32 w[4] = {~0u, ~0u, ~0u, ~0u};
-                    if (vb > 0) for (int i = 0; i < 4; i++) w[i] = win[4 * q + i];
-                    u32 z = zero_nib(w[0]) | (zero_nib(w[1]) << 4) | (zero_nib(w[2]) << 8) | (zero_nib(w[3]) << 12);
-                    const u32 valid = (1u << vb) - 1u;
-                    z &= valid;
-                    if (chunk_byte0 == 0 && q == 0) z &= ~0x1Fu;
-                    zs[t] = z; vbs[t] = vb;
-                    tr[t] = epb_group_trail(z, std::max(vb, 1), 0) | (z == valid ? 0x100u : 0u);
-                }
-                u32 pass_ins = 0, zrun_next = zrun;
-                for (int t = 0; t < NTHREADS; t++) {
-                    const int q = q0 + t, vb = vbs[t];
+                    vbs[t] = vb;
                     if (vb == 0) continue;
-                    u32 w[5];
-                    for (int i = 0; i < 5; i++) w[i] = win[4 * q + i];
-                    const u32 valid = (1u << vb) - 1u, z = zs[t];
-                    u32 keep = valid;
-                    if (chunk_byte0 == 0 && q == 0) keep &= ~0x1Fu;
-                    const bool b0_le3 = (w[0] >> 26) == 0 && (keep & 1);
-                    const bool need = b0_le3 || (z & 1);
-                    u32 rin = 0;
-                    if (need) {
-                        int u = t - 1;
-                        for (;;) {
-                            if (u < 0) { rin += zrun; break; }
-                            rin += tr[u] & 0xFF;
-                            if (!(tr[u] & 0x100)) break;
-                            u--;
+                    u32 w[4];
+                    for (int i = 0; i < 4; i++) w[i] = win[4 * q + i];
+                    const u32 hz = ((w[0] - 0x01010101u) & ~w[0]) | ((w[1] - 0x01010101u) & ~w[1]) |
+                                   ((w[2] - 0x01010101u) & ~w[2]) | ((w[3] - 0x01010101u) & ~w[3]);
+                    if ((hz & 0x80808080u) || (w[0] >> 26) == 0) {
+                        const u32 valid = (1u << vb) - 1u;
+                        u32 z = (zero_nib(w[0]) | (zero_nib(w[1]) << 4) | (zero_nib(w[2]) << 8) | (zero_nib(w[3]) << 12)) & valid;
+                        u32 keep = valid;
+                        if (chunk_byte0 == 0 && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }
+                        const bool need = ((w[0] >> 26) == 0) && (keep & 1);
+                        if (need || (z & (z << 1))) {
+                            u32 rin = 0;
+                            if (need && (q == 0 || (win[4 * q - 1] & 0xFF) == 0)) rin = zeros_before(win.data(), 16u * q, zrun_in);
+                            const u32 m3 = zero_nib(w[0] & 0xFCFCFCFCu) | (zero_nib(w[1] & 0xFCFCFCFCu) << 4) |
+                                           (zero_nib(w[2] & 0xFCFCFCFCu) << 8) | (zero_nib(w[3] & 0xFCFCFCFCu) << 12);
+                            insv[t] = epb_group_mask(z, m3 & keep, vb, rin);
                         }
                     }
-                    u32 ins = 0;
-                    if (need || (z & (z << 1))) {
-                        u32 m3 = zero_nib(w[0] & 0xFCFCFCFCu) | (zero_nib(w[1] & 0xFCFCFCFCu) << 4) |
-                                 (zero_nib(w[2] & 0xFCFCFCFCu) << 8) | (zero_nib(w[3] & 0xFCFCFCFCu) << 12);
-                        ins = epb_group_mask(z, m3 & keep, vb, rin);
-                    }
-                    insv[t] = ins; rins[t] = rin;
-                    const int vb_next = t == NTHREADS - 1 ? 0 : std::min(std::max(chunk_bytes - 16 * (q + 1), 0), 16);
-                    if (vb_next == 0) zrun_next = epb_group_trail(z, vb, rin);
+                    if (16 * (q + 1) >= chunk_bytes) zrun = zeros_before(win.data(), (u32)chunk_bytes, zrun_in);
                 }
+                u32 pass_ins = 0;
+                for (int t = 0; t < NTHREADS; t++) pass_ins += (u32)__builtin_popcount(insv[t]);
+                const bool roomy = chunk_byte0 + 16u * (u32)(q0 + NTHREADS) + ins_total + pass_ins + 4u <= cap;
                 u32 before = ins_total;
                 for (int t = 0; t < NTHREADS; t++) {
                     const int q = q0 + t, vb = vbs[t];
                     if (vb == 0) continue;
                     const u32 cnt = (u32)__builtin_popcount(insv[t]);
                     const u32 D = chunk_byte0 + 16u * q + before;
-                    auto is_clean = [&](int u) { return u >= 0 && u < NTHREADS && vbs[u] == 16 && insv[u] == 0; };
-                    const bool clean = is_clean(t), prev_clean = is_clean(t - 1), next_clean = is_clean(t + 1);
+                    auto full_clean = [&](int u) { return u >= 0 && u < NTHREADS && vbs[u] == 16 && insv[u] == 0 && roomy; };
+                    const bool clean = cnt == 0 && (vb & 3) == 0 && roomy;
+                    const bool prev_clean = full_clean(t - 1), next_clean = full_clean(t + 1);
                     u32 w[5];
                     for (int i = 0; i < 5; i++) w[i] = win[4 * q + i];
                     if (clean) {
                         const u32 s = (4u - (D & 3u)) & 3u;
-                        if (s && !prev_clean)
-                            for (u32 k = 0; k < s; k++) if (D + k < cap) fout[D + k] = (uint8_t)(w[0] >> (24 - 8 * k));
                         const u32 sel = realign_selector(s);
+                        const int nw = vb >> 2;
                         u32 o[4];
                         for (int i = 0; i < 4; i++) o[i] = byte_perm(w[i], w[i + 1], sel);
-                        const u32 nfull = (s == 0 || next_clean) ? 4 : 3;
-                        for (u32 i = 0; i < nfull; i++)
-                            if (D + s + 4 * i + 4 <= cap) memcpy(fout + D + s + 4 * i, &o[i], 4);
-                            else for (u32 k = 0; k < 4; k++) if (D + s + 4 * i + k < cap) fout[D + s + 4 * i + k] = (uint8_t)(o[i] >> (8 * k));
-                        if (nfull == 3)
-                            for (u32 k = 0; k < 4u - s; k++) if (D + s + 12 + k < cap) fout[D + s + 12 + k] = (uint8_t)(o[3] >> (8 * k));
+                        const bool whole_last = s == 0 || (vb == 16 && next_clean);
+                        for (int i = 0; i < nw; i++)
+                            if (i < nw - 1 || whole_last) memcpy(fout + D + s + 4 * i, &o[i], 4);
+                        if (!whole_last)
+                            for (u32 k = 0; k < 4u - s; k++) fout[D + s + 4 * (nw - 1) + k] = (uint8_t)(o[nw - 1] >> (8 * k));
+                        if (s && (!prev_clean || vb < 16))
+                            for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w[0] >> (24 - 8 * k));
                     } else {
                         u32 pos = D;
                         for (int k = 0; k < vb; k++) {
@@ -272,10 +277,9 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                             pos++;
                         }
                     }
-                    before += cnt; pass_ins += cnt;
+                    before += cnt;
                 }
                 ins_total += pass_ins;
-                zrun = zrun_next;
             }
         }
         bitpos = end;
