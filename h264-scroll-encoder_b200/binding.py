@@ -17,7 +17,7 @@ GPU_SYMBOLS = [
     "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
     "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
-    "h264gpu_compose_host", "h264gpu_launch_count"]
+    "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints"]
 REFERENCE_API_SYMBOLS = [
     # include/composer.h
     "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
@@ -67,6 +67,7 @@ def load_library(path=None):
     L.h264gpu_compose_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
     L.h264gpu_raster_regions.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     L.h264gpu_pack_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.h264gpu_canonicalize_hints.argtypes = [vp, sz, vp]
     L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
     L.h264gpu_launch_count.restype = C.c_uint64
     return L
@@ -161,6 +162,9 @@ class GpuComposer:
         p = lambda b: b.ptr if b is not None else None
         self.check(self.lib.h264gpu_raster_regions(p(d_rdesc), n, max_mbs, p(d_regions), p(d_dyn_info),
                                                    p(d_hints), stream))
+
+    def canonicalize_hints(self, d_hints, n_hints, stream=None):
+        self.check(self.lib.h264gpu_canonicalize_hints(d_hints.ptr, n_hints, stream))
 
     def pack_frames(self, d_desc, d_sizes, n, d_slots, d_packed, d_offsets, stream=None):
         self.check(self.lib.h264gpu_pack_frames(d_desc.ptr, d_sizes.ptr, n, d_slots.ptr, d_packed.ptr,

@@ -168,6 +168,15 @@ int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int m
     return H264GPU_OK;
 }
 
+int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *stream) {
+    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    if (!d_hints && n_hints) return fail(H264GPU_ERR_ARG, "null argument");
+    cudaError_t e = h264scroll::launch_canonicalize(d_hints, n_hints, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "canonicalize launch", e);
+    if (n_hints > 0) g_launches.fetch_add(1);
+    return H264GPU_OK;
+}
+
 int h264gpu_pack_frames(const H264GpuFrameDesc *d_desc, const uint32_t *d_sizes, int n_frames,
                         const uint8_t *d_slots, uint8_t *d_packed, uint64_t *d_offsets, void *stream) {
     if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
@@ -225,6 +234,9 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
         if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_pay, h_payload, payload_bytes, cudaMemcpyHostToDevice, st);
     }
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "upload", e);
+    e = h264scroll::launch_canonicalize((H264GpuMbHint *)(base + o_hint), n_hints, st);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "canonicalize launch", e);
+    g_launches.fetch_add(1);
     e = h264scroll::launch_compose((const H264GpuFrameDesc *)(base + o_desc), n_frames,
                                    (const H264GpuMbHint *)(base + o_hint),
                                    (const H264GpuDynDesc *)(base + o_dyn),

@@ -1,27 +1,27 @@
 /*
  * compose_kernels.cu - sm_100a kernels of the P-slice composer.
  *
- * compose_frames_kernel: one CTA composes one frame at a time (grid-stride over
- * frames); a frame is walked in tiles of TILE = 256 threads x 8 macroblocks.
- * Everything per-macroblock lives in registers; shared memory only holds the
- * slice bits of the tile (the "window") on their way out.
+ * compose_frames_kernel (v4): one CTA composes one frame at a time (grid-stride over frames).
+ * A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns one
+ * segment, a tile is up to 256 consecutive segments.
  *
- *   load     every thread reads its 8 consecutive hints (4 x 128-bit loads) plus
- *            the 10 hints above and the one to the left straight from global memory
- *            (the rows above come back from L1/L2); nothing is staged
- *   decide   per MB: A/B/C(D) neighbour views, packed int16x2 predictor, P_Skip test,
- *            mvd, closed-form Exp-Golomb -> a <= 64-bit code + length in registers
+ *   stage    the hints of the tile plus the row above it are copied global -> shared with
+ *            16-byte cp.async into a swizzled layout (every thread later reads its own 64 bytes
+ *            with conflict-free 128-bit loads); the copy of the next tile - of the next frame
+ *            when this one ends - is in flight while the current tile is composed
+ *   decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test,
+ *            mvd, closed-form Exp-Golomb -> a <= 32-bit code + length in registers.  Where a whole
+ *            warp sits in uniform motion the constant code is taken instead
  *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
  *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
  *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
- *   write    each thread appends its codes with a sequential bit writer: whole words
- *            are plain stores; the partial first/last words of neighbouring threads are
- *            merged with a segmented warp-shuffle OR, so shared-memory atomics are left
- *            for the two words a warp shares with its neighbours
- *   splice   whole words inside a spliced macroblock are funnel-shifted in from the
- *            pre-encoded payload by groups of 8 lanes (semantics of copy_bits,
- *            src/h264_writer.c:228); the partial words at both ends go through the
- *            owner thread's bit writer
+ *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word
+ *            integer (picked per warp), shifts it to its slice bit offset and stores whole words;
+ *            partial first/last words of neighbouring threads are merged by shuffle
+ *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice
+ *            trailer - becomes 16-byte work items that are spread over all lanes of the CTA:
+ *            one lane splices one pre-encoded MB (copy_bits, src/h264_writer.c:228) with funnel
+ *            shifts, whole words as plain stores, edge words with shared-memory atomicOr
  *   emit     emulation prevention (src/nal.c:24-50) on 16-byte groups: zero-byte masks,
  *            a bit-parallel run-parity rule, prefix sum of the insert counts; groups
  *            without insertions leave as re-aligned 32-bit words (one byte-permute each)
@@ -36,33 +36,22 @@
 namespace h264scroll {
 
 constexpr int NT = COMPOSE_THREADS;      /* threads per CTA */
-constexpr int MPT = COMPOSE_MPT;         /* consecutive macroblocks per thread */
-constexpr int TILE = NT * MPT;           /* macroblocks per tile */
+constexpr int MPT = 8;                   /* macroblocks per segment / thread */
 constexpr int NW = NT / 32;
 constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass */
-constexpr int LCAP = COMPOSE_COPY_SLOTS; /* splice copy list entries per pass */
+constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
+constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
 constexpr u32 FULL = 0xFFFFFFFFu;
-#ifndef COMPOSE_ABLATE
-#define COMPOSE_ABLATE 0                 /* timing experiments only (scripts/variant.sh); 0 in the shipped build */
-#endif
-#ifndef COMPOSE_TIMING
-#define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
-#endif
-#if COMPOSE_TIMING
-__device__ unsigned long long g_stage_cycles[8];
-#define STAGE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); stage_acc[i] += t_ - stage_t; stage_t = t_; } } while (0)
-#else
-#define STAGE_MARK(i) do { } while (0)
-#endif
 
 struct __align__(16) ComposeSmem {
     u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
-    uint4 copy[LCAP];                    /* {first window word, payload bit, words, -} */
+    uint4 hbuf[2][HBS * 4];              /* staged hint tiles (swizzled 16-byte chunks), double buffered */
+    uint4 items[LCAP];                   /* work queue */
     u32 gi[NT];                          /* emit: (insert count << 8) | valid bytes of each group */
     u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
     u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
-    u32 n_copy[2];                       /* queued splice runs, double buffered per tile */
-    /* per-frame constants only the splice and emit stages need: kept out of the register file */
+    u32 n_items[2];                      /* queued items, double buffered per tile */
+    /* per-frame constants only the queue and emit stages need: kept out of the register file */
     const u32 *tab;                      /* the frame's payload bit-offset table */
     const u32 *pay_words;                /* the frame's payload */
     u32 n_pay_words;
@@ -74,7 +63,7 @@ struct __align__(16) ComposeSmem {
  * Exclusive prefix sum over the CTA; every thread gets its offset and the total.  One barrier:
  * consecutive scans must alternate between the two s_scan buffers.
  */
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total, int pred, int &any_pred) {
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 inc = v;
 #pragma unroll
@@ -83,7 +72,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total, i
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_scan[warp] = inc;
-    any_pred = __syncthreads_or(pred);                 /* the scan's barrier doubles as a block-wide vote */
+    __syncthreads();
     const u32 wsum = lane < NW ? s_scan[lane] : 0u;    /* every warp scans the NW warp totals itself */
     u32 winc = wsum;
 #pragma unroll
@@ -123,89 +112,91 @@ __device__ __noinline__ int block_excl_scan_max(int v, int *s_scan, int &total) 
     return max(wexc, exc);
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+/* ---- asynchronous global -> shared copies ---------------------------------------------- */
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(u32 dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(u32 dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-/* payload word wi as an MSB-first word (payload bytes are a bit stream, so big-endian in memory) */
-__device__ __forceinline__ u32 payload_word(const u32 *__restrict__ pw, u32 n_words, u32 wi) {
-    return wi < n_words ? __byte_perm(__ldg(pw + wi), 0u, 0x0123u) : 0u;
+/* geometry of a frame as the tile loop needs it */
+struct FrameGeo {
+    const uint2 *fh;      /* the frame's dense hint map */
+    int W, H;
+    int tpr;              /* segments (threads) per row */
+    int n_seg;            /* tpr * H */
+    int seg_max;          /* segments per tile */
+    u32 tpr_magic;        /* s / tpr == umulhi(s, tpr_magic) for s < 2^25 (tpr > 1) */
+};
+
+__device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict__ descs, int f,
+                                             const H264GpuMbHint *__restrict__ hints) {
+    const uint4 *dq = (const uint4 *)(descs + f);
+    const uint4 d2 = __ldg(dq + 2), d3 = __ldg(dq + 3);
+    FrameGeo g;
+    g.fh = (const uint2 *)hints + ((u64)d2.x | ((u64)d2.y << 32));
+    g.W = (int)(d3.z & 0xFFFFu);
+    g.H = (int)(d3.z >> 16);
+    g.tpr = (g.W + MPT - 1) / MPT;
+    g.n_seg = g.tpr * g.H;
+    g.seg_max = min(NT, HBS - g.tpr - 1);
+    g.tpr_magic = 0xFFFFFFFFu / (u32)g.tpr + 1u;
+    return g;
 }
 
-/* 32 payload bits from bit position p */
-__device__ __forceinline__ u32 payload_ld32(const u32 *__restrict__ pw, u32 n_words, u32 p) {
-    const u32 wi = p >> 5;
-    return __funnelshift_l(payload_word(pw, n_words, wi + 1u), payload_word(pw, n_words, wi), p & 31u);
-}
-
-/* n whole slice words of a spliced macroblock: window word j.. <- payload bits p.. (copy_bits, src/h264_writer.c:228) */
-__device__ __forceinline__ void splice_words(u32 *win, u32 j, u32 n, const u32 *__restrict__ pw, u32 n_words, u32 p) {
-    u32 wi = p >> 5;
-    const u32 sh = p & 31u;
-    u32 a = payload_word(pw, n_words, wi);
-    u32 i = 0;
-    for (; i + 4u <= n; i += 4u) {                          /* four independent loads in flight */
-        const u32 b0 = payload_word(pw, n_words, wi + 1u), b1 = payload_word(pw, n_words, wi + 2u),
-                  b2 = payload_word(pw, n_words, wi + 3u), b3 = payload_word(pw, n_words, wi + 4u);
-        if (j + i < (u32)CH) win[j + i] = __funnelshift_l(b0, a, sh);
-        if (j + i + 1u < (u32)CH) win[j + i + 1u] = __funnelshift_l(b1, b0, sh);
-        if (j + i + 2u < (u32)CH) win[j + i + 2u] = __funnelshift_l(b2, b1, sh);
-        if (j + i + 3u < (u32)CH) win[j + i + 3u] = __funnelshift_l(b3, b2, sh);
-        a = b3;
-        wi += 4u;
-    }
-    for (; i < n; i++) {
-        const u32 b = payload_word(pw, n_words, ++wi);
-        if (j + i < (u32)CH) win[j + i] = __funnelshift_l(b, a, sh);
-        a = b;
-    }
-}
-
-/* the rare inline macroblock whose code may exceed 64 bits: prefix, then the body word by word */
-__device__ __noinline__ void put_long(BitPut &bp, u64 code, u32 meta, int num_refs, u32 *win, u32 wbase) {
-    const u32 pre = long_prefix(code);
-    bp_put(bp, (u64)pre, 63u - 2u * (u32)__clz((int)pre), win, wbase, CH);
-    MbEntry e;
-    int bl = encode_p16x16_body((int)(meta >> META_REF_SHIFT), long_dx(code), long_dy(code), num_refs, e);
-    const u32 ws[3] = {e.w1, e.w2, e.w3};
-    for (int i = 0; i < 3 && bl > 0; i++, bl -= 32) {
-        const u32 n = (u32)min(bl, 32);
-        bp_put(bp, (u64)(ws[i] >> (32u - n)), n, win, wbase, CH);
-    }
+__device__ __forceinline__ int seg_row(const FrameGeo &g, int s) {
+    return g.tpr == 1 ? s : (int)__umulhi((u32)s, g.tpr_magic);
 }
 
 /*
- * A spliced macroblock: mb_skip_run prefix, then its pre-encoded bits.  The partial words at both
- * ends go through the bit writer, the whole words in between are queued for the copy stage.
+ * Stage the hints of segments [s0 - tpr - 1, s0 + n) into buf: slot q holds segment s0 - tpr - 1 + q
+ * (8 hints, the tail of a row's last segment stays unwritten), chunks swizzled.  Segments before the
+ * frame's first are filled with the "unavailable" hint.
  */
-__device__ __noinline__ void put_spliced(BitPut &bp, u64 code, ComposeSmem &sm, u32 wbase, u32 *n_copy) {
-    const u32 *__restrict__ tab = sm.tab;
-    const u32 *__restrict__ pw = sm.pay_words;
-    const u32 n_words = sm.n_pay_words;
-    u32 *win = sm.win;
-    const u32 pre = dyn_prefix(code);
-    bp_put(bp, (u64)pre, 63u - 2u * (u32)__clz((int)pre), win, wbase, CH);
-    const u32 di = dyn_index(code);
-    const u32 b0 = __ldg(tab + di), len = __ldg(tab + di + 1) - b0;
-    const u32 hb = min(len, (32u - bp.fill) & 31u);
-    if (hb) bp_put(bp, (u64)(payload_ld32(pw, n_words, b0) >> (32u - hb)), hb, win, wbase, CH);
-    const u32 rest = len - hb, nw = rest >> 5, tb = rest & 31u;
-    if (nw) {
-        const u32 slot = atomicAdd(n_copy, 1u);
-        if (slot < (u32)LCAP) sm.copy[slot] = make_uint4(bp.j - wbase, b0 + hb, nw, 0u);
-        else splice_words(win, bp.j - wbase, nw, pw, n_words, b0 + hb);      /* list full: copy it here */
-        bp.j += nw;
+__device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s0, int n) {
+    const int s_base = s0 - g.tpr - 1;
+    const int n_chunks = 4 * (n + g.tpr + 1);
+    const u32 buf_s = smem_u32(buf);
+    if ((g.W & 7) == 0) {
+        /* segments tile the dense map exactly: chunk c of the tile is chunk 4 * s_base + c of the map */
+        const uint4 *src = (const uint4 *)g.fh + 4 * (long long)s_base;
+        const int c_lo = -4 * s_base;                        /* first chunk inside the frame */
+        const int c_hi = 4 * (g.n_seg - s_base);             /* first chunk past its end */
+        for (int c = threadIdx.x; c < n_chunks; c += NT) {
+            const u32 pc = hint_swizzle((u32)c);
+            if (c >= c_lo) { if (c < c_hi) cp_async16(buf_s + 16u * pc, src + c); }
+            else buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
+        }
+    } else {
+        for (int c = threadIdx.x; c < n_chunks; c += NT) {
+            const u32 pc = hint_swizzle((u32)c);
+            const int s = s_base + (c >> 2);
+            if (s < 0) { buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL); continue; }
+            if (s >= g.n_seg) continue;
+            const int row = seg_row(g, s), x = MPT * (s - row * g.tpr) + 2 * (c & 3);
+            const long long gi = (long long)row * g.W + x;
+            if (x + 1 < g.W && !(gi & 1)) cp_async16(buf_s + 16u * pc, g.fh + gi);
+            else {
+                if (x < g.W) cp_async8(buf_s + 16u * pc, g.fh + gi);
+                if (x + 1 < g.W) cp_async8(buf_s + 16u * pc + 8u, g.fh + gi + 1);
+            }
+        }
     }
-    if (tb) bp_put(bp, (u64)(payload_ld32(pw, n_words, b0 + len - tb) >> (32u - tb)), tb, win, wbase, CH);
 }
 
-/* the copy stage: one lane per queued run */
-__device__ __noinline__ void splice_queued(ComposeSmem &sm, u32 n_copy) {
-    const u32 *__restrict__ pw = sm.pay_words;
-    const u32 n_words = sm.n_pay_words;
-    for (u32 d = threadIdx.x; d < n_copy; d += NT) {
-        const uint4 c = sm.copy[d];
-        splice_words(sm.win, c.x, c.z, pw, n_words, c.y);
-    }
+/* hint i (0..7) of slot q / 16-byte chunk of a staged tile */
+__device__ __forceinline__ uint2 staged_hint(const uint4 *buf, int q, int i) {
+    const u32 pc = hint_swizzle((u32)(4 * q + (i >> 1)));
+    return ((const uint2 *)buf)[2u * pc + (u32)(i & 1)];
+}
+__device__ __forceinline__ uint4 staged_chunk(const uint4 *buf, int q, int sub) {
+    return buf[hint_swizzle((u32)(4 * q + sub))];
 }
 
 /* out of line: the backward scan is rare */
@@ -221,6 +212,125 @@ __device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w
     }
 }
 
+/*
+ * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from
+ * chunk_byte0 on).  Returns the bytes inserted; leaves the closing zero run in sm.zrun[zpar ^ 1].
+ * Called by all threads after a barrier; ends without one.
+ */
+__device__ __forceinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar, u32 &spar) {
+    const int tid = threadIdx.x;
+    const u32 zrun_in = sm.zrun[zpar];
+    const u32 cap = sm.cap;
+    uint8_t *fout = sm.fout;
+    u32 *fout32 = (u32 *)fout;
+    const u32 ins_in = ins_total;
+    for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NT) {
+        const int q = q0 + tid;
+        const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+        const int vb_next = tid == NT - 1 ? 0 : min(max(chunk_bytes - 16 * (q + 1), 0), 16);
+        uint4 w = make_uint4(FULL, FULL, FULL, FULL);
+        u32 wn = 0, ins = 0;
+        if (vb > 0) {
+            w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4];
+            const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+            if ((hz & 0x80808080u) || (w.x >> 26) == 0u) {
+                /* a zero byte, or a first byte <= 3 that may close a zero run of the bytes before */
+                const u32 valid = (1u << vb) - 1u;
+                u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
+                u32 keep = valid;
+                if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
+                const bool need = ((w.x >> 26) == 0u) && (keep & 1u);
+                if (need || (z & (z << 1))) {
+                    u32 rin = 0;
+                    if (need && (q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(sm.win, 16u * (u32)q, zrun_in);
+                    const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
+                                   (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
+                    ins = epb_group_mask(z, m3 & keep, vb, rin);
+                }
+            }
+            /* the holder of the window's last byte hands the zero run to the next window */
+            if (16 * (q + 1) >= chunk_bytes)
+                sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
+        }
+        const u32 cnt = (u32)__popc(ins);
+        sm.gi[tid] = (cnt << 8) | (u32)vb;
+        u32 before = ins_total, pass_ins = 0;
+        before += block_excl_scan(cnt, sm.scan[spar], pass_ins);
+        spar ^= 1u;
+        /* the whole pass stays clear of the slot's end, else everybody goes byte by byte */
+        const bool roomy = chunk_byte0 + 16u * (u32)(q0 + NT) + ins_total + pass_ins + 4u <= cap;
+        if (vb > 0) {
+            const u32 D = chunk_byte0 + 16u * (u32)q + before;      /* output byte of the group's first byte */
+            const bool clean = cnt == 0u && (vb & 3) == 0 && roomy;
+            bool prev_clean = tid > 0 && roomy, next_clean = tid < NT - 1 && vb_next == 16 && roomy;
+            if (pass_ins) {
+                if (tid > 0) prev_clean = prev_clean && sm.gi[tid - 1] == 16u;
+                if (tid < NT - 1) next_clean = next_clean && sm.gi[tid + 1] == 16u;
+            }
+            if (clean) {
+                /* vb / 4 whole source words leave as re-aligned 32-bit words */
+                const u32 s = (4u - (D & 3u)) & 3u;                 /* source bytes before the first aligned word */
+                const u32 sel = realign_selector(s);
+                const int nw = vb >> 2;
+                u32 *dst = fout32 + ((D + s) >> 2);
+                const u32 o0 = __byte_perm(w.x, w.y, sel), o1 = __byte_perm(w.y, w.z, sel),
+                          o2 = __byte_perm(w.z, w.w, sel), o3 = __byte_perm(w.w, wn, sel);
+                const bool whole_last = s == 0u || (vb == 16 && next_clean);   /* else the last word keeps to its own bytes */
+                if ((D & 15u) == 0u && nw == 4) *(uint4 *)dst = make_uint4(o0, o1, o2, o3);   /* no insertion so far in the frame (mod 16) */
+                else {
+                    if (nw > 1 || whole_last) dst[0] = o0;
+                    if (nw > 2 || (nw == 2 && whole_last)) dst[1] = o1;
+                    if (nw > 3 || (nw == 3 && whole_last)) dst[2] = o2;
+                    if (nw == 4 && whole_last) dst[3] = o3;
+                }
+                if (!whole_last) {
+                    const u32 ol = nw == 4 ? o3 : nw == 3 ? o2 : nw == 2 ? o1 : o0;
+                    const u32 base = D + s + 4u * (u32)(nw - 1);
+                    for (u32 k = 0; k < 4u - s; k++) fout[base + k] = (uint8_t)(ol >> (8u * k));
+                }
+                if (s && (!prev_clean || vb < 16))                  /* nobody else covers the bytes before the first aligned word */
+                    for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
+            } else {
+                emit_bytes(fout, cap, D, w, ins, vb);
+            }
+        }
+        ins_total += pass_ins;
+    }
+    return ins_total - ins_in;
+}
+
+/*
+ * The concatenation path of a thread whose macroblocks are all MBK_SHORT / MBK_NONE: bits [O, O + Ls)
+ * of the slice.  Stores the whole words it owns; hands back the partial head word H (word O >> 5, when
+ * O is not word aligned) and the last word T (word (O + Ls - 1) >> 5) unless that is the head word.
+ */
+template <int NWc>
+__device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (&len)[MPT], u32 O, u32 Ls,
+                                             u32 *win, u32 wbase, u32 &H, u32 &T, bool &has_t) {
+    u32 a[NWc];
+#pragma unroll
+    for (int i = 0; i < NWc; i++) a[i] = 0u;
+#pragma unroll
+    for (int k = 0; k < MPT; k++) concat_append<NWc>(a, code[k], len[k], k);
+    const u32 E = O + Ls;
+    const u32 j0 = O >> 5, s = O & 31u, jl = (E - 1u) >> 5;
+    u32 b[NWc + 1];
+    concat_place<NWc>(a, (32u - (E & 31u)) & 31u, b);
+    const u32 lo_idx = j0 + (s ? 1u : 0u);                   /* first word this thread stores itself */
+    H = 0u;
+#pragma unroll
+    for (int i = 0; i < NWc; i++) {
+        const u32 idx = jl - (u32)(NWc - i);
+        if ((int)(idx - lo_idx) >= 0 && idx - wbase < (u32)CH) win[idx - wbase] = b[i];
+        if (idx == j0) H = b[i];
+    }
+    has_t = !(jl == j0 && s);
+    T = b[NWc];
+    if (!has_t) H = b[NWc];
+    if (!s) H = 0u;
+}
+
 __global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuMbHint *__restrict__ hints,
@@ -228,205 +338,193 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const u32 *__restrict__ dyn_tab,
                       const uint8_t *__restrict__ payload,
                       uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
-    __shared__ ComposeSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
+
+    int f = blockIdx.x;
+    if (f >= n_frames) return;
 
     {   /* the window is zero wherever nothing was written: cleared once here, then every flush clears what it used */
         uint4 *w4 = (uint4 *)sm.win;
         for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) { sm.n_copy[0] = 0; sm.n_copy[1] = 0; }
+        if (tid == 0) { sm.n_items[0] = 0; sm.n_items[1] = 0; }
     }
     u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
-    u32 cpar = 0;                      /* which sm.n_copy counter the current tile uses */
-#if COMPOSE_TIMING
-    long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
-#endif
+    u32 ipar = 0;                      /* which sm.n_items counter the current tile uses */
+    u32 hpar = 0;                      /* which sm.hbuf holds the current tile */
 
-    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    FrameGeo geo = load_geo(descs, f, hints);
+    stage_hints(sm.hbuf[0], geo, 0, min(geo.seg_max, geo.n_seg));
+    cp_async_commit();
+
+    while (f < n_frames) {
         /* ---- frame setup: the descriptor is read by every thread (one broadcast line) ------ */
         const uint4 *dq = (const uint4 *)(descs + f);
         const uint4 d2 = __ldg(dq + 2), d3 = __ldg(dq + 3);
-        const u64 hint_off = (u64)d2.x | ((u64)d2.y << 32), out_off = (u64)d2.z | ((u64)d2.w << 32);
+        const u64 out_off = (u64)d2.z | ((u64)d2.w << 32);
         const u32 cap = d3.x, dyn_id = d3.y;
-        const int W = (int)(d3.z & 0xFFFFu), N = W * (int)(d3.z >> 16);
+        const int W = geo.W;
         const u32 hdr_total = 40u + (d3.w & 0xFFu);
         const int num_refs = (int)((d3.w >> 8) & 0xFFu);
         const int skip_spec = ((d3.w >> 16) & H264GPU_SKIP_SPEC) != 0;
         const int pred_spec = ((d3.w >> 16) & H264GPU_PRED_SPEC) != 0;
         const u32 nal_header = d3.w >> 24;
-        const u32 w_magic = 0xFFFFFFFFu / (u32)W + 1u;         /* g / W == umulhi(g, magic): exact for g < 2^20, 1 < W < 2^10 */
-        const uint2 *fh = (const uint2 *)hints + hint_off;
         const u32 *tab = nullptr;
-        const u32 *pay_words = nullptr;
-        u32 n_pay_words = 0;
-        if (dyn_id != H264GPU_NO_DYN) {
-            const uint4 *yq = (const uint4 *)(dyns + dyn_id);
-            const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
-            tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
-            pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
-            n_pay_words = (y1.y + 3u) >> 2;
+        {
+            const u32 *pay_words = nullptr;
+            u32 n_pay_words = 0;
+            if (dyn_id != H264GPU_NO_DYN) {
+                const uint4 *yq = (const uint4 *)(dyns + dyn_id);
+                const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
+                tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
+                pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
+                n_pay_words = (y1.y + 3u) >> 2;
+                /* the payload is first touched by the queue stage: have it on its way to L2 now */
+                for (u32 o = 128u * (u32)tid; o < 4u * n_pay_words; o += 128u * NT) prefetch_l2((const uint8_t *)pay_words + o);
+            }
+            if (tid == 0) {                                    /* read again only after this frame's first barrier */
+                sm.zrun[0] = 0; sm.zrun[1] = 0;
+                sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
+                sm.cap = cap; sm.fout = out + out_off;
+            }
         }
-        if (tid == 0) {                                        /* read again only after this frame's first barrier */
-            sm.zrun[0] = 0; sm.zrun[1] = 0;
-            sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
-            sm.cap = cap; sm.fout = out + out_off;
-        }
+        const int kc = (W - 1) & 7;                            /* position of a row's last MB inside its segment */
 
         /* frame state every thread tracks identically (all of it follows from block-wide totals) */
         u32 bitpos = hdr_total;        /* slice bits composed so far (incl. the 40-bit Annex-B prefix) */
-        int last_coded = -1;           /* frame index of the last non-skipped MB */
+        int last_coded = -1;           /* raster index of the last non-skipped MB */
         u32 ins_total = 0;             /* emulation-prevention bytes inserted so far */
         u32 zpar = 0;                  /* which sm.zrun slot holds the current state */
         u32 wbase = 0;                 /* frame word held by window word 0; words below it have left for global memory */
 
-        for (int t0 = 0; t0 < N; t0 += TILE) {
-            const bool last = (t0 + TILE >= N);
-            const bool tile0 = (t0 == 0);
-            const int g0 = t0 + tid * MPT;
-            const int nmb = min(max(N - g0, 0), MPT);          /* real macroblocks of this thread */
+        const int f_next = f + (int)gridDim.x;
+        FrameGeo geo_next = geo;
+        if (f_next < n_frames) geo_next = load_geo(descs, f_next, hints);
 
-            /* ---- load: own hints, the row above, the left neighbour ---------- */
+        for (int s0 = 0; s0 < geo.n_seg;) {
+            const int n = min(geo.seg_max, geo.n_seg - s0);
+            const bool last = (s0 + n >= geo.n_seg);
+            const bool tile0 = (s0 == 0);
+            const uint4 *hb = sm.hbuf[hpar];
+
+            /* ---- stage: this tile's hints have landed; start the copy of the next tile ---------- */
+            cp_async_wait_all();
+            __syncthreads();
+            if (!last) stage_hints(sm.hbuf[hpar ^ 1u], geo, s0 + n, min(geo.seg_max, geo.n_seg - s0 - n));
+            else if (f_next < n_frames) stage_hints(sm.hbuf[hpar ^ 1u], geo_next, 0, min(geo_next.seg_max, geo_next.n_seg));
+            cp_async_commit();
+
+            /* ---- load: own segment, the one above, the hints beside them ------------------------ */
+            const int s = s0 + tid;
+            const bool active = tid < n;
+            const int row = seg_row(geo, active ? s : s0), col = (active ? s : s0) - row * geo.tpr;
+            const int nmb = active ? min(MPT, W - MPT * col) : 0;
+            const int g0 = row * W + MPT * col;                 /* raster index of the segment's first MB */
+            const bool first = col == 0, lastseg = col == geo.tpr - 1;
+            const int qo = tid + geo.tpr + 1, qa = tid + 1;     /* slots of the own segment and of the one above */
+
             uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
-            uint2 abv[MPT + 2];                                 /* abv[j] = hint g0 - W - 1 + j */
-#pragma unroll
-            for (int k = 0; k <= MPT; k++) own[k] = make_uint2(0u, 0u);
-#pragma unroll
-            for (int j = 0; j < MPT + 2; j++) abv[j] = make_uint2(0u, 0u);
-            if (nmb == MPT) {
-                const uint4 *src = (const uint4 *)(fh + g0);    /* hint_off even, g0 % MPT == 0: 16-byte aligned */
+            uint2 abv[MPT + 2];                                 /* abv[j] = hint above-left of MB j */
+            if (active) {
 #pragma unroll
                 for (int k = 0; k < MPT / 2; k++) {
-                    const uint4 v = __ldg(src + k);
-                    own[1 + 2 * k] = make_uint2(v.x, v.y);
-                    own[2 + 2 * k] = make_uint2(v.z, v.w);
+                    const uint4 v = staged_chunk(hb, qo, k), u = staged_chunk(hb, qa, k);
+                    own[1 + 2 * k] = make_uint2(v.x, v.y); own[2 + 2 * k] = make_uint2(v.z, v.w);
+                    abv[1 + 2 * k] = make_uint2(u.x, u.y); abv[2 + 2 * k] = make_uint2(u.z, u.w);
+                }
+                own[0] = staged_hint(hb, qo - 1, 7);
+                abv[0] = staged_hint(hb, qa - 1, 7);
+                abv[MPT + 1] = staged_hint(hb, qa + 1, 0);
+                if (first) { own[0] = make_uint2(0u, HINT_Y_UNAVAIL); abv[0] = make_uint2(0u, HINT_Y_UNAVAIL); }
+                if (lastseg) {                                  /* C of the row's last MB is D (src/h264_writer.c:391-399) */
+                    if (kc == 7) abv[9] = abv[7];
+                    else {
+#pragma unroll
+                        for (int j = 0; j < MPT - 1; j++)
+                            if (kc == j) abv[j + 2] = abv[j];
+                    }
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < MPT; k++)
-                    if (k < nmb) own[1 + k] = __ldg(fh + g0 + k);
-            }
-            if (nmb > 0) {
-                if (g0 > 0) own[0] = __ldg(fh + g0 - 1);
-                const int a0 = g0 - W - 1;
-                if (a0 >= 0 && a0 + MPT + 2 <= N) {
+                for (int k = 0; k <= MPT; k++) own[k] = make_uint2(0u, HINT_Y_UNAVAIL);
 #pragma unroll
-                    for (int j = 0; j < MPT + 2; j++) abv[j] = __ldg(fh + a0 + j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < MPT + 2; j++)
-                        if (a0 + j >= 0 && a0 + j < N) abv[j] = __ldg(fh + a0 + j);
-                }
+                for (int j = 0; j < MPT + 2; j++) abv[j] = make_uint2(0u, HINT_Y_UNAVAIL);
             }
 
             /* ---- decide + code ------------------------------------------------ */
-            u64 code[MPT];
-            u32 meta[MPT];
-            u32 dynlen = 0;                                     /* payload bits of this thread's spliced MBs */
-            {
-                int y = W == 1 ? g0 : (int)__umulhi((u32)g0, w_magic), x = g0 - y * W;
+            u32 code[MPT], len[MPT];
+            u32 kinds = 0;
 #pragma unroll
-                for (int k = 0; k < MPT; k++) {
-                    code[k] = 0; meta[k] = 0;
-                    const uint2 h = own[1 + k];
-                    const bool present = k < nmb;
-                    const bool inter = ((h.y >> 8) & 0xFFu) == H264GPU_MB_INTER;
-                    const int avA = x > 0, avB = y > 0;
-                    const bool hasC = x + 1 < W;
-                    const int avC = avB && (hasC || x > 0);
-                    const uint2 c = hasC ? abv[k + 2] : abv[k];             /* C, else D (:391-399) */
-                    /* uniform neighbourhood: A, B, C available and equal to this MB's (mv, ref, kind) */
-                    const u32 hkey = h.y & 0xFFFFu;
-                    const bool uni = inter && avA && avC &&
-                                     own[k].x == h.x && abv[k + 1].x == h.x && c.x == h.x &&
-                                     (own[k].y & 0xFFFFu) == hkey && (abv[k + 1].y & 0xFFFFu) == hkey && (c.y & 0xFFFFu) == hkey;
-                    if (__all_sync(FULL, uni || !present)) {
-                        if (present) meta[k] = decide_uniform(h.y, num_refs, skip_spec, code[k]);
-                    } else if (present) {
-                        if (inter) {
-                            meta[k] = decide_inter(h.x, h.y, own[k].x, own[k].y, avA, abv[k + 1].x, abv[k + 1].y, avB,
-                                                   c.x, c.y, avC, num_refs, pred_spec, skip_spec, code[k]);
-                        } else {
-                            const u32 di = h.y >> 16;
-                            const u32 b0 = __ldg(tab + di), b1 = __ldg(tab + di + 1);
-                            dynlen += b1 - b0;
-                            prefetch_l1((const uint8_t *)pay_words + (b0 >> 3));      /* the payload is first touched here: */
-                            prefetch_l1((const uint8_t *)pay_words + (b1 >> 3));      /* have it on its way before the splice */
-                            meta[k] = META_DYN | META_CODED;
-                            code[k] = (u64)di << 48;
-                        }
+            for (int k = 0; k < MPT; k++) {
+                const uint2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
+                const bool present = k < nmb;
+                /* uniform neighbourhood: an inter MB whose A, B, C carry its own (mv, ref) */
+                const u32 diff = (h.x ^ a.x) | (h.x ^ b.x) | (h.x ^ c.x) | (h.y ^ a.y) | (h.y ^ b.y) | (h.y ^ c.y) | (h.y & 0xFFFFFF00u);
+                u32 kd = MBK_NONE;
+                code[k] = 0u; len[k] = 0u;
+                if (__all_sync(FULL, diff == 0u || !present)) {
+                    if (present) kd = decide_mb_uniform(h.y, num_refs, skip_spec, code[k], len[k]);
+                } else if (present) {
+                    if ((h.y & 0xFF00u) == 0u) {
+                        kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, code[k], len[k]);
+                    } else {
+                        const u32 di = h.y >> 16;
+                        len[k] = __ldg(tab + di + 1) - __ldg(tab + di) + (skip_spec ? 0u : 1u);
+                        code[k] = di;
+                        kd = MBK_DYN;
                     }
-                    if (++x == W) { x = 0; y++; }
                 }
+                kinds |= kd << (4 * k);
             }
 
-            STAGE_MARK(0);                                      /* load + decide */
-            if (g0 + TILE < N && (tid & 3) == 0) prefetch_l2(fh + g0 + TILE);   /* next tile's hints: one 128-byte line per 4 threads */
-
-            /* ---- mb_skip_run prefixes ------------------------------------------ */
+            /* ---- mb_skip_run prefixes (SPEC skip; with skip OFF the constant bit is already in) ---- */
             int last_coded_total = last_coded;
+            int prev0 = 0;
             if (skip_spec) {
                 int lc = -1;
 #pragma unroll
                 for (int k = 0; k < MPT; k++)
-                    if (meta[k] & META_CODED) lc = g0 + k;
+                    if ((kinds >> (4 * k)) & 0xFu) lc = g0 + k;
                 int blk_max;
-                int prev = max(block_excl_scan_max(lc, (int *)sm.scan[spar], blk_max), last_coded);
+                prev0 = max(block_excl_scan_max(lc, (int *)sm.scan[spar], blk_max), last_coded);
                 spar ^= 1u;
                 last_coded_total = max(blk_max, last_coded);
-#pragma unroll
-                for (int k = 0; k < MPT; k++)
-                    if (meta[k] & META_CODED) {
-                        const u32 pre = (u32)(g0 + k - prev);              /* run + 1 */
-                        attach_prefix(code[k], meta[k], pre, 63 - 2 * __clz((int)pre));
-                        prev = g0 + k;
-                    }
-            } else {
-#pragma unroll
-                for (int k = 0; k < MPT; k++)
-                    if (meta[k] & META_CODED) attach_prefix(code[k], meta[k], 1u, 1);   /* ue(0), :630 */
-            }
-
-            /* ---- merge: consecutive plain codes -> one <= 64-bit item per run, bit count of the thread ---- */
-            u32 L = dynlen;
-            {
-                u64 acc = 0;
-                u32 accn = 0;
-#pragma unroll
-                for (int k = 0; k < MPT; k++) {
-                    const u64 c = code[k];
-                    const u32 m = meta[k];
-                    L += m & META_LEN_MASK;
-                    code[k] = 0; meta[k] = 0;
-                    if (m & (META_DYN | META_LONG)) {
-                        if (k > 0 && accn) { code[k - 1] = acc; meta[k - 1] = accn; acc = 0; accn = 0; }
-                        code[k] = c; meta[k] = m;
-                    } else if (m & META_CODED) {
-                        u64 sc = 0; u32 sn = 0;
-                        const bool seal = merge_plain(acc, accn, c, m & META_LEN_MASK, sc, sn);
-                        if (k > 0 && seal) { code[k - 1] = sc; meta[k - 1] = sn; }
-                    }
-                }
-                if (accn) { code[MPT - 1] = acc; meta[MPT - 1] = accn; }
+                attach_runs(code, len, kinds, g0, prev0);
             }
 
             /* ---- slice trailer: trailing mb_skip_run + rbsp_stop_one_bit ---------- */
-            const bool owns_trailer = last && nmb > 0 && g0 + nmb == N;
+            const bool owns_trailer = last && tid == n - 1;
             u32 tr_code = 1u, tr_len = 1u;
             if (owns_trailer && skip_spec) {
-                const u32 run_end = (u32)(N - 1 - last_coded_total);
+                const u32 run_end = (u32)(W * geo.H - 1 - last_coded_total);
                 if (run_end > 0u) {
-                    const int pn = 63 - 2 * __clz((int)(run_end + 1u));
                     tr_code = ((run_end + 1u) << 1) | 1u;
-                    tr_len = (u32)pn + 1u;
+                    tr_len = 2u * flo32(run_end + 1u) + 2u;
                 }
             }
-            if (owns_trailer) L += tr_len;
+
+            /* ---- bit count of the thread, queue slots ---------------------------- */
+            u32 Ls = 0;
+#pragma unroll
+            for (int k = 0; k < MPT; k++) Ls += len[k];
+            const bool cplx = kinds_complex(kinds);
+            u32 n_it = 0;
+            if (cplx) {
+#pragma unroll
+                for (int k = 0; k < MPT; k++) n_it += len[k] ? 1u : 0u;
+            }
+            if (owns_trailer) n_it++;
+            u32 ibase = 0;
+            if (n_it) ibase = atomicAdd(&sm.n_items[ipar], n_it);
+            const u32 L = Ls + (owns_trailer ? tr_len : 0u);
 
             /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
             u32 total;
-            int tile_has_dyn;
-            const u32 O = bitpos + block_excl_scan(L, sm.scan[spar], total, dynlen != 0u, tile_has_dyn);
+            const u32 O = bitpos + block_excl_scan(L, sm.scan[spar], total);
             spar ^= 1u;
+            const u32 total_items = sm.n_items[ipar];
+            if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
             const u32 E = O + L;
             const u32 end = bitpos + total;
             const u32 total_bytes = (end + 7u) >> 3;                       /* meaningful when last */
@@ -434,186 +532,136 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const u32 w_stop = last ? ((total_bytes + 3u) >> 2) : w_end;   /* frame words [.., w_stop) are complete after this tile */
             const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end; /* last word this tile writes to */
             const u32 warp_end = __shfl_sync(FULL, E, 31);
-            STAGE_MARK(1);                                      /* prefixes + merge + scan (incl. its barrier) */
-#if COMPOSE_ABLATE == 1                                                     /* timing experiment: stop after decide + scan */
+
+            /* ---- the tile does not fit behind what the window already holds: send that off first ---- */
             {
-                u32 x = O;
-#pragma unroll
-                for (int k = 0; k < MPT; k++) x ^= (u32)code[k] ^ (u32)(code[k] >> 32) ^ meta[k];
-                if (x == 0x12345u) sizes[f] = x;
-                bitpos = end; last_coded = last_coded_total;
-                continue;
+                const u32 wf_al = (bitpos >> 5) & ~3u;             /* 16-byte group of the tile's first word */
+                if (!tile0 && w_last - wbase >= (u32)CH && wf_al > wbase) {
+                    __syncthreads();
+                    const u32 src = wf_al - wbase;
+                    ins_total += emit_window(sm, wbase << 2, (int)(src << 2), ins_total, zpar, spar);
+                    zpar ^= 1u;
+                    __syncthreads();                                       /* window consumed */
+                    if (tid < 4) { const u32 c = sm.win[src + tid]; sm.win[src + tid] = 0u; sm.win[tid] = c; }
+                    uint4 *w4 = (uint4 *)sm.win;
+                    for (u32 i = 1u + (u32)tid; i < src / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+                    wbase = wf_al;
+                    __syncthreads();
+                }
             }
-#endif
 
             for (;;) {
-                /* ---- write: sequential bit writer per thread, clipped to the window ---------- */
-                BitPut bp;
-                bp_init(bp, (tile0 && tid == 0) ? 0u : O);
-                const u32 key = bp.j;
-                if (tile0 && tid == 0) {
+                /* ---- header: start code, NAL header byte, slice header bits ---------- */
+                if (tile0 && tid < 10 && 32u * (u32)tid < hdr_total) {
                     const uint4 h0 = __ldg(dq), h1 = __ldg(dq + 1);
                     const u64 hdr[4] = {(u64)h0.x | ((u64)h0.y << 32), (u64)h0.z | ((u64)h0.w << 32),
                                         (u64)h1.x | ((u64)h1.y << 32), (u64)h1.z | ((u64)h1.w << 32)};
-                    for (u32 p = 0; p < hdr_total; p += 32u) {
-                        const u32 n = min(32u, hdr_total - p);
-                        bp_put(bp, (u64)(header_bits32(hdr, nal_header, p) >> (32u - n)), n, sm.win, wbase, CH);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < MPT; k++) {
-                    const u32 m = meta[k];
-                    if (m) {
-                        if (!(m & (META_DYN | META_LONG))) bp_put(bp, code[k], m, sm.win, wbase, CH);
-                        else if (m & META_DYN) put_spliced(bp, code[k], sm, wbase, &sm.n_copy[cpar]);
-                        else put_long(bp, code[k], m, num_refs, sm.win, wbase);
-                    }
-                }
-                if (owns_trailer) bp_put(bp, (u64)tr_code, tr_len, sm.win, wbase, CH);
-                u32 T = 0, tj = 0;
-                bool has_tail = false;
-                if (bp.fill) {
-                    if (bp.head) bp.H = bp.acc;
-                    else { T = bp.acc; tj = bp.j; has_tail = true; }
+                    u32 v = header_bits32(hdr, nal_header, 32u * (u32)tid);
+                    const u32 left = hdr_total - 32u * (u32)tid;
+                    if (left < 32u) v &= ~(FULL >> left);
+                    if ((u32)tid - wbase < (u32)CH && v) atomicOr(&sm.win[(u32)tid - wbase], v);
                 }
 
-                /* ---- merge the partial words of neighbouring threads (segmented suffix OR) ---- */
+                /* ---- write: concatenation path + merge of the partial words between threads ---------- */
                 {
-                    u32 X = bp.H;
+                    const u32 Lc = cplx ? 0u : Ls;                         /* bits through the concatenation path */
+                    const u32 Ec = O + Lc;
+                    u32 H = 0u, T = 0u;
+                    bool has_t = false;
+                    const u32 lmax = __reduce_max_sync(FULL, Lc);
+                    if (lmax <= 64u) { if (Lc) simple_words<2>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
+                    else if (lmax <= 128u) { if (Lc) simple_words<4>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
+                    else { if (Lc) simple_words<8>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
+                    const u32 key = O >> 5;
+                    u32 tj = (Ec - 1u) >> 5;
+                    if (!Lc) {
+                        /* nothing through this path: the thread still closes the word its range ends in for the heads behind it */
+                        tj = E >> 5;
+                        has_t = L != 0u && (E & 31u) != 0u && (tj > key || (O & 31u) == 0u);
+                    }
+                    const bool plain = Lc != 0u && (has_t || (O & 31u) == 0u) && ((O & 31u) == 0u || tj > key);
+                    if (__all_sync(FULL, plain)) {
+                        /* every string reaches past its head word: a word is shared by two neighbours at most */
+                        u32 v = T | __shfl_down_sync(FULL, H, 1);
+                        if (lane == 31) v = T;
+                        if (tj - wbase < (u32)CH) {
+                            if (lane == 31) atomicOr(&sm.win[tj - wbase], v);   /* the next warp's (or tile's) first head lands here */
+                            else sm.win[tj - wbase] = v;
+                        }
+                        if (lane == 0 && H != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], H);
+                    } else {
+                        /* general case: segmented suffix OR of the heads that share a word */
+                        u32 X = H;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const u32 v = __shfl_down_sync(FULL, X, d);
-                        const u32 kk = __shfl_down_sync(FULL, key, d);
-                        if (lane + d < 32 && kk == key) X |= v;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const u32 v = __shfl_down_sync(FULL, X, d);
+                            const u32 kk = __shfl_down_sync(FULL, key, d);
+                            if (lane + d < 32 && kk == key) X |= v;
+                        }
+                        const u32 Xn = __shfl_down_sync(FULL, X, 1);
+                        const u32 kn = __shfl_down_sync(FULL, key, 1);
+                        if (has_t && tj - wbase < (u32)CH) {
+                            u32 v = T;
+                            if (lane < 31 && kn == tj) v |= Xn;
+                            if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps (or the next tile) add to this word */
+                            else sm.win[tj - wbase] = v;
+                        }
+                        if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], X);
                     }
-                    const u32 Xn = __shfl_down_sync(FULL, X, 1);
-                    const u32 kn = __shfl_down_sync(FULL, key, 1);
-                    if (has_tail && tj - wbase < (u32)CH) {
-                        u32 v = T;
-                        if (lane < 31 && kn == tj) v |= Xn;
-                        if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps (or the next tile) add to this word */
-                        else sm.win[tj - wbase] = v;
-                    }
-                    if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], X);
                 }
 
-#if COMPOSE_ABLATE == 2                                                     /* timing experiment: stop after the bit writer */
-                __syncthreads();
-                if (sm.win[(tid * 7) % CH] == 0x12345u) sizes[f] = 1;
-                {
-                    uint4 *w4 = (uint4 *)sm.win;
-                    for (u32 i = (u32)tid; i < (CH + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                if (tid == 0) { sm.n_copy[0] = 0; sm.n_copy[1] = 0; }
-                __syncthreads();
-                break;
-#endif
-                STAGE_MARK(2);                                  /* bit writer + partial-word merge */
-                const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
-                const bool flush = last || !fits;
-                bool synced = false;
-
-                /* ---- splice: whole words of spliced MBs, one lane per queued run ----------- */
-                if (tile_has_dyn) {
+                /* ---- queue: items of this tile in rounds of LCAP, one lane per item ----------- */
+                for (u32 r0 = 0; r0 < total_items; r0 += (u32)LCAP) {
+                    if (r0) __syncthreads();                               /* the previous round is consumed */
+                    if (n_it && ibase < r0 + (u32)LCAP && ibase + n_it > r0) {
+                        u32 slot = ibase - r0, bit = O;
+                        int prev = prev0;
+                        if (cplx) {
+#pragma unroll
+                            for (int k = 0; k < MPT; k++) {
+                                const u32 kd = (kinds >> (4 * k)) & 0xFu;
+                                if (len[k]) {
+                                    const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
+                                    prev = g0 + k;
+                                    if (slot < (u32)LCAP) {
+                                        uint2 h = make_uint2(0u, 0u);
+                                        if (kd == MBK_LONG) h = staged_hint(hb, qo, k);
+                                        const Item it = make_item(kd, code[k], len[k], bit, pre, h.x, h.y);
+                                        sm.items[slot] = make_uint4(it.x, it.y, it.z, it.w);
+                                    }
+                                    slot++;
+                                    bit += len[k];
+                                }
+                            }
+                        } else bit += Ls;
+                        if (owns_trailer && slot < (u32)LCAP)
+                            sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
+                    }
                     __syncthreads();
-                    synced = true;
-                    splice_queued(sm, min(sm.n_copy[cpar], (u32)LCAP));
-                    cpar ^= 1u;
-                    if (tid == 0) sm.n_copy[cpar] = 0;                     /* nobody reads that one before the next tile's barrier */
+                    const u32 n_round = min((u32)LCAP, total_items - r0);
+                    for (u32 i = (u32)tid; i < n_round; i += NT) {
+                        const uint4 q = sm.items[i];
+                        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
+                        consume_item(it, sm.win, wbase, (u32)CH, num_refs, sm.tab, sm.pay_words, sm.n_pay_words);
+                    }
                 }
-                STAGE_MARK(3);                                  /* splice copy (incl. its barrier) */
-                if (!flush) break;                                         /* keep filling the window with the next tile */
+
+                const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
+                if (!(last || !fits)) break;                               /* keep filling the window with the next tile */
 
                 /* ---- emit: emulation prevention + store of frame words [wbase, e_hi) --------- */
-                if (!synced || tile_has_dyn) __syncthreads();
-                STAGE_MARK(4);                                  /* barrier before emit */
+                __syncthreads();
                 const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
                 const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
-                const u32 zrun_in = sm.zrun[zpar];
-                const u32 cap = sm.cap;
-                uint8_t *fout = sm.fout;
-                u32 *fout32 = (u32 *)fout;
-                for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NT) {
-                    const int q = q0 + tid;
-                    const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
-                    const int vb_next = tid == NT - 1 ? 0 : min(max(chunk_bytes - 16 * (q + 1), 0), 16);
-                    uint4 w = make_uint4(FULL, FULL, FULL, FULL);
-                    u32 wn = 0, ins = 0;
-                    if (vb > 0) {
-                        w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4];
-                        const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                                       ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-                        if ((hz & 0x80808080u) || (w.x >> 26) == 0u) {
-                            /* a zero byte, or a first byte <= 3 that may close a zero run of the bytes before */
-                            const u32 valid = (1u << vb) - 1u;
-                            u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
-                            u32 keep = valid;
-                            if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
-                            const bool need = ((w.x >> 26) == 0u) && (keep & 1u);
-                            if (need || (z & (z << 1))) {
-                                u32 rin = 0;
-                                if (need && (q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(sm.win, 16u * (u32)q, zrun_in);
-                                const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
-                                               (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
-                                ins = epb_group_mask(z, m3 & keep, vb, rin);
-                            }
-                        }
-                        /* the holder of the window's last byte hands the zero run to the next window */
-                        if (16 * (q + 1) >= chunk_bytes)
-                            sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
-                    }
-                    const u32 cnt = (u32)__popc(ins);
-                    sm.gi[tid] = (cnt << 8) | (u32)vb;
-                    u32 before = ins_total, pass_ins = 0;
-                    int any_ins;
-                    before += block_excl_scan(cnt, sm.scan[spar], pass_ins, 0, any_ins);
-                    spar ^= 1u;
-                    /* the whole pass stays clear of the slot's end, else everybody goes byte by byte */
-                    const bool roomy = chunk_byte0 + 16u * (u32)(q0 + NT) + ins_total + pass_ins + 4u <= cap;
-                    if (vb > 0) {
-                        const u32 D = chunk_byte0 + 16u * (u32)q + before;      /* output byte of the group's first byte */
-                        const bool clean = cnt == 0u && (vb & 3) == 0 && roomy;
-                        bool prev_clean = tid > 0 && roomy, next_clean = tid < NT - 1 && vb_next == 16 && roomy;
-                        if (pass_ins) {
-                            if (tid > 0) prev_clean = prev_clean && sm.gi[tid - 1] == 16u;
-                            if (tid < NT - 1) next_clean = next_clean && sm.gi[tid + 1] == 16u;
-                        }
-                        if (clean) {
-                            /* vb / 4 whole source words leave as re-aligned 32-bit words */
-                            const u32 s = (4u - (D & 3u)) & 3u;                 /* source bytes before the first aligned word */
-                            const u32 sel = realign_selector(s);
-                            const int nw = vb >> 2;
-                            u32 *dst = fout32 + ((D + s) >> 2);
-                            const u32 o0 = __byte_perm(w.x, w.y, sel), o1 = __byte_perm(w.y, w.z, sel),
-                                      o2 = __byte_perm(w.z, w.w, sel), o3 = __byte_perm(w.w, wn, sel);
-                            const bool whole_last = s == 0u || (vb == 16 && next_clean);   /* else the last word keeps to its own bytes */
-                            if (nw > 1 || whole_last) dst[0] = o0;
-                            if (nw > 2 || (nw == 2 && whole_last)) dst[1] = o1;
-                            if (nw > 3 || (nw == 3 && whole_last)) dst[2] = o2;
-                            if (nw == 4 && whole_last) dst[3] = o3;
-                            if (!whole_last) {
-                                const u32 ol = nw == 4 ? o3 : nw == 3 ? o2 : nw == 2 ? o1 : o0;
-                                const u32 base = D + s + 4u * (u32)(nw - 1);
-                                for (u32 k = 0; k < 4u - s; k++) fout[base + k] = (uint8_t)(ol >> (8u * k));
-                            }
-                            if (s && (!prev_clean || vb < 16))                  /* nobody else covers the bytes before the first aligned word */
-                                for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
-                        } else {
-                            emit_bytes(fout, cap, D, w, ins, vb);
-                        }
-                    }
-                    ins_total += pass_ins;
-                }
+                ins_total += emit_window(sm, chunk_byte0, chunk_bytes, ins_total, zpar, spar);
                 if (chunk_bytes > 0) zpar ^= 1u;
-                STAGE_MARK(5);                                  /* emit passes */
                 __syncthreads();                                               /* window fully consumed */
                 {   /* clear the words this window used */
                     const u32 used = min((u32)CH, w_last - wbase + 1u);
                     uint4 *w4 = (uint4 *)sm.win;
                     for (u32 i = (u32)tid; i < (used + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
-                STAGE_MARK(6);                                  /* barrier + window clear */
                 if (fits) break;                                               /* (frame done) */
                 wbase += CH;                                                   /* a full window has left; the tile goes on in the next one */
                 __syncthreads();
@@ -622,22 +670,15 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             bitpos = end;
             last_coded = last_coded_total;
             if (last && tid == 0) sizes[f] = total_bytes + ins_total;
+            ipar ^= 1u;
+            hpar ^= 1u;
+            s0 += n;
         }
+        f = f_next;
+        geo = geo_next;
     }
-#if COMPOSE_TIMING
-    if (tid == 0)
-        for (int i = 0; i < 8; i++) atomicAdd(&g_stage_cycles[i], (unsigned long long)stage_acc[i]);
-#endif
+    cp_async_wait_all();
 }
-
-#if COMPOSE_TIMING
-cudaError_t read_stage_cycles(unsigned long long *h8) {
-    cudaError_t e = cudaMemcpyFromSymbol(h8, g_stage_cycles, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof z);
-    return e;
-}
-#endif
 
 /* ------------------------------------------------------------ rasteriser */
 
@@ -673,11 +714,21 @@ raster_regions_kernel(const H264GpuRasterDesc *__restrict__ rdescs, int n_frames
                 else {
                     const u32 local = (u32)((y - y0) * (x1 - x0) + (x - x0));
                     h = __ldg(dinfo + (q.w >> 16) + local);
+                    h = make_uint2(canonical_hint_x(h.x, h.y), canonical_hint_y(h.y));
                 }
                 break;
             }
         }
         dst[g] = h;
+    }
+}
+
+/* dense maps that did not come from the rasteriser: spliced intra MBs -> (mv 0, ref 0xFF) */
+__global__ void __launch_bounds__(256)
+canonicalize_hints_kernel(uint2 *__restrict__ hints, unsigned long long n) {
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+        const uint2 h = hints[i];
+        if (((h.y >> 8) & 0xFFu) == H264GPU_MB_DYN_INTRA) hints[i] = make_uint2(0u, h.y | KEY_INTRA);
     }
 }
 
@@ -762,15 +813,26 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     static int ctas_per_sm = 0;           /* resident CTAs per SM for this build (registers / shared memory) */
+    const int smem = (int)sizeof(ComposeSmem);
     if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(compose_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel, NT, 0) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel, NT, smem) != cudaSuccess || n < 1) n = 1;
         ctas_per_sm = n;
     }
     const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
     int grid = n_frames < resident ? n_frames : resident;
-    compose_frames_kernel<<<grid, NT, 0, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab,
-                                                   d_payload, d_out, d_sizes);
+    compose_frames_kernel<<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab,
+                                                      d_payload, d_out, d_sizes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_canonicalize(H264GpuMbHint *d_hints, size_t n_hints, cudaStream_t stream) {
+    if (n_hints == 0) return cudaSuccess;
+    size_t blocks = (n_hints + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    canonicalize_hints_kernel<<<(int)blocks, 256, 0, stream>>>((uint2 *)d_hints, (unsigned long long)n_hints);
     return cudaGetLastError();
 }
 

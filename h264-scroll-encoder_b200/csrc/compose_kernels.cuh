@@ -9,17 +9,18 @@
 #ifndef COMPOSE_THREADS
 #define COMPOSE_THREADS      256     /* threads per CTA */
 #endif
-#ifndef COMPOSE_MPT
-#define COMPOSE_MPT          8       /* consecutive macroblocks per thread (even) */
-#endif
 #ifndef COMPOSE_MIN_CTAS
 #define COMPOSE_MIN_CTAS     3       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
 #define COMPOSE_WINDOW_WORDS 6144    /* slice words staged in shared memory per pass (multiple of 4) */
 #endif
-#ifndef COMPOSE_COPY_SLOTS
-#define COMPOSE_COPY_SLOTS   512     /* queued splice runs per pass */
+#ifndef COMPOSE_ITEM_SLOTS
+#define COMPOSE_ITEM_SLOTS   256     /* work-queue items per round */
+#endif
+#ifndef COMPOSE_HINT_SLOTS
+#define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
+                                                         up to 264 MBs wide, at least 2 segments per tile at the widest */
 #endif
 #define COMPOSE_MAX_MB_W  H264GPU_MAX_MB_W
 
@@ -29,6 +30,8 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
                            const H264GpuMbHint *d_hints, const H264GpuDynDesc *d_dyn,
                            const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream);
+
+cudaError_t launch_canonicalize(H264GpuMbHint *d_hints, size_t n_hints, cudaStream_t stream);
 
 cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs,
                           const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,

@@ -640,5 +640,295 @@ HSD u32 zeros_before(const u32 *win, u32 b, u32 zrun_in) {
 /* byte-permute selector: output word = stream bytes s..s+3 of the MSB-first pair (a, b) */
 HSD u32 realign_selector(u32 s) { return (u32)((0x5670670170120123ull >> (16u * s)) & 0xFFFFu); }
 
+
+/* ======================================================================
+ * Compose kernel v4: row-aligned segments of 8 macroblocks per thread, hints staged in shared
+ * memory, 32-bit codes per macroblock, branch-free multi-word concatenation, and a work queue
+ * that spreads everything that is not a short inline code (spliced macroblocks, long codes,
+ * separately prefixed codes, the slice trailer) over the lanes of the CTA.
+ * Pure functions again, shared with tests/emu.
+ * ==================================================================== */
+
+/*
+ * Canonical hints.  The kernel compares neighbours through (mv word, low byte of the key word):
+ *   - a spliced intra macroblock (H264GPU_MB_DYN_INTRA) must carry mv 0 and ref 0xFF
+ *     ("available, never matches": src/h264_writer.c:636-640 publishes ref -1, mv 0),
+ *   - positions outside the picture are filled in by the kernel with HINT_Y_UNAVAIL.
+ * h264gpu_raster_regions and h264gpu_compose_host canonicalise; dense maps handed straight to
+ * h264gpu_compose_batch go through h264gpu_canonicalize_hints once.  Inter refs >= 0xF0 are invalid.
+ */
+#define KEY_INTRA      0xFFu
+#define KEY_UNAVAIL    0xFEu
+#define HINT_Y_UNAVAIL 0x0000FFFEu        /* kind 0xFF, ref KEY_UNAVAIL, mv word 0 */
+
+HSD u32 canonical_hint_x(u32 x, u32 y) { return ((y >> 8) & 0xFFu) == H264GPU_MB_DYN_INTRA ? 0u : x; }
+HSD u32 canonical_hint_y(u32 y) { return ((y >> 8) & 0xFFu) == H264GPU_MB_DYN_INTRA ? (y | KEY_INTRA) : y; }
+
+/* per-macroblock kinds held by the owning thread (4 bits each) */
+#define MBK_NONE  0u      /* absent or P_Skip: no bits of its own */
+#define MBK_SHORT 1u      /* whole code (with its mb_skip_run prefix) in <= 32 bits */
+#define MBK_LONG  2u      /* inline code longer than that: code = packed predictor, rebuilt by the consumer */
+#define MBK_DYN   3u      /* spliced: code = dyn index */
+#define MBK_PFX   4u      /* short body whose mb_skip_run prefix does not fit beside it (SPEC skip only) */
+
+/* queue items: x = slice bit | type << 30 */
+#define IT_BITS 0u        /* y = prefix value (0: none), z = code, w = code bits */
+#define IT_DYN  1u        /* y = prefix value, z = dyn index */
+#define IT_LONG 2u        /* y = prefix value | ref << 24, z = mvd_x, w = mvd_y */
+#define IT_BIT_MASK 0x3FFFFFFFu
+
+struct Item { u32 x, y, z, w; };
+
+/* high word of (hi:lo) << n, 0 <= n <= 32 (n == 32 gives lo) */
+HSD u32 fshl_c(u32 hi, u32 lo, u32 n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(lo, hi, n);
+#else
+    return n >= 32u ? lo : (n ? (hi << n) | (lo >> (32u - n)) : hi);
+#endif
+}
+
+/* index of the leading one (v != 0) */
+HSD u32 flo32(u32 v) { return 31u - (u32)clz32(v); }
+
+/* se(v): value written (code number + 1) and its bit count (src/bitwriter.c:50-101) */
+HSD u32 se_val(int v, u32 &n) {
+    const u32 a = (u32)(v < 0 ? -v : v);
+    const u32 cv = (a << 1) | (v <= 0 ? 1u : 0u);          /* v > 0: 2v, else 1 - 2v */
+    n = 2u * flo32(cv) + 1u;
+    return cv;
+}
+
+/* te(ref) of write_p16x16_mb (src/h264_writer.c:439-445): value and bit count */
+HSD u32 ref_val(u32 ref, int num_refs, u32 &rl) {
+    if (num_refs == 2) { rl = 1u; return ~ref & 1u; }
+    if (num_refs < 2) { rl = 0u; return 0u; }
+    const u32 rc = ref + 1u;
+    rl = 2u * flo32(rc) + 1u;
+    return rc;
+}
+
+/*
+ * One inter macroblock against its neighbours A, B, C (C already replaced by D where the
+ * reference does so; unavailable positions carry HINT_Y_UNAVAIL / mv 0).
+ * Skip OFF: the code starts with the constant mb_skip_run bit (src/h264_writer.c:629-631).
+ * Skip SPEC: body only, the prefix is attached once the run is known.
+ */
+HSD u32 decide_mb(u32 hx, u32 hy, u32 ax, u32 ay, u32 bx, u32 by, u32 cx, u32 cy,
+                  int num_refs, int pred_spec, int skip_spec, u32 &code, u32 &len) {
+    const u32 key = hy & 0xFFu;
+    u32 ka = ay & 0xFFu, kb = by & 0xFFu, kc = cy & 0xFFu;
+    const bool b_zero = kb == KEY_UNAVAIL || (kb == 0u && bx == 0u);   /* B as the P_Skip rule sees it */
+    if (pred_spec && ka != KEY_UNAVAIL && kb == KEY_UNAVAIL && kc == KEY_UNAVAIL) { bx = ax; cx = ax; kb = ka; kc = ka; }
+    const int ma = ka == key, mb = kb == key, mc = kc == key;
+    u32 med = vmin2(vmax2(ax, bx), cx);                     /* the reference's median3 (:362-367) */
+    if (pred_spec) med = vmax2(vmin2(ax, bx), med);
+    const u32 single = ma ? ax : (mb ? bx : cx);
+    const u32 pred = (ma + mb + mc == 1) ? single : med;
+    if (skip_spec && key == 0u) {                           /* H.264 8.4.1.1 */
+        const bool zero = ka == KEY_UNAVAIL || (ka == 0u && ax == 0u) || b_zero;
+        if (hx == (zero ? 0u : pred)) { code = 0u; len = 0u; return MBK_NONE; }
+    }
+    const int dx = (int)(int16_t)(hx & 0xFFFFu) - (int)(int16_t)(pred & 0xFFFFu);
+    const int dy = (int)(int16_t)(hx >> 16) - (int)(int16_t)(pred >> 16);
+    u32 nx, ny, rl;
+    const u32 vx = se_val(dx, nx), vy = se_val(dy, ny);
+    const u32 rc = ref_val(key, num_refs, rl);
+    const u32 tl = skip_spec ? 1u : 2u;
+    len = tl + rl + nx + ny + 1u;
+    if (len <= 32u) {
+        u32 v = ((skip_spec ? 1u : 3u) << rl) | rc;
+        v = (v << nx) | vx;
+        v = (v << ny) | vy;
+        code = (v << 1) | 1u;
+        return MBK_SHORT;
+    }
+    code = pred;
+    return MBK_LONG;
+}
+
+/* the same when A, B and C all equal the macroblock's own inter hint: mvd = 0, P_Skip with ref 0 */
+HSD u32 decide_mb_uniform(u32 hy, int num_refs, int skip_spec, u32 &code, u32 &len) {
+    const u32 key = hy & 0xFFu;
+    if (skip_spec && key == 0u) { code = 0u; len = 0u; return MBK_NONE; }
+    u32 rl;
+    const u32 rc = ref_val(key, num_refs, rl);
+    code = (((((skip_spec ? 1u : 3u) << rl) | rc) << 3) | 7u);
+    len = (skip_spec ? 1u : 2u) + rl + 3u;
+    return MBK_SHORT;
+}
+
+/* append the low n (0..32) bits of code to the right-aligned NWc-word integer a[] (a[NWc-1] least
+   significant); step = how many codes went in before (words above step+1 are still zero) */
+template <int NWc>
+HSD void concat_append(u32 (&a)[NWc], u32 code, u32 n, int step) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NWc - 1; i++)
+        if (i >= NWc - 1 - step) a[i] = fshl_c(a[i], a[i + 1], n);
+    a[NWc - 1] = fshl_c(a[NWc - 1], 0u, n) | code;
+}
+
+/* b[0..NWc] = a[] shifted left by r (0..31): b[NWc] is the least significant word */
+template <int NWc>
+HSD void concat_place(const u32 (&a)[NWc], u32 r, u32 (&b)[NWc + 1]) {
+    b[0] = fshl(0u, a[0], (int)r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < NWc; i++) b[i] = fshl(a[i - 1], a[i], (int)r);
+    b[NWc] = a[NWc - 1] << r;
+}
+
+#if defined(__CUDA_ARCH__)
+#define WIN_OR(p, v) atomicOr((p), (v))
+#else
+#define WIN_OR(p, v) (*(p) |= (v))
+#endif
+
+/* OR the low n (1..64) bits of v into the window at slice bit `bit`; words outside [wbase, wbase+wcap) are dropped */
+HSD void win_or64(u32 *win, u32 wbase, u32 wcap, u32 bit, u64 v, u32 n) {
+    const u32 j = (bit >> 5) - wbase, s = bit & 31u;
+    const u64 t = v << (64u - n);                           /* left aligned */
+    const u64 u = t >> s;                                   /* bits for words j, j+1 */
+    const u32 lo2 = s ? (u32)((t << (64u - s)) >> 32) : 0u; /* bits for word j+2 */
+    if (j < wcap && (u32)(u >> 32)) WIN_OR(&win[j], (u32)(u >> 32));
+    if (j + 1u < wcap && (u32)u) WIN_OR(&win[j + 1u], (u32)u);            /* u32 index: wraps like the check */
+    if (j + 2u < wcap && lo2) WIN_OR(&win[j + 2u], lo2);
+}
+
+/* payload word wi as an MSB-first word (payload bytes are a bit stream: big-endian words) */
+HSD u32 pay_word(const u32 *pw, u32 n_words, u32 wi) {
+#if defined(__CUDA_ARCH__)
+    return wi < n_words ? __byte_perm(__ldg(pw + wi), 0u, 0x0123u) : 0u;
+#else
+    return wi < n_words ? bswap32(pw[wi]) : 0u;
+#endif
+}
+HSD u32 pay_ld32(const u32 *pw, u32 n_words, u32 p) {
+    const u32 wi = p >> 5;
+    return fshl(pay_word(pw, n_words, wi), pay_word(pw, n_words, wi + 1u), (int)(p & 31u));
+}
+
+/* copy `len` payload bits from payload bit `src` to slice bit `dst` (copy_bits, src/h264_writer.c:228-240):
+   whole window words are plain stores, the partial words at both ends are OR-ed in */
+HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 n_words, u32 src, u32 len) {
+    const u32 s = dst & 31u;
+    if (s && len) {
+        const u32 hb = len < 32u - s ? len : 32u - s;
+        const u32 v = (pay_ld32(pw, n_words, src) >> (32u - hb)) << (32u - s - hb);
+        const u32 j = (dst >> 5) - wbase;
+        if (j < wcap && v) WIN_OR(&win[j], v);
+        dst += hb; src += hb; len -= hb;
+    }
+    u32 j = (dst >> 5) - wbase;
+    const u32 nw = len >> 5, tb = len & 31u;
+    if (nw) {
+        u32 wi = src >> 5;
+        const u32 sh = src & 31u;
+        u32 a = pay_word(pw, n_words, wi);
+        u32 i = 0;
+        for (; i + 4u <= nw; i += 4u) {                      /* four independent loads in flight */
+            const u32 b0 = pay_word(pw, n_words, wi + 1u), b1 = pay_word(pw, n_words, wi + 2u),
+                      b2 = pay_word(pw, n_words, wi + 3u), b3 = pay_word(pw, n_words, wi + 4u);
+            if (j + i < wcap) win[j + i] = fshl(a, b0, (int)sh);
+            if (j + i + 1u < wcap) win[j + i + 1u] = fshl(b0, b1, (int)sh);
+            if (j + i + 2u < wcap) win[j + i + 2u] = fshl(b1, b2, (int)sh);
+            if (j + i + 3u < wcap) win[j + i + 3u] = fshl(b2, b3, (int)sh);
+            a = b3;
+            wi += 4u;
+        }
+        for (; i < nw; i++) {
+            const u32 b = pay_word(pw, n_words, ++wi);
+            if (j + i < wcap) win[j + i] = fshl(a, b, (int)sh);
+            a = b;
+        }
+    }
+    if (tb) {
+        const u32 v = (pay_ld32(pw, n_words, src + 32u * nw) >> (32u - tb)) << (32u - tb);
+        if (j + nw < wcap && v) WIN_OR(&win[j + nw], v);
+    }
+}
+
+/* one queue item -> window */
+HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_refs,
+                      const u32 *tab, const u32 *pw, u32 n_words) {
+    u32 bit = it.x & IT_BIT_MASK;
+    const u32 type = it.x >> 30;
+    const u32 pre = type == IT_LONG ? (it.y & 0xFFFFFFu) : it.y;
+    if (pre) {
+        const u32 pn = 2u * flo32(pre) + 1u;                 /* ue(run): run + 1 in 2m+1 bits */
+        win_or64(win, wbase, wcap, bit, (u64)pre, pn);
+        bit += pn;
+    }
+    if (type == IT_BITS) {
+        if (it.w) win_or64(win, wbase, wcap, bit, (u64)it.z, it.w);
+    } else if (type == IT_DYN) {
+        const u32 b0 = tab[it.z], len = tab[it.z + 1u] - b0;
+        splice_bits(win, wbase, wcap, bit, pw, n_words, b0, len);
+    } else {
+        MbEntry e;
+        int bl = encode_p16x16_body((int)(it.y >> 24), (int)it.z, (int)it.w, num_refs, e);
+        const u32 ws[3] = {e.w1, e.w2, e.w3};
+        for (int i = 0; i < 3 && bl > 0; i++, bl -= 32) {
+            const u32 n = (u32)(bl < 32 ? bl : 32);
+            win_or64(win, wbase, wcap, bit, (u64)(ws[i] >> (32u - n)), n);
+            bit += n;
+        }
+    }
+}
+
+/*
+ * mb_skip_run prefixes for the coded macroblocks of a thread (SPEC skip): g0 = raster index of the
+ * thread's first macroblock, prev = raster index of the last coded macroblock before it.  A short code
+ * takes its prefix in when both fit 32 bits, else it becomes MBK_PFX (prefix travels separately).
+ * Returns the raster index of the thread's last coded macroblock (or prev).
+ */
+HSD int attach_runs(u32 (&code)[8], u32 (&len)[8], u32 &kinds, int g0, int prev) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; k++) {
+        const u32 kd = (kinds >> (4 * k)) & 0xFu;
+        if (kd != MBK_NONE) {
+            const u32 pre = (u32)(g0 + k - prev);           /* run + 1 */
+            const u32 pn = 2u * flo32(pre) + 1u;
+            if (kd == MBK_SHORT) {
+                if (pn + len[k] <= 32u) code[k] |= pre << len[k];
+                else kinds += (MBK_PFX - MBK_SHORT) << (4 * k);
+            }
+            len[k] += pn;
+            prev = g0 + k;
+        }
+    }
+    return prev;
+}
+
+/* true when a thread's macroblocks cannot all go through the concatenation path */
+HSD bool kinds_complex(u32 kinds) { return (kinds & 0xEEEEEEEEu) != 0u; }
+
+/*
+ * The queue item of macroblock k of a complex thread.  bit = slice bit of the macroblock's first bit,
+ * pre = its mb_skip_run prefix value (run + 1), (hx, hy) = its own hint (for MBK_LONG).
+ */
+HSD Item make_item(u32 kd, u32 code, u32 len, u32 bit, u32 pre, u32 hx, u32 hy) {
+    Item it;
+    if (kd == MBK_SHORT) { it.x = bit | (IT_BITS << 30); it.y = 0u; it.z = code; it.w = len; }
+    else if (kd == MBK_PFX) { it.x = bit | (IT_BITS << 30); it.y = pre; it.z = code; it.w = len - (2u * flo32(pre) + 1u); }
+    else if (kd == MBK_DYN) { it.x = bit | (IT_DYN << 30); it.y = pre; it.z = code; it.w = 0u; }
+    else {
+        it.x = bit | (IT_LONG << 30);
+        it.y = pre | ((hy & 0xFFu) << 24);
+        it.z = (u32)((int)(int16_t)(hx & 0xFFFFu) - (int)(int16_t)(code & 0xFFFFu));
+        it.w = (u32)((int)(int16_t)(hx >> 16) - (int)(int16_t)(code >> 16));
+    }
+    return it;
+}
+
+/* 16-byte chunk c of a staged hint tile lives at chunk c ^ ((c >> 3) & 7): conflict-free 128-bit reads
+   for threads that each own 64 consecutive bytes */
+HSD u32 hint_swizzle(u32 c) { return c ^ ((c >> 3) & 7u); }
+
 } /* namespace h264scroll */
 #endif

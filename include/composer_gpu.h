@@ -47,10 +47,17 @@ extern "C" {
 typedef struct {
     int16_t  mv_x_qpel;     /* quarter-pel, as coded (src/h264_writer.c:619-620) */
     int16_t  mv_y_qpel;
-    uint8_t  ref_idx;       /* index into RefPicList0                           */
+    uint8_t  ref_idx;       /* index into RefPicList0 (< 0xF0)                  */
     uint8_t  kind;          /* H264GPU_MB_*                                     */
     uint16_t dyn_idx;       /* kind != INTER: index into the frame's dyn table  */
 } H264GpuMbHint;
+
+/*
+ * Canonical form (what h264gpu_compose_batch reads): a H264GPU_MB_DYN_INTRA hint carries mv 0 and
+ * ref_idx 0xFF - "available, never matches", the (ref -1, mv 0) the reference publishes for an
+ * intra neighbour (src/h264_writer.c:636-640).  h264gpu_raster_regions and h264gpu_compose_host
+ * produce it; dense maps built elsewhere go through h264gpu_canonicalize_hints once.
+ */
 
 /* ---- frame flags ------------------------------------------------------ */
 #define H264GPU_SKIP_OFF    0x00  /* reference behaviour: mb_skip_run always 0 (src/h264_writer.c:629-631) */
@@ -162,6 +169,9 @@ int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int m
                            const H264GpuRegion *d_regions,
                            const H264GpuMbHint *d_dyn_info,   /* may be NULL without DYN regions */
                            H264GpuMbHint *d_hints, void *stream);
+
+/* Rewrites spliced-intra hints of a dense map into canonical form, in place (asynchronous on `stream`). */
+int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *stream);
 
 /*
  * Exact output packing: gathers the frames' slots into one contiguous Annex-B

@@ -159,7 +159,8 @@ def have_ref():
 
 
 def raster_regions_numpy(regions, mb_w, mb_h, dyn_info=None):
-    """Checker for the device rasteriser: later regions occlude earlier ones; uncovered = (ref 0, mv 0)."""
+    """Checker for the device rasteriser: later regions occlude earlier ones; uncovered = (ref 0, mv 0);
+    spliced intra macroblocks come out in canonical form."""
     from importlib import import_module
     abi = import_module("h264_scroll_encoder_b200.abi")
     hints = np.zeros((mb_h, mb_w), dtype=abi.HINT)
@@ -176,4 +177,8 @@ def raster_regions_numpy(regions, mb_w, mb_h, dyn_info=None):
             for y in range(y0, y1):
                 base = int(r["dyn_base"]) + (y - int(r["y0"])) * rw + (x0 - int(r["x0"]))
                 hints[y, x0:x1] = dyn_info[base:base + (x1 - x0)]
+    intra = hints["kind"] == abi.MB_DYN_INTRA        # canonical form (include/composer_gpu.h): mv 0, ref 0xFF
+    hints["mvx"][intra] = 0
+    hints["mvy"][intra] = 0
+    hints["ref"][intra] = 0xFF
     return hints.reshape(-1)
