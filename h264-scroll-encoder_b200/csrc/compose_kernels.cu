@@ -42,13 +42,22 @@ constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass 
 constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
 constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
 constexpr u32 FULL = 0xFFFFFFFFu;
+constexpr int EG = 4;                    /* emit: 16-byte groups per thread per pass */
+constexpr int EPASS = EG * NT;           /* emit: groups per pass */
+static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
 
 struct __align__(16) ComposeSmem {
     u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
     uint4 hbuf[2][HBS * 4];              /* staged hint tiles (swizzled 16-byte chunks), double buffered */
-    uint4 items[LCAP];                   /* work queue */
-    u32 gi[NT];                          /* emit: (insert count << 8) | valid bytes of each group */
+    union {
+        uint4 items[LCAP];               /* work queue (compose stages) */
+        u32 gi[EPASS];                   /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
+    };
+    u32 gpre[EPASS];                     /* emit: bytes inserted before a listed group */
+    unsigned short elist[EPASS];         /* emit: pass-local indices of the listed groups */
+    u32 n_list;
     u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
+    uint2 scan2[2][NW + 1];
     u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
     u32 n_items[2];                      /* queued items, double buffered per tile */
     /* per-frame constants only the queue and emit stages need: kept out of the register file */
@@ -212,90 +221,157 @@ __device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w
     }
 }
 
+/* exclusive prefix sums of two words of packed 16-bit counters over the CTA (one barrier; alternate the buffers) */
+__device__ __forceinline__ void block_excl_scan_x2(u32 &lo, u32 &hi, uint2 *s_scan, u32 &tot_lo, u32 &tot_hi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 il = lo, ih = hi;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 a = __shfl_up_sync(FULL, il, d), b = __shfl_up_sync(FULL, ih, d);
+        if (lane >= d) { il += a; ih += b; }
+    }
+    if (lane == 31) s_scan[warp] = make_uint2(il, ih);
+    __syncthreads();
+    const uint2 ws = lane < NW ? s_scan[lane] : make_uint2(0u, 0u);
+    u32 wl = ws.x, wh = ws.y;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+        const u32 a = __shfl_up_sync(FULL, wl, d), b = __shfl_up_sync(FULL, wh, d);
+        if (lane >= d) { wl += a; wh += b; }
+    }
+    const u32 el = __shfl_sync(FULL, wl - ws.x, warp), eh = __shfl_sync(FULL, wh - ws.y, warp);
+    tot_lo = __shfl_sync(FULL, wl, NW - 1);
+    tot_hi = __shfl_sync(FULL, wh, NW - 1);
+    lo = el + il - lo;
+    hi = eh + ih - hi;
+}
+
+/* exact insert mask of group q of the window (src/nal.c:24-50 in closed form) */
+__device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, int vb, u32 chunk_byte0, u32 zrun_in) {
+    const u32 valid = (1u << vb) - 1u;
+    u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
+    u32 keep = valid;
+    if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
+    const bool need = ((w.x >> 26) == 0u) && (keep & 1u);                /* a first byte <= 3 may close a zero run of the bytes before */
+    if (!(need || (z & (z << 1)))) return 0u;
+    u32 rin = 0;
+    if (need && (q == 0 || (win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(win, 16u * (u32)q, zrun_in);
+    const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
+                   (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
+    return epb_group_mask(z, m3 & keep, vb, rin);
+}
+
+constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without insertions: ins << 16 | valid bytes << 8 | count */
+
 /*
  * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from
  * chunk_byte0 on).  Returns the bytes inserted; leaves the closing zero run in sm.zrun[zpar ^ 1].
- * Called by all threads after a barrier; ends without one.
+ * A pass covers EG 16-byte groups per thread:
+ *   classify  a group that holds a zero byte (or starts with a byte <= 3 behind one), the frame's last
+ *             partial group, everything next to the slot's end -> list; all other groups are clean
+ *   masks     one lane per listed group: exact insert mask + count
+ *   offsets   prefix sum of the counts (packed 16-bit fields, one scan for the EG rounds)
+ *   store     clean groups leave as aligned or re-aligned 32/128-bit words; the listed groups that
+ *             do insert (or are partial) go byte by byte, again one lane per group
+ * Called by all threads after a barrier; ends with one.
  */
 __device__ __forceinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar, u32 &spar) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const u32 zrun_in = sm.zrun[zpar];
     const u32 cap = sm.cap;
     uint8_t *fout = sm.fout;
     u32 *fout32 = (u32 *)fout;
     const u32 ins_in = ins_total;
-    for (int q0 = 0; q0 * 16 < chunk_bytes; q0 += NT) {
-        const int q = q0 + tid;
-        const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
-        const int vb_next = tid == NT - 1 ? 0 : min(max(chunk_bytes - 16 * (q + 1), 0), 16);
-        uint4 w = make_uint4(FULL, FULL, FULL, FULL);
-        u32 wn = 0, ins = 0;
-        if (vb > 0) {
-            w = ((const uint4 *)sm.win)[q]; wn = sm.win[4 * q + 4];
-            const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-            if ((hz & 0x80808080u) || (w.x >> 26) == 0u) {
-                /* a zero byte, or a first byte <= 3 that may close a zero run of the bytes before */
-                const u32 valid = (1u << vb) - 1u;
-                u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
-                u32 keep = valid;
-                if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
-                const bool need = ((w.x >> 26) == 0u) && (keep & 1u);
-                if (need || (z & (z << 1))) {
-                    u32 rin = 0;
-                    if (need && (q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(sm.win, 16u * (u32)q, zrun_in);
-                    const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
-                                   (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
-                    ins = epb_group_mask(z, m3 & keep, vb, rin);
-                }
+    const int n_groups = (chunk_bytes + 15) >> 4;
+    for (int q0 = 0; q0 < n_groups; q0 += EPASS) {
+        /* even with an insertion after every second byte the pass stays clear of the slot's end */
+        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) + ins_total + 4u <= cap;
+        /* ---- classify ---- */
+#pragma unroll
+        for (int r = 0; r < EG; r++) {
+            const int gl = tid + NT * r, q = q0 + gl;
+            const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+            bool slow = false;
+            if (vb > 0) {
+                const uint4 w = ((const uint4 *)sm.win)[q];
+                const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                               ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+                slow = (hz & 0x80808080u) != 0u || vb < 16 || !roomy;
+                if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
+                /* the holder of the window's last byte hands the zero run to the next window */
+                if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
             }
-            /* the holder of the window's last byte hands the zero run to the next window */
-            if (16 * (q + 1) >= chunk_bytes)
-                sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
+            sm.gi[gl] = (u32)vb << 8;
+            const u32 m = __ballot_sync(FULL, slow);
+            if (m) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&sm.n_list, (u32)__popc(m));
+                base = __shfl_sync(FULL, base, 0);
+                if (slow) sm.elist[base + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)gl;
+            }
         }
-        const u32 cnt = (u32)__popc(ins);
-        sm.gi[tid] = (cnt << 8) | (u32)vb;
-        u32 before = ins_total, pass_ins = 0;
-        before += block_excl_scan(cnt, sm.scan[spar], pass_ins);
+        __syncthreads();
+        const u32 nl = sm.n_list;
+        /* ---- masks ---- */
+        for (u32 i = (u32)tid; i < nl; i += NT) {
+            const int gl = sm.elist[i], q = q0 + gl;
+            const int vb = min(chunk_bytes - 16 * q, 16);
+            const u32 ins = group_insert_mask(sm.win, q, ((const uint4 *)sm.win)[q], vb, chunk_byte0, zrun_in);
+            sm.gi[gl] = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
+        }
+        __syncthreads();
+        if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
+        /* ---- offsets ---- */
+        u32 g[EG];
+#pragma unroll
+        for (int r = 0; r < EG; r++) g[r] = sm.gi[tid + NT * r];
+        u32 lo = (g[0] & 0xFFu) | ((g[1] & 0xFFu) << 16), hi = (g[2] & 0xFFu) | ((g[3] & 0xFFu) << 16);
+        u32 tlo, thi;
+        block_excl_scan_x2(lo, hi, sm.scan2[spar], tlo, thi);
         spar ^= 1u;
-        /* the whole pass stays clear of the slot's end, else everybody goes byte by byte */
-        const bool roomy = chunk_byte0 + 16u * (u32)(q0 + NT) + ins_total + pass_ins + 4u <= cap;
-        if (vb > 0) {
-            const u32 D = chunk_byte0 + 16u * (u32)q + before;      /* output byte of the group's first byte */
-            const bool clean = cnt == 0u && (vb & 3) == 0 && roomy;
-            bool prev_clean = tid > 0 && roomy, next_clean = tid < NT - 1 && vb_next == 16 && roomy;
-            if (pass_ins) {
-                if (tid > 0) prev_clean = prev_clean && sm.gi[tid - 1] == 16u;
-                if (tid < NT - 1) next_clean = next_clean && sm.gi[tid + 1] == 16u;
-            }
-            if (clean) {
-                /* vb / 4 whole source words leave as re-aligned 32-bit words */
-                const u32 s = (4u - (D & 3u)) & 3u;                 /* source bytes before the first aligned word */
-                const u32 sel = realign_selector(s);
-                const int nw = vb >> 2;
-                u32 *dst = fout32 + ((D + s) >> 2);
-                const u32 o0 = __byte_perm(w.x, w.y, sel), o1 = __byte_perm(w.y, w.z, sel),
-                          o2 = __byte_perm(w.z, w.w, sel), o3 = __byte_perm(w.w, wn, sel);
-                const bool whole_last = s == 0u || (vb == 16 && next_clean);   /* else the last word keeps to its own bytes */
-                if ((D & 15u) == 0u && nw == 4) *(uint4 *)dst = make_uint4(o0, o1, o2, o3);   /* no insertion so far in the frame (mod 16) */
-                else {
-                    if (nw > 1 || whole_last) dst[0] = o0;
-                    if (nw > 2 || (nw == 2 && whole_last)) dst[1] = o1;
-                    if (nw > 3 || (nw == 3 && whole_last)) dst[2] = o2;
-                    if (nw == 4 && whole_last) dst[3] = o3;
-                }
-                if (!whole_last) {
-                    const u32 ol = nw == 4 ? o3 : nw == 3 ? o2 : nw == 2 ? o1 : o0;
-                    const u32 base = D + s + 4u * (u32)(nw - 1);
-                    for (u32 k = 0; k < 4u - s; k++) fout[base + k] = (uint8_t)(ol >> (8u * k));
-                }
-                if (s && (!prev_clean || vb < 16))                  /* nobody else covers the bytes before the first aligned word */
-                    for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
+        const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
+        const u32 before[EG] = {ins_total + (lo & 0xFFFFu), ins_total + t0 + (lo >> 16),
+                                ins_total + t0 + t1 + (hi & 0xFFFFu), ins_total + t0 + t1 + t2 + (hi >> 16)};
+        /* ---- store: clean groups ---- */
+#pragma unroll
+        for (int r = 0; r < EG; r++) {
+            const int gl = tid + NT * r, q = q0 + gl;
+            if ((g[r] >> 8) == 0u) continue;                 /* past the chunk */
+            if (!(roomy && g[r] == GI_CLEAN)) { sm.gpre[gl] = before[r]; continue; }
+            const u32 D = chunk_byte0 + 16u * (u32)q + before[r];      /* output byte of the group's first byte */
+            const uint4 w = ((const uint4 *)sm.win)[q];
+            const u32 s = (4u - (D & 3u)) & 3u;              /* source bytes before the first aligned word */
+            u32 *dst = fout32 + ((D + s) >> 2);
+            if (s == 0u) {
+                const uint4 o = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
+                                           __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
+                if ((D & 15u) == 0u) *(uint4 *)dst = o;
+                else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
             } else {
-                emit_bytes(fout, cap, D, w, ins, vb);
+                /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
+                const bool prev_clean = gl > 0 && sm.gi[gl - 1] == GI_CLEAN;
+                const bool next_clean = gl < EPASS - 1 && sm.gi[gl + 1] == GI_CLEAN;
+                const u32 wn = sm.win[4 * q + 4];
+                const u32 sel = realign_selector(s);
+                dst[0] = __byte_perm(w.x, w.y, sel);
+                dst[1] = __byte_perm(w.y, w.z, sel);
+                dst[2] = __byte_perm(w.z, w.w, sel);
+                const u32 o3 = __byte_perm(w.w, wn, sel);
+                if (next_clean) dst[3] = o3;
+                else for (u32 k = 0; k < 4u - s; k++) fout[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
+                if (!prev_clean) for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
             }
         }
-        ins_total += pass_ins;
+        __syncthreads();
+        /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
+        for (u32 i = (u32)tid; i < nl; i += NT) {
+            const int gl = sm.elist[i], q = q0 + gl;
+            const u32 gg = sm.gi[gl];
+            if (roomy && gg == GI_CLEAN) continue;           /* turned out clean: stored above */
+            emit_bytes(fout, cap, chunk_byte0 + 16u * (u32)q + sm.gpre[gl], ((const uint4 *)sm.win)[q], gg >> 16, (int)((gg >> 8) & 0xFFu));
+        }
+        ins_total += t0 + t1 + t2 + t3;
+        __syncthreads();                                     /* list, counts and offsets are reused by the next pass */
     }
     return ins_total - ins_in;
 }
@@ -331,6 +407,52 @@ __device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (
     if (!s) H = 0u;
 }
 
+/*
+ * The 8 macroblocks of a segment -> codes, lengths, kinds (4 bits each).  GEN = 0 is the reference mode
+ * (skip OFF, reference predictor) with everything mode dependent folded away; GEN = 1 takes the flags.
+ * A macroblock in uniform motion - every available neighbour carries its own hint - takes the constant
+ * zero-mvd code; the vote keeps the warp on that path as long as no lane needs the predictor
+ * (spliced macroblocks do not: their length comes from the offset table).
+ */
+template <int GEN, int DUMMY>
+__device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const uint2 (&abv)[MPT + 2], int nmb, bool first, bool row0,
+                                              int num_refs, const u32 *__restrict__ tab, u32 (&code)[MPT], u32 (&len)[MPT],
+                                              int skip_spec_in = 0, int pred_spec_in = 0) {
+    const int skip_spec = GEN ? skip_spec_in : 0, pred_spec = GEN ? pred_spec_in : 0;
+    u32 kinds = 0;
+#pragma unroll
+    for (int k = 0; k < MPT; k++) {
+        const uint2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
+        const bool present = k < nmb;
+        const bool dyn = (h.y & 0xFF00u) != 0u;
+        u32 dA = (h.x ^ a.x) | (h.y ^ a.y);
+        u32 dBC = (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y);
+        bool none = false;                                  /* no neighbour at all: the predictor is 0, not the MB's own mv */
+        if (!skip_spec) {
+            /* neighbours outside the picture do not disturb uniform motion (they do change the P_Skip inference) */
+            if (k == 0 && first) dA = 0u;
+            if (row0) dBC = 0u;
+            none = k == 0 && first && row0;
+        }
+        const bool uni = (dA | dBC) == 0u && !none;
+        u32 kd = MBK_NONE;
+        code[k] = 0u; len[k] = 0u;
+        if (__all_sync(FULL, uni || dyn || !present)) {
+            if (present && !dyn) kd = decide_mb_uniform(h.y, num_refs, skip_spec, code[k], len[k]);
+        } else if (present && !dyn) {
+            kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, code[k], len[k]);
+        }
+        if (present && dyn) {
+            const u32 di = h.y >> 16;
+            len[k] = __ldg(tab + di + 1) - __ldg(tab + di) + (skip_spec ? 0u : 1u);
+            code[k] = di;
+            kd = MBK_DYN;
+        }
+        kinds |= kd << (4 * k);
+    }
+    return kinds;
+}
+
 __global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuMbHint *__restrict__ hints,
@@ -348,7 +470,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
     {   /* the window is zero wherever nothing was written: cleared once here, then every flush clears what it used */
         uint4 *w4 = (uint4 *)sm.win;
         for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) { sm.n_items[0] = 0; sm.n_items[1] = 0; }
+        if (tid == 0) { sm.n_items[0] = 0; sm.n_items[1] = 0; sm.n_list = 0; }
     }
     u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
     u32 ipar = 0;                      /* which sm.n_items counter the current tile uses */
@@ -454,29 +576,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
             /* ---- decide + code ------------------------------------------------ */
             u32 code[MPT], len[MPT];
-            u32 kinds = 0;
-#pragma unroll
-            for (int k = 0; k < MPT; k++) {
-                const uint2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
-                const bool present = k < nmb;
-                /* uniform neighbourhood: an inter MB whose A, B, C carry its own (mv, ref) */
-                const u32 diff = (h.x ^ a.x) | (h.x ^ b.x) | (h.x ^ c.x) | (h.y ^ a.y) | (h.y ^ b.y) | (h.y ^ c.y) | (h.y & 0xFFFFFF00u);
-                u32 kd = MBK_NONE;
-                code[k] = 0u; len[k] = 0u;
-                if (__all_sync(FULL, diff == 0u || !present)) {
-                    if (present) kd = decide_mb_uniform(h.y, num_refs, skip_spec, code[k], len[k]);
-                } else if (present) {
-                    if ((h.y & 0xFF00u) == 0u) {
-                        kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, code[k], len[k]);
-                    } else {
-                        const u32 di = h.y >> 16;
-                        len[k] = __ldg(tab + di + 1) - __ldg(tab + di) + (skip_spec ? 0u : 1u);
-                        code[k] = di;
-                        kd = MBK_DYN;
-                    }
-                }
-                kinds |= kd << (4 * k);
-            }
+            u32 kinds;
+            if (!skip_spec && !pred_spec) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
+            else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
 
             /* ---- mb_skip_run prefixes (SPEC skip; with skip OFF the constant bit is already in) ---- */
             int last_coded_total = last_coded;

@@ -806,6 +806,14 @@ HSD u32 pay_word(const u32 *pw, u32 n_words, u32 wi) {
     return wi < n_words ? bswap32(pw[wi]) : 0u;
 #endif
 }
+/* the same without the bounds check */
+HSD u32 pay_raw(const u32 *p) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(__ldg(p), 0u, 0x0123u);
+#else
+    return bswap32(*p);
+#endif
+}
 HSD u32 pay_ld32(const u32 *pw, u32 n_words, u32 p) {
     const u32 wi = p >> 5;
     return fshl(pay_word(pw, n_words, wi), pay_word(pw, n_words, wi + 1u), (int)(p & 31u));
@@ -827,22 +835,32 @@ HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 
     if (nw) {
         u32 wi = src >> 5;
         const u32 sh = src & 31u;
-        u32 a = pay_word(pw, n_words, wi);
-        u32 i = 0;
-        for (; i + 4u <= nw; i += 4u) {                      /* four independent loads in flight */
-            const u32 b0 = pay_word(pw, n_words, wi + 1u), b1 = pay_word(pw, n_words, wi + 2u),
-                      b2 = pay_word(pw, n_words, wi + 3u), b3 = pay_word(pw, n_words, wi + 4u);
-            if (j + i < wcap) win[j + i] = fshl(a, b0, (int)sh);
-            if (j + i + 1u < wcap) win[j + i + 1u] = fshl(b0, b1, (int)sh);
-            if (j + i + 2u < wcap) win[j + i + 2u] = fshl(b1, b2, (int)sh);
-            if (j + i + 3u < wcap) win[j + i + 3u] = fshl(b2, b3, (int)sh);
-            a = b3;
-            wi += 4u;
-        }
-        for (; i < nw; i++) {
-            const u32 b = pay_word(pw, n_words, ++wi);
-            if (j + i < wcap) win[j + i] = fshl(a, b, (int)sh);
-            a = b;
+        if (j < wcap && j + nw <= wcap && wi + nw < n_words) {
+            /* the whole run lies inside the window and the payload: no per-word checks */
+            const u32 *p = pw + wi;
+            u32 *d = win + j;
+            u32 a = pay_raw(p);
+            u32 i = 0;
+            for (; i + 4u <= nw; i += 4u) {                  /* four independent loads in flight */
+                const u32 b0 = pay_raw(p + i + 1u), b1 = pay_raw(p + i + 2u), b2 = pay_raw(p + i + 3u), b3 = pay_raw(p + i + 4u);
+                d[i] = fshl(a, b0, (int)sh);
+                d[i + 1u] = fshl(b0, b1, (int)sh);
+                d[i + 2u] = fshl(b1, b2, (int)sh);
+                d[i + 3u] = fshl(b2, b3, (int)sh);
+                a = b3;
+            }
+            for (; i < nw; i++) {
+                const u32 b = pay_raw(p + i + 1u);
+                d[i] = fshl(a, b, (int)sh);
+                a = b;
+            }
+        } else {
+            u32 a = pay_word(pw, n_words, wi);
+            for (u32 i = 0; i < nw; i++) {
+                const u32 b = pay_word(pw, n_words, ++wi);
+                if (j + i < wcap) win[j + i] = fshl(a, b, (int)sh);
+                a = b;
+            }
         }
     }
     if (tb) {

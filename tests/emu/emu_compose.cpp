@@ -175,9 +175,18 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 T.own[k] = own[1 + k];
                 if (k >= nmb) continue;
                 const H2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
-                const u32 diff = (h.x ^ a.x) | (h.x ^ b.x) | (h.x ^ c.x) | (h.y ^ a.y) | (h.y ^ b.y) | (h.y ^ c.y) | (h.y & 0xFFFFFF00u);
+                const bool dyn = (h.y & 0xFF00u) != 0u;
+                u32 dA = (h.x ^ a.x) | (h.y ^ a.y);
+                u32 dBC = (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y);
+                bool none = false;
+                if (!skip_spec) {                       /* as decide_segment in the kernel */
+                    if (k == 0 && col == 0) dA = 0u;
+                    if (row == 0) dBC = 0u;
+                    none = k == 0 && col == 0 && row == 0;
+                }
+                const bool uni = (dA | dBC) == 0u && !none && !dyn;
                 u32 kd;
-                if (diff == 0 && ((s + k) & 1)) kd = decide_mb_uniform(h.y, num_refs, skip_spec, T.code[k], T.len[k]);
+                if (uni && ((s + k) % 3)) kd = decide_mb_uniform(h.y, num_refs, skip_spec, T.code[k], T.len[k]);
                 else if ((h.y & 0xFF00u) == 0) kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, T.code[k], T.len[k]);
                 else {
                     const u32 di = h.y >> 16;
