@@ -46,9 +46,19 @@ constexpr int EG = 4;                    /* emit: 16-byte groups per thread per 
 constexpr int EPASS = EG * NT;           /* emit: groups per pass */
 static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
 
+#ifndef COMPOSE_TIMING
+#define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
+#endif
+#if COMPOSE_TIMING
+__device__ unsigned long long g_stage_cycles[8];
+#define STAGE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); stage_acc[i] += t_ - stage_t; stage_t = t_; } } while (0)
+#else
+#define STAGE_MARK(i) do { } while (0)
+#endif
+
 struct __align__(16) ComposeSmem {
     u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
-    uint4 hbuf[2][HBS * 4];              /* staged hint tiles (swizzled 16-byte chunks), double buffered */
+    uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks) */
     union {
         uint4 items[LCAP];               /* work queue (compose stages) */
         u32 gi[EPASS];                   /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
@@ -57,7 +67,7 @@ struct __align__(16) ComposeSmem {
     unsigned short elist[EPASS];         /* emit: pass-local indices of the listed groups */
     u32 n_list;
     u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
-    uint2 scan2[2][NW + 1];
+    uint2 scan2[NW + 1];
     u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
     u32 n_items[2];                      /* queued items, double buffered per tile */
     /* per-frame constants only the queue and emit stages need: kept out of the register file */
@@ -275,7 +285,7 @@ constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without
  *             do insert (or are partial) go byte by byte, again one lane per group
  * Called by all threads after a barrier; ends with one.
  */
-__device__ __forceinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar, u32 &spar) {
+__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar) {
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 zrun_in = sm.zrun[zpar];
     const u32 cap = sm.cap;
@@ -327,8 +337,7 @@ __device__ __forceinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int
         for (int r = 0; r < EG; r++) g[r] = sm.gi[tid + NT * r];
         u32 lo = (g[0] & 0xFFu) | ((g[1] & 0xFFu) << 16), hi = (g[2] & 0xFFu) | ((g[3] & 0xFFu) << 16);
         u32 tlo, thi;
-        block_excl_scan_x2(lo, hi, sm.scan2[spar], tlo, thi);
-        spar ^= 1u;
+        block_excl_scan_x2(lo, hi, sm.scan2, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
         const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
         const u32 before[EG] = {ins_total + (lo & 0xFFFFu), ins_total + t0 + (lo >> 16),
                                 ins_total + t0 + t1 + (hi & 0xFFFFu), ins_total + t0 + t1 + t2 + (hi >> 16)};
@@ -407,6 +416,17 @@ __device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (
     if (!s) H = 0u;
 }
 
+/* the queue's consumer side: one lane per item.  Out of line: its loops get their own register allocation */
+__device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wbase, int num_refs) {
+    const u32 *pw = sm.pay_words;
+    const u32 n_words = sm.n_pay_words;
+    for (u32 i = threadIdx.x; i < n_round; i += NT) {
+        const uint4 q = sm.items[i];
+        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
+        consume_item(it, sm.win, wbase, (u32)CH, num_refs, pw, n_words);
+    }
+}
+
 /*
  * The 8 macroblocks of a segment -> codes, lengths, kinds (4 bits each).  GEN = 0 is the reference mode
  * (skip OFF, reference predictor) with everything mode dependent folded away; GEN = 1 takes the flags.
@@ -425,16 +445,17 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
         const uint2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
         const bool present = k < nmb;
         const bool dyn = (h.y & 0xFF00u) != 0u;
-        u32 dA = (h.x ^ a.x) | (h.y ^ a.y);
-        u32 dBC = (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y);
-        bool none = false;                                  /* no neighbour at all: the predictor is 0, not the MB's own mv */
-        if (!skip_spec) {
-            /* neighbours outside the picture do not disturb uniform motion (they do change the P_Skip inference) */
-            if (k == 0 && first) dA = 0u;
-            if (row0) dBC = 0u;
-            none = k == 0 && first && row0;
+        bool uni;
+        if (skip_spec) {
+            /* P_Skip looks at A and B themselves: all three neighbours must carry the MB's own hint */
+            uni = ((h.x ^ a.x) | (h.y ^ a.y) | (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
+        } else if (row0) {
+            /* top row: A alone decides (src/h264_writer.c:407-417); no neighbour at all predicts 0 */
+            uni = ((h.x ^ a.x) | (h.y ^ a.y)) == 0u;
+        } else {
+            /* B == C == the MB's own hint: two refs match, and both medians of (a, h, h) are h whatever A is */
+            uni = ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
         }
-        const bool uni = (dA | dBC) == 0u && !none;
         u32 kd = MBK_NONE;
         code[k] = 0u; len[k] = 0u;
         if (__all_sync(FULL, uni || dyn || !present)) {
@@ -444,8 +465,9 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
         }
         if (present && dyn) {
             const u32 di = h.y >> 16;
-            len[k] = __ldg(tab + di + 1) - __ldg(tab + di) + (skip_spec ? 0u : 1u);
-            code[k] = di;
+            const u32 b0 = __ldg(tab + di);
+            len[k] = __ldg(tab + di + 1) - b0 + (skip_spec ? 0u : 1u);
+            code[k] = b0;
             kd = MBK_DYN;
         }
         kinds |= kd << (4 * k);
@@ -474,10 +496,12 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
     }
     u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
     u32 ipar = 0;                      /* which sm.n_items counter the current tile uses */
-    u32 hpar = 0;                      /* which sm.hbuf holds the current tile */
 
+#if COMPOSE_TIMING
+    long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
+#endif
     FrameGeo geo = load_geo(descs, f, hints);
-    stage_hints(sm.hbuf[0], geo, 0, min(geo.seg_max, geo.n_seg));
+    stage_hints(sm.hbuf, geo, 0, min(geo.seg_max, geo.n_seg));
     cp_async_commit();
 
     while (f < n_frames) {
@@ -528,14 +552,13 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const int n = min(geo.seg_max, geo.n_seg - s0);
             const bool last = (s0 + n >= geo.n_seg);
             const bool tile0 = (s0 == 0);
-            const uint4 *hb = sm.hbuf[hpar];
+            const uint4 *hb = sm.hbuf;
 
-            /* ---- stage: this tile's hints have landed; start the copy of the next tile ---------- */
+            /* ---- stage: this tile's hints have landed ---------- */
+            STAGE_MARK(7);                                      /* frame setup / loop glue */
             cp_async_wait_all();
             __syncthreads();
-            if (!last) stage_hints(sm.hbuf[hpar ^ 1u], geo, s0 + n, min(geo.seg_max, geo.n_seg - s0 - n));
-            else if (f_next < n_frames) stage_hints(sm.hbuf[hpar ^ 1u], geo_next, 0, min(geo_next.seg_max, geo_next.n_seg));
-            cp_async_commit();
+            STAGE_MARK(0);                                      /* wait for the hint tile (and for the slowest warp of the tile before) */
 
             /* ---- load: own segment, the one above, the hints beside them ------------------------ */
             const int s = s0 + tid;
@@ -580,6 +603,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             if (!skip_spec && !pred_spec) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
             else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
 
+            STAGE_MARK(1);                                      /* load + decide */
             /* ---- mb_skip_run prefixes (SPEC skip; with skip OFF the constant bit is already in) ---- */
             int last_coded_total = last_coded;
             int prev0 = 0;
@@ -626,6 +650,11 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const u32 O = bitpos + block_excl_scan(L, sm.scan[spar], total);
             spar ^= 1u;
             const u32 total_items = sm.n_items[ipar];
+            STAGE_MARK(2);                                      /* prefixes, bit counts, scan (incl. its barrier) */
+            /* ---- stage: everybody is past its loads from the hint tile: start the copy of the next one ---- */
+            if (!last) stage_hints(sm.hbuf, geo, s0 + n, min(geo.seg_max, geo.n_seg - s0 - n));
+            else if (f_next < n_frames) stage_hints(sm.hbuf, geo_next, 0, min(geo_next.seg_max, geo_next.n_seg));
+            cp_async_commit();
             if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
             const u32 E = O + L;
             const u32 end = bitpos + total;
@@ -641,7 +670,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 if (!tile0 && w_last - wbase >= (u32)CH && wf_al > wbase) {
                     __syncthreads();
                     const u32 src = wf_al - wbase;
-                    ins_total += emit_window(sm, wbase << 2, (int)(src << 2), ins_total, zpar, spar);
+                    ins_total += emit_window(sm, wbase << 2, (int)(src << 2), ins_total, zpar);
                     zpar ^= 1u;
                     __syncthreads();                                       /* window consumed */
                     if (tid < 4) { const u32 c = sm.win[src + tid]; sm.win[src + tid] = 0u; sm.win[tid] = c; }
@@ -649,6 +678,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     for (u32 i = 1u + (u32)tid; i < src / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
                     wbase = wf_al;
                     __syncthreads();
+                    STAGE_MARK(5);
                 }
             }
 
@@ -712,6 +742,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     }
                 }
 
+                STAGE_MARK(3);                                  /* stage next tile, header, concatenation path + merge */
                 /* ---- queue: items of this tile in rounds of LCAP, one lane per item ----------- */
                 for (u32 r0 = 0; r0 < total_items; r0 += (u32)LCAP) {
                     if (r0) __syncthreads();                               /* the previous round is consumed */
@@ -727,7 +758,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                                     prev = g0 + k;
                                     if (slot < (u32)LCAP) {
                                         uint2 h = make_uint2(0u, 0u);
-                                        if (kd == MBK_LONG) h = staged_hint(hb, qo, k);
+                                        if (kd == MBK_LONG) h = __ldg(geo.fh + g0 + k);   /* the staged tile is being replaced */
                                         const Item it = make_item(kd, code[k], len[k], bit, pre, h.x, h.y);
                                         sm.items[slot] = make_uint4(it.x, it.y, it.z, it.w);
                                     }
@@ -740,14 +771,11 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                             sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
                     }
                     __syncthreads();
-                    const u32 n_round = min((u32)LCAP, total_items - r0);
-                    for (u32 i = (u32)tid; i < n_round; i += NT) {
-                        const uint4 q = sm.items[i];
-                        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
-                        consume_item(it, sm.win, wbase, (u32)CH, num_refs, sm.tab, sm.pay_words, sm.n_pay_words);
-                    }
+                    STAGE_MARK(6);                              /* queue: push + wait for the slowest writer */
+                    consume_round(sm, min((u32)LCAP, total_items - r0), wbase, num_refs);
                 }
 
+                STAGE_MARK(4);                                  /* queue */
                 const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
                 if (!(last || !fits)) break;                               /* keep filling the window with the next tile */
 
@@ -756,7 +784,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
                 const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
-                ins_total += emit_window(sm, chunk_byte0, chunk_bytes, ins_total, zpar, spar);
+                ins_total += emit_window(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
                 if (chunk_bytes > 0) zpar ^= 1u;
                 __syncthreads();                                               /* window fully consumed */
                 {   /* clear the words this window used */
@@ -764,6 +792,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     uint4 *w4 = (uint4 *)sm.win;
                     for (u32 i = (u32)tid; i < (used + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
+                STAGE_MARK(5);                                  /* emit + window clear */
                 if (fits) break;                                               /* (frame done) */
                 wbase += CH;                                                   /* a full window has left; the tile goes on in the next one */
                 __syncthreads();
@@ -773,14 +802,26 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             last_coded = last_coded_total;
             if (last && tid == 0) sizes[f] = total_bytes + ins_total;
             ipar ^= 1u;
-            hpar ^= 1u;
             s0 += n;
         }
         f = f_next;
         geo = geo_next;
     }
     cp_async_wait_all();
+#if COMPOSE_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(&g_stage_cycles[i], (unsigned long long)stage_acc[i]);
+#endif
 }
+
+#if COMPOSE_TIMING
+cudaError_t read_stage_cycles(unsigned long long *h8) {
+    cudaError_t e = cudaMemcpyFromSymbol(h8, g_stage_cycles, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof z);
+    return e;
+}
+#endif
 
 /* ------------------------------------------------------------ rasteriser */
 

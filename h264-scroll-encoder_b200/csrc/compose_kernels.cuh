@@ -10,7 +10,7 @@
 #define COMPOSE_THREADS      256     /* threads per CTA */
 #endif
 #ifndef COMPOSE_MIN_CTAS
-#define COMPOSE_MIN_CTAS     3       /* resident CTAs per SM the register budget is sized for */
+#define COMPOSE_MIN_CTAS     4       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
 #define COMPOSE_WINDOW_WORDS 6144    /* slice words staged in shared memory per pass (multiple of 4) */

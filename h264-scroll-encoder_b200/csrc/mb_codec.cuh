@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define HSD __host__ __device__ __forceinline__
+#define HSD_NOINLINE __host__ __device__ __noinline__
 #else
 #define HSD static inline
+#define HSD_NOINLINE static
 #endif
 
 namespace h264scroll {
@@ -668,12 +670,12 @@ HSD u32 canonical_hint_y(u32 y) { return ((y >> 8) & 0xFFu) == H264GPU_MB_DYN_IN
 #define MBK_NONE  0u      /* absent or P_Skip: no bits of its own */
 #define MBK_SHORT 1u      /* whole code (with its mb_skip_run prefix) in <= 32 bits */
 #define MBK_LONG  2u      /* inline code longer than that: code = packed predictor, rebuilt by the consumer */
-#define MBK_DYN   3u      /* spliced: code = dyn index */
+#define MBK_DYN   3u      /* spliced: code = payload bit offset (len = prefix + payload bits) */
 #define MBK_PFX   4u      /* short body whose mb_skip_run prefix does not fit beside it (SPEC skip only) */
 
 /* queue items: x = slice bit | type << 30 */
 #define IT_BITS 0u        /* y = prefix value (0: none), z = code, w = code bits */
-#define IT_DYN  1u        /* y = prefix value, z = dyn index */
+#define IT_DYN  1u        /* y = prefix value, z = payload bit offset, w = payload bits */
 #define IT_LONG 2u        /* y = prefix value | ref << 24, z = mvd_x, w = mvd_y */
 #define IT_BIT_MASK 0x3FFFFFFFu
 
@@ -869,22 +871,86 @@ HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 
     }
 }
 
+/* four payload words (MSB-first) from the 16-byte aligned chunk `c` of the payload's address range;
+   words outside [lo, hi) (absolute word indices) read as 0 */
+HSD void pay_chunk(const u32 *base_al, u32 c, u32 lo, u32 hi, u32 (&w)[4]) {
+#if defined(__CUDA_ARCH__)
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (4u * c + 3u >= lo && 4u * c < hi) v = __ldg((const uint4 *)base_al + c);   /* inside the allocation: see DESIGN.md */
+    w[0] = __byte_perm(v.x, 0u, 0x0123u); w[1] = __byte_perm(v.y, 0u, 0x0123u);
+    w[2] = __byte_perm(v.z, 0u, 0x0123u); w[3] = __byte_perm(v.w, 0u, 0x0123u);
+#else
+    for (u32 t = 0; t < 4u; t++) { const u32 x = 4u * c + t; w[t] = (x >= lo && x < hi) ? bswap32(base_al[x]) : 0u; }
+#endif
+}
+
+/*
+ * copy_bits (src/h264_writer.c:228-240) as one funnel-shift stream: `len` payload bits from payload bit `src`
+ * to slice bit `dst`.  The stream is read from payload bit src - (dst & 31), so every output word is one
+ * funnel shift of two consecutive payload words; the payload is fetched in 16-byte aligned chunks (one
+ * 128-bit load per four words).  Whole window words are plain stores; the first and the last word are masked
+ * and OR-ed in (first_or = extra bits for the first word, e.g. the mb_skip_run '1').
+ */
+HSD void splice_stream(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 n_words, u32 src, u32 len, u32 first_or) {
+    const u32 s = dst & 31u;
+    if (src < s) {                                           /* the stream would start before the payload: rare, word by word */
+        splice_bits(win, wbase, wcap, dst, pw, n_words, src, len);
+        const u32 j = (dst >> 5) - wbase;
+        if (first_or && j < wcap) WIN_OR(&win[j], first_or);
+        return;
+    }
+    const u32 P = src - s, sh = P & 31u;
+    const u32 M = (s + len + 31u) >> 5;                      /* output words */
+    const u32 e = (s + len) & 31u;
+    const u32 fm = 0xFFFFFFFFu >> s, lm = e ? ~(0xFFFFFFFFu >> e) : 0xFFFFFFFFu;
+    const u32 j0 = (dst >> 5) - wbase;
+    const u32 a0 = (u32)(((uintptr_t)pw >> 2) & 3u);         /* words between the 16-byte boundary below the payload and its start */
+    const u32 *base_al = pw - a0;
+    const u32 X0 = (P >> 5) + a0, hi = n_words + a0;
+    u32 c = X0 >> 2;
+    u32 m = 4u * c - X0 - 1u;                                /* output word completed by the chunk's first payload word (wraps below 0) */
+    u32 prev = 0u;
+    for (; (int)m < (int)M; c++, m += 4u) {
+        u32 w[4];
+        pay_chunk(base_al, c, a0, hi, w);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (u32 t = 0; t < 4u; t++) {
+            const u32 mm = m + t;
+            if (mm < M) {
+                u32 v = fshl(prev, w[t], (int)sh);
+                const u32 j = j0 + mm;
+                if (mm - 1u < M - 2u) { if (j < wcap) win[j] = v; }          /* 1 <= mm <= M - 2: a whole word of this macroblock */
+                else {
+                    if (mm == 0u) v = (v & fm) | first_or;
+                    if (mm == M - 1u) v &= lm;
+                    if (j < wcap && v) WIN_OR(&win[j], v);
+                }
+            }
+            prev = w[t];
+        }
+    }
+}
+
 /* one queue item -> window */
-HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_refs,
-                      const u32 *tab, const u32 *pw, u32 n_words) {
+HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_refs, const u32 *pw, u32 n_words) {
     u32 bit = it.x & IT_BIT_MASK;
     const u32 type = it.x >> 30;
-    const u32 pre = type == IT_LONG ? (it.y & 0xFFFFFFu) : it.y;
+    u32 pre = type == IT_LONG ? (it.y & 0xFFFFFFu) : it.y;
+    u32 src = it.z, n = it.w;
+    const bool fused = type == IT_DYN && pre == 1u && src != 0u;
+    const u32 bit0 = bit;
+    if (fused) { src -= 1u; n += 1u; pre = 0u; }              /* mb_skip_run = 0, a single '1' in front: splice from one bit early, set that bit afterwards */
     if (pre) {
         const u32 pn = 2u * flo32(pre) + 1u;                 /* ue(run): run + 1 in 2m+1 bits */
         win_or64(win, wbase, wcap, bit, (u64)pre, pn);
         bit += pn;
     }
     if (type == IT_BITS) {
-        if (it.w) win_or64(win, wbase, wcap, bit, (u64)it.z, it.w);
+        if (n) win_or64(win, wbase, wcap, bit, (u64)src, n);
     } else if (type == IT_DYN) {
-        const u32 b0 = tab[it.z], len = tab[it.z + 1u] - b0;
-        splice_bits(win, wbase, wcap, bit, pw, n_words, b0, len);
+        if (n) splice_stream(win, wbase, wcap, bit, pw, n_words, src, n, fused ? 0x80000000u >> (bit0 & 31u) : 0u);
     } else {
         MbEntry e;
         int bl = encode_p16x16_body((int)(it.y >> 24), (int)it.z, (int)it.w, num_refs, e);
@@ -934,7 +1000,7 @@ HSD Item make_item(u32 kd, u32 code, u32 len, u32 bit, u32 pre, u32 hx, u32 hy) 
     Item it;
     if (kd == MBK_SHORT) { it.x = bit | (IT_BITS << 30); it.y = 0u; it.z = code; it.w = len; }
     else if (kd == MBK_PFX) { it.x = bit | (IT_BITS << 30); it.y = pre; it.z = code; it.w = len - (2u * flo32(pre) + 1u); }
-    else if (kd == MBK_DYN) { it.x = bit | (IT_DYN << 30); it.y = pre; it.z = code; it.w = 0u; }
+    else if (kd == MBK_DYN) { it.x = bit | (IT_DYN << 30); it.y = pre; it.z = code; it.w = len - (2u * flo32(pre) + 1u); }
     else {
         it.x = bit | (IT_LONG << 30);
         it.y = pre | ((hy & 0xFFu) << 24);

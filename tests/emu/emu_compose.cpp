@@ -176,22 +176,18 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 if (k >= nmb) continue;
                 const H2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
                 const bool dyn = (h.y & 0xFF00u) != 0u;
-                u32 dA = (h.x ^ a.x) | (h.y ^ a.y);
-                u32 dBC = (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y);
-                bool none = false;
-                if (!skip_spec) {                       /* as decide_segment in the kernel */
-                    if (k == 0 && col == 0) dA = 0u;
-                    if (row == 0) dBC = 0u;
-                    none = k == 0 && col == 0 && row == 0;
-                }
-                const bool uni = (dA | dBC) == 0u && !none && !dyn;
+                bool uni;                                /* as decide_segment in the kernel */
+                if (skip_spec) uni = ((h.x ^ a.x) | (h.y ^ a.y) | (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
+                else if (row == 0) uni = ((h.x ^ a.x) | (h.y ^ a.y)) == 0u;
+                else uni = ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
+                uni = uni && !dyn;
                 u32 kd;
                 if (uni && ((s + k) % 3)) kd = decide_mb_uniform(h.y, num_refs, skip_spec, T.code[k], T.len[k]);
                 else if ((h.y & 0xFF00u) == 0) kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, T.code[k], T.len[k]);
                 else {
                     const u32 di = h.y >> 16;
                     T.len[k] = tab[di + 1] - tab[di] + (skip_spec ? 0u : 1u);
-                    T.code[k] = di;
+                    T.code[k] = tab[di];
                     kd = MBK_DYN;
                 }
                 T.kinds |= kd << (4 * k);
@@ -270,7 +266,7 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 } else bit += T.Ls;
                 if (T.trailer) { Item it; it.x = bit | (IT_BITS << 30); it.y = 0; it.z = tr_code; it.w = tr_len; items.push_back(it); }
             }
-            for (auto &it : items) consume_item(it, win.data(), wbase, CH, num_refs, tab, pay_words, n_pay_words);
+            for (auto &it : items) consume_item(it, win.data(), wbase, CH, num_refs, pay_words, n_pay_words);
 
             const bool fits = w_last - wbase < CH;
             if (!(last || !fits)) break;
