@@ -45,50 +45,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~2 ms during the timed region
+    (the region lasts tens of milliseconds: too short for nvidia-smi's 100 ms loop)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.sm, self.reasons, self.stop_flag, self.t, self.max = index, [], 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                       # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:                        # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        nv, names = self.nv, []
+        for name, bit in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                          ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                          ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                          ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            b = getattr(nv, bit, None)
+            if b is None:
+                b = getattr(nv, bit.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
+            if self.reasons & int(b):
+                names.append(name)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max,
+                "samples": len(self.sm), "reasons": names}
 
 
 def dist_env():
@@ -201,8 +203,7 @@ def main_ours(args):
     d_info, d_dyn, d_tab, d_pay = gc.to_device(b.dyn_info), gc.to_device(b.dyn), gc.to_device(b.dyn_tab), gc.to_device(pay_pad)
     d_hints = gc.alloc(8 * b.hint_stride * n)
     d_out = gc.alloc(b.slot_cap * n)
-    d_packed = gc.alloc(b.slot_cap * n // 2)
-    d_sizes, d_offs = gc.alloc(4 * n), gc.alloc(8 * (n + 1))
+    d_sizes = gc.alloc(4 * n)
     gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
     gc.sync()
 
@@ -246,33 +247,69 @@ def main_ours(args):
     b_alg = 8 * total_mbs + s_dyn + 4 * 626 * n + s_out + 64 * n
 
     # ---- end to end: host buffers in, packed Annex-B stream out, every step ------------------------
+    # The batch goes through in chunks of frames on a few streams, so that the H2D of one chunk, the kernels of
+    # another and the D2H of a third overlap (PCIe is full duplex).  Every byte of input still crosses the bus
+    # every step and every byte of the packed stream comes back.
     def pinned(a):
         a = np.ascontiguousarray(a)
         p = L.h264gpu_host_alloc(max(a.nbytes, 16))
-        v = np.ctypeslib.as_array((ctypes.c_uint8 * a.nbytes).from_address(p))
-        v[:] = a.view(np.uint8).reshape(-1)
-        return p, a.nbytes
-    ups = [(pinned(x), d) for x, d in ((b.desc, d_desc), (b.rdesc, d_rdesc), (b.regions, d_reg), (b.dyn_info, d_info),
-                                       (b.dyn, d_dyn), (b.dyn_tab, d_tab), (b.payload, d_pay))]
-    h2d_bytes = sum(nb for (p, nb), d in ups)
+        v = np.ctypeslib.as_array((ctypes.c_uint8 * max(a.nbytes, 1)).from_address(p))
+        v[:a.nbytes] = a.view(np.uint8).reshape(-1)
+        return p
+    n_chunks = max(1, min(args.e2e_chunks, n))
+    bounds = [n * c // n_chunks for c in range(n_chunks + 1)]
+
+    def edge(arr_off, item, f, total):        # byte offset where frame f's share of a per-frame-indexed array starts
+        return int(arr_off[f]) * item if f < n else total
+    arrays = [  # (host array, device buffer, byte range of frames [f0, f1))
+        (b.desc, d_desc, lambda f: f * b.desc.itemsize),
+        (b.rdesc, d_rdesc, lambda f: f * b.rdesc.itemsize),
+        (b.regions, d_reg, lambda f: edge(b.rdesc["region_first"], b.regions.itemsize, f, b.regions.nbytes)),
+        (b.dyn_info, d_info, lambda f: edge(b.rdesc["dyn_info_off"], b.dyn_info.itemsize, f, b.dyn_info.nbytes)),
+        (b.dyn, d_dyn, lambda f: f * b.dyn.itemsize),
+        (b.dyn_tab, d_tab, lambda f: edge(b.dyn["table_off"], 4, f, b.dyn_tab.nbytes)),
+        (b.payload, d_pay, lambda f: edge(b.dyn["payload_off"], 1, f, b.payload.nbytes)),
+    ]
+    ups = [(pinned(a), d, rng) for a, d, rng in arrays]
+    h2d_bytes = sum(a.nbytes for a, _, _ in arrays)
+    chunk_frames = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
+    chunk_cap = b.slot_cap * chunk_frames // 2
+    d_packed_c = gc.alloc(chunk_cap * n_chunks)
+    d_offs_c = gc.alloc(8 * (chunk_frames + 1) * n_chunks)
     h_out = L.h264gpu_host_alloc(b.slot_cap * n // 2)
-    h_offs = L.h264gpu_host_alloc(8 * (n + 1))
-    offs_view = np.ctypeslib.as_array((ctypes.c_uint64 * (n + 1)).from_address(h_offs))
-    est_total = [s_out]
+    h_offs = L.h264gpu_host_alloc(8 * (chunk_frames + 1) * n_chunks)
+    offs_view = np.ctypeslib.as_array((ctypes.c_uint64 * ((chunk_frames + 1) * n_chunks)).from_address(h_offs))
+    streams = [L.h264gpu_stream_create() for _ in range(min(4, n_chunks))]
+    LAG = 2
 
     def e2e_step():
-        for (p, nb), d in ups:
-            gc.check(L.h264gpu_memcpy_h2d(d.ptr, p, nb, None))
-        gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
-        gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
-        gc.pack_frames(d_desc, d_sizes, n, d_out, d_packed, d_offs)
-        gc.check(L.h264gpu_memcpy_d2h(h_offs, d_offs.ptr, 8 * (n + 1), None))
-        gc.sync()
-        tot = int(offs_view[n])
-        gc.check(L.h264gpu_memcpy_d2h(h_out, d_packed.ptr, tot, None))
-        gc.sync()
-        est_total[0] = tot
-        return tot
+        total = 0
+        for c in range(n_chunks + LAG):
+            if c < n_chunks:
+                f0, f1, st = bounds[c], bounds[c + 1], streams[c % len(streams)]
+                for p, d, rng in ups:
+                    o0, o1 = rng(f0), rng(f1)
+                    if o1 > o0:
+                        gc.check(L.h264gpu_memcpy_h2d(d.ptr + o0, p + o0, o1 - o0, st))
+                gc.check(L.h264gpu_raster_regions(d_rdesc.ptr + f0 * b.rdesc.itemsize, f1 - f0, n_mbs, d_reg.ptr, d_info.ptr,
+                                                  d_hints.ptr, st))
+                gc.check(L.h264gpu_compose_batch(d_desc.ptr + f0 * b.desc.itemsize, f1 - f0, d_hints.ptr, d_dyn.ptr, d_tab.ptr,
+                                                 d_pay.ptr, d_out.ptr, d_sizes.ptr + 4 * f0, st))
+                oo = 8 * (chunk_frames + 1) * c
+                gc.check(L.h264gpu_pack_frames(d_desc.ptr + f0 * b.desc.itemsize, d_sizes.ptr + 4 * f0, f1 - f0, d_out.ptr,
+                                               d_packed_c.ptr + chunk_cap * c, d_offs_c.ptr + oo, st))
+                gc.check(L.h264gpu_memcpy_d2h(h_offs + oo, d_offs_c.ptr + oo, 8 * (f1 - f0 + 1), st))
+            d = c - LAG
+            if d >= 0:
+                st = streams[d % len(streams)]
+                gc.check(L.h264gpu_stream_sync(st))
+                tot = int(offs_view[(chunk_frames + 1) * d + (bounds[d + 1] - bounds[d])])
+                assert tot <= chunk_cap, "packed chunk larger than its buffer"
+                gc.check(L.h264gpu_memcpy_d2h(h_out + total, d_packed_c.ptr + chunk_cap * d, tot, st))
+                total += tot
+        for st in streams:
+            gc.check(L.h264gpu_stream_sync(st))
+        return total
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -284,6 +321,7 @@ def main_ours(args):
     gc.sync()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert ablate or d2h == s_out, "packed stream size differs from the sum of the frame sizes"
+    e2e_launches = 4 * n_chunks                                  # raster + compose + pack (2 kernels) per chunk
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------
     ms_step, e2e_step_s = ms / args.steps, e2e_s
@@ -307,8 +345,10 @@ def main_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h + 8 * (n + 1)), "ms_per_step": 1e3 * e2e_step_s,
-                    "path": "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream"},
+                    "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks)), "ms_per_step": 1e3 * e2e_step_s,
+                    "chunks": n_chunks, "gpu_launches_per_step": e2e_launches,
+                    "path": "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream, "
+                            "in %d frame chunks over %d streams" % (n_chunks, len(streams))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "compose_frames_kernel",
                          "algorithmic_bytes_per_launch": int(b_alg), "bytes_per_mb": b_alg / total_mbs,
@@ -340,6 +380,7 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="frame chunks the end-to-end path pipelines over streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

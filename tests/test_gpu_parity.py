@@ -115,3 +115,28 @@ def test_overflowing_slot_is_reported(gpu, po, oracle):
     with pytest.raises(GpuError):
         gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload, out_bytes=4096)
     assert len(want) > 64
+
+
+def test_foreign_dense_map_is_canonicalised(gpu, po, oracle):
+    # a dense map written by somebody else: spliced intra MBs with arbitrary mv / ref 0 instead of mv 0 / ref 0xFF
+    b = workloads.make_random(40, 24, 2, seed=11, num_refs=3, n_regions=12, p_dyn=0.5)
+    hints = helpers.dense_hints(po, b)
+    raw = hints.copy()
+    intra = raw["kind"] == abi.MB_DYN_INTRA
+    assert intra.any()
+    raw["mvx"][intra] = 77
+    raw["mvy"][intra] = -5
+    raw["ref"][intra] = 0
+    d_h = gpu.to_device(raw)
+    gpu.canonicalize_hints(d_h, len(raw))
+    gpu.sync()
+    assert np.array_equal(d_h.download(abi.HINT), hints)
+    _compare(gpu, po, oracle, b, hints=raw)          # compose_host canonicalises on the device; the oracle goes by `kind`
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 9), (2, 3), (9, 1), (17, 2), (263, 3), (300, 2), (1023, 1)])
+def test_ragged_and_extreme_widths(gpu, po, oracle, w, h):
+    # widths that are not multiples of the 8-MB segment, single rows/columns, frames wider than a full hint tile
+    for flags in (0, abi.SKIP_SPEC | abi.PRED_SPEC):
+        b = workloads.make_random(w, h, 2, seed=w * 31 + h, num_refs=3, flags=flags, n_regions=6)
+        _compare(gpu, po, oracle, b)

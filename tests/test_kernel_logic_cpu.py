@@ -45,3 +45,12 @@ def test_emulated_pipeline_config_generators(emu, po, oracle):
     _check(emu, po, oracle, workloads.make_config5(1, 2), 256, 6144)
     _check(emu, po, oracle, workloads.make_config5(1, 1), 256, 512)
     _check(emu, po, oracle, workloads.make_config4(1), 256, 6144)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (9, 1), (17, 2), (263, 3), (300, 2), (1023, 1)])
+def test_emulated_pipeline_ragged_and_extreme_widths(emu, po, oracle, w, h):
+    # widths that are not multiples of the 8-MB segment; frames wider than a full hint tile (fewer segments per tile)
+    for flags in (0, abi.SKIP_SPEC | abi.PRED_SPEC):
+        b = workloads.make_random(w, h, 2, seed=w * 31 + h, num_refs=3, flags=flags, n_regions=6)
+        _check(emu, po, oracle, b, 256, 6144)
+        _check(emu, po, oracle, b, 8, 16)
