@@ -234,9 +234,9 @@ def main_ours(args):
     clocks = sampler.stop()
 
     if hasattr(L, "h264gpu_debug_stage_cycles"):                  # timing-instrumented experiment build only
-        cyc = (ctypes.c_uint64 * 8)()
+        cyc = (ctypes.c_uint64 * 16)()
         L.h264gpu_debug_stage_cycles(cyc)
-        tot = float(sum(cyc)) or 1.0
+        tot = float(sum(cyc[:8])) or 1.0
         sys.stderr.write("stage cycles (thread 0 of every CTA, warm-up + timed): " +
                          " ".join("%d:%.1f%%" % (i, 100.0 * c / tot) for i, c in enumerate(cyc)) + "\n")
     sizes = d_sizes.download(np.uint32)

@@ -950,7 +950,9 @@ HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_ref
     if (type == IT_BITS) {
         if (n) win_or64(win, wbase, wcap, bit, (u64)src, n);
     } else if (type == IT_DYN) {
-        if (n) splice_stream(win, wbase, wcap, bit, pw, n_words, src, n, fused ? 0x80000000u >> (bit0 & 31u) : 0u);
+        splice_bits(win, wbase, wcap, bit, pw, n_words, src, n);
+        const u32 j = (bit0 >> 5) - wbase;
+        if (fused && j < wcap) WIN_OR(&win[j], 0x80000000u >> (bit0 & 31u));
     } else {
         MbEntry e;
         int bl = encode_p16x16_body((int)(it.y >> 24), (int)it.z, (int)it.w, num_refs, e);
