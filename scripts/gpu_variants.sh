@@ -1,0 +1,18 @@
+#!/bin/bash
+# GPU box: bench several prebuilt library variants (variants/<tag>.so). Usage: gpu_variants.sh tag1 tag2 ...
+mkdir -p gpurun_out
+cp h264-scroll-encoder_b200/libh264scroll_b200.so /tmp/orig.so
+for tag in "$@"; do
+  cp variants/$tag.so h264-scroll-encoder_b200/libh264scroll_b200.so
+  timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -1
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_$tag.log 2> gpurun_out/bench_$tag.err
+  python - <<P
+import json
+try:
+    l=json.loads(open("gpurun_out/bench_$tag.log").read().strip().split("\n")[-1])
+    print("$tag: kernel %.3f ms  roofline %.3f  e2e %.2f ms" % (l["ms_per_step"], l["roofline"]["frac"], l["e2e"]["ms_per_step"]))
+except Exception as e:
+    print("$tag: failed", e)
+P
+done
+cp /tmp/orig.so h264-scroll-encoder_b200/libh264scroll_b200.so
