@@ -152,7 +152,7 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
     cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload,
                                                d_out, d_sizes, g_sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
-    if (n_frames > 0) g_launches.fetch_add(1);
+    if (n_frames > 0) g_launches.fetch_add(2);        /* reference-mode kernel + SPEC-mode kernel */
     return H264GPU_OK;
 }
 
@@ -243,7 +243,7 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
                                    (const uint32_t *)(base + o_tab), (const uint8_t *)(base + o_pay),
                                    (uint8_t *)(base + o_out), (uint32_t *)(base + o_sz), g_sm_count, st);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(2);
     e = cudaMemcpyAsync(h_sizes, base + o_sz, sizeof(uint32_t) * n_frames, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, base + o_out, out_bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -475,6 +475,19 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
     return kinds;
 }
 
+/* frames whose flags ask for SPEC skip / SPEC prediction belong to the SPEC = true instantiation, all others to the
+   SPEC = false one: the reference-mode kernel carries none of the SPEC code (the kernel is sensitive to the size of
+   its instruction stream).  Both are launched over the whole batch; each walks only its own frames. */
+__device__ __forceinline__ bool frame_is_spec(const H264GpuFrameDesc *__restrict__ descs, int f) {
+    return ((__ldg((const u32 *)(descs + f) + 15) >> 16) & (H264GPU_SKIP_SPEC | H264GPU_PRED_SPEC)) != 0u;
+}
+template <bool SPEC>
+__device__ __forceinline__ int next_own_frame(const H264GpuFrameDesc *__restrict__ descs, int f, int n_frames, int step) {
+    while (f < n_frames && frame_is_spec(descs, f) != SPEC) f += step;
+    return f;
+}
+
+template <bool SPEC>
 __global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
 compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuMbHint *__restrict__ hints,
@@ -486,7 +499,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
     ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
 
-    int f = blockIdx.x;
+    int f = next_own_frame<SPEC>(descs, blockIdx.x, n_frames, (int)gridDim.x);
     if (f >= n_frames) return;
 
     {   /* the window is zero wherever nothing was written: cleared once here, then every flush clears what it used */
@@ -513,8 +526,8 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         const int W = geo.W;
         const u32 hdr_total = 40u + (d3.w & 0xFFu);
         const int num_refs = (int)((d3.w >> 8) & 0xFFu);
-        const int skip_spec = ((d3.w >> 16) & H264GPU_SKIP_SPEC) != 0;
-        const int pred_spec = ((d3.w >> 16) & H264GPU_PRED_SPEC) != 0;
+        const int skip_spec = SPEC ? ((d3.w >> 16) & H264GPU_SKIP_SPEC) != 0 : 0;
+        const int pred_spec = SPEC ? ((d3.w >> 16) & H264GPU_PRED_SPEC) != 0 : 0;
         const u32 nal_header = d3.w >> 24;
         const u32 *tab = nullptr;
         {
@@ -544,7 +557,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         u32 zpar = 0;                  /* which sm.zrun slot holds the current state */
         u32 wbase = 0;                 /* frame word held by window word 0; words below it have left for global memory */
 
-        const int f_next = f + (int)gridDim.x;
+        const int f_next = next_own_frame<SPEC>(descs, f + (int)gridDim.x, n_frames, (int)gridDim.x);
         FrameGeo geo_next = geo;
         if (f_next < n_frames) geo_next = load_geo(descs, f_next, hints);
 
@@ -600,7 +613,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             /* ---- decide + code ------------------------------------------------ */
             u32 code[MPT], len[MPT];
             u32 kinds;
-            if (!skip_spec && !pred_spec) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
+            if (!SPEC) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
             else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
 
             STAGE_MARK(1);                                      /* load + decide */
@@ -958,16 +971,18 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
     static int ctas_per_sm = 0;           /* resident CTAs per SM for this build (registers / shared memory) */
     const int smem = (int)sizeof(ComposeSmem);
     if (ctas_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(compose_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(compose_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(compose_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel, NT, smem) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel<false>, NT, smem) != cudaSuccess || n < 1) n = 1;
         ctas_per_sm = n;
     }
     const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
     int grid = n_frames < resident ? n_frames : resident;
-    compose_frames_kernel<<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab,
-                                                      d_payload, d_out, d_sizes);
+    /* reference-mode frames, then the frames with SPEC flags (that launch returns at once when there are none) */
+    compose_frames_kernel<false><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
+    compose_frames_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
     return cudaGetLastError();
 }
 
