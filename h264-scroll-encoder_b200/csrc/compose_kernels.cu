@@ -178,12 +178,30 @@ __device__ __forceinline__ int seg_row(const FrameGeo &g, int s) {
  * (8 hints, the tail of a row's last segment stays unwritten), chunks swizzled.  Segments before the
  * frame's first are filled with the "unavailable" hint.
  */
+/* frames whose width is not a multiple of 8 macroblocks: chunk by chunk, with its row and column (rare: out of line) */
+__device__ __noinline__ void stage_hints_ragged(uint4 *buf, const uint2 *fh, int W, int tpr, u32 tpr_magic, int n_seg, int s_base, int n_chunks) {
+    const u32 buf_s = smem_u32(buf);
+    for (int c = threadIdx.x; c < n_chunks; c += NT) {
+        const u32 pc = hint_swizzle((u32)c);
+        const int s = s_base + (c >> 2);
+        if (s < 0) { buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL); continue; }
+        if (s >= n_seg) continue;
+        const int row = tpr == 1 ? s : (int)__umulhi((u32)s, tpr_magic), x = MPT * (s - row * tpr) + 2 * (c & 3);
+        const long long gi = (long long)row * W + x;
+        if (x + 1 < W && !(gi & 1)) cp_async16(buf_s + 16u * pc, fh + gi);
+        else {
+            if (x < W) cp_async8(buf_s + 16u * pc, fh + gi);
+            if (x + 1 < W) cp_async8(buf_s + 16u * pc + 8u, fh + gi + 1);
+        }
+    }
+}
+
 __device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s0, int n) {
     const int s_base = s0 - g.tpr - 1;
     const int n_chunks = 4 * (n + g.tpr + 1);
-    const u32 buf_s = smem_u32(buf);
     if ((g.W & 7) == 0) {
         /* segments tile the dense map exactly: chunk c of the tile is chunk 4 * s_base + c of the map */
+        const u32 buf_s = smem_u32(buf);
         const uint4 *src = (const uint4 *)g.fh + 4 * (long long)s_base;
         const int c_lo = -4 * s_base;                        /* first chunk inside the frame */
         const int c_hi = 4 * (g.n_seg - s_base);             /* first chunk past its end */
@@ -192,21 +210,7 @@ __device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s
             if (c >= c_lo) { if (c < c_hi) cp_async16(buf_s + 16u * pc, src + c); }
             else buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
         }
-    } else {
-        for (int c = threadIdx.x; c < n_chunks; c += NT) {
-            const u32 pc = hint_swizzle((u32)c);
-            const int s = s_base + (c >> 2);
-            if (s < 0) { buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL); continue; }
-            if (s >= g.n_seg) continue;
-            const int row = seg_row(g, s), x = MPT * (s - row * g.tpr) + 2 * (c & 3);
-            const long long gi = (long long)row * g.W + x;
-            if (x + 1 < g.W && !(gi & 1)) cp_async16(buf_s + 16u * pc, g.fh + gi);
-            else {
-                if (x < g.W) cp_async8(buf_s + 16u * pc, g.fh + gi);
-                if (x + 1 < g.W) cp_async8(buf_s + 16u * pc + 8u, g.fh + gi + 1);
-            }
-        }
-    }
+    } else stage_hints_ragged(buf, g.fh, g.W, g.tpr, g.tpr_magic, g.n_seg, s_base, n_chunks);
 }
 
 /* hint i (0..7) of slot q / 16-byte chunk of a staged tile */
@@ -297,7 +301,7 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
         /* even with an insertion after every second byte the pass stays clear of the slot's end */
         const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) + ins_total + 4u <= cap;
         /* ---- classify ---- */
-#pragma unroll
+#pragma unroll 1                                             /* (code size matters more than the loop overhead) */
         for (int r = 0; r < EG; r++) {
             const int gl = tid + NT * r, q = q0 + gl;
             const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
@@ -332,22 +336,22 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
         __syncthreads();
         if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
         /* ---- offsets ---- */
-        u32 g[EG];
-#pragma unroll
-        for (int r = 0; r < EG; r++) g[r] = sm.gi[tid + NT * r];
-        u32 lo = (g[0] & 0xFFu) | ((g[1] & 0xFFu) << 16), hi = (g[2] & 0xFFu) | ((g[3] & 0xFFu) << 16);
+        u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
+        u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
         u32 tlo, thi;
         block_excl_scan_x2(lo, hi, sm.scan2, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
         const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
-        const u32 before[EG] = {ins_total + (lo & 0xFFFFu), ins_total + t0 + (lo >> 16),
-                                ins_total + t0 + t1 + (hi & 0xFFFFu), ins_total + t0 + t1 + t2 + (hi >> 16)};
         /* ---- store: clean groups ---- */
-#pragma unroll
+        u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
+#pragma unroll 1
         for (int r = 0; r < EG; r++) {
             const int gl = tid + NT * r, q = q0 + gl;
-            if ((g[r] >> 8) == 0u) continue;                 /* past the chunk */
-            if (!(roomy && g[r] == GI_CLEAN)) { sm.gpre[gl] = before[r]; continue; }
-            const u32 D = chunk_byte0 + 16u * (u32)q + before[r];      /* output byte of the group's first byte */
+            const u32 g = sm.gi[gl];
+            const u32 before = round_base + (((r & 2) ? hi : lo) >> (16 * (r & 1)) & 0xFFFFu);
+            round_base += ((r & 2) ? thi : tlo) >> (16 * (r & 1)) & 0xFFFFu;
+            if ((g >> 8) == 0u) continue;                    /* past the chunk */
+            if (!(roomy && g == GI_CLEAN)) { sm.gpre[gl] = before; continue; }
+            const u32 D = chunk_byte0 + 16u * (u32)q + before;         /* output byte of the group's first byte */
             const uint4 w = ((const uint4 *)sm.win)[q];
             const u32 s = (4u - (D & 3u)) & 3u;              /* source bytes before the first aligned word */
             u32 *dst = fout32 + ((D + s) >> 2);
@@ -665,8 +669,11 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const u32 total_items = sm.n_items[ipar];
             STAGE_MARK(2);                                      /* prefixes, bit counts, scan (incl. its barrier) */
             /* ---- stage: everybody is past its loads from the hint tile: start the copy of the next one ---- */
-            if (!last) stage_hints(sm.hbuf, geo, s0 + n, min(geo.seg_max, geo.n_seg - s0 - n));
-            else if (f_next < n_frames) stage_hints(sm.hbuf, geo_next, 0, min(geo_next.seg_max, geo_next.n_seg));
+            if (!last || f_next < n_frames) {
+                const FrameGeo &gn = last ? geo_next : geo;
+                const int sn = last ? 0 : s0 + n;
+                stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
+            }
             cp_async_commit();
             if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
             const u32 E = O + L;
