@@ -7,16 +7,17 @@
 #include "composer_gpu.h"
 
 #ifndef COMPOSE_THREADS
-#define COMPOSE_THREADS      256     /* threads per CTA */
+#define COMPOSE_THREADS      512     /* threads per CTA: a tile is 4096 macroblocks.  Few large CTAs beat many small ones here:
+                                        fewer code regions in flight per SM (the kernel is sensitive to instruction fetch) */
 #endif
 #ifndef COMPOSE_MIN_CTAS
-#define COMPOSE_MIN_CTAS     4       /* resident CTAs per SM the register budget is sized for */
+#define COMPOSE_MIN_CTAS     2       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
-#define COMPOSE_WINDOW_WORDS 6144    /* slice words staged in shared memory per pass (multiple of 4) */
+#define COMPOSE_WINDOW_WORDS 8192    /* slice words staged in shared memory per pass (multiple of 4) */
 #endif
 #ifndef COMPOSE_ITEM_SLOTS
-#define COMPOSE_ITEM_SLOTS   256     /* work-queue items per round */
+#define COMPOSE_ITEM_SLOTS   512     /* work-queue items per round */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
 #define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
