@@ -200,15 +200,22 @@ __device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s
     const int s_base = s0 - g.tpr - 1;
     const int n_chunks = 4 * (n + g.tpr + 1);
     if ((g.W & 7) == 0) {
-        /* segments tile the dense map exactly: chunk c of the tile is chunk 4 * s_base + c of the map */
-        const u32 buf_s = smem_u32(buf);
-        const uint4 *src = (const uint4 *)g.fh + 4 * (long long)s_base;
+        /* segments tile the dense map exactly: chunk c of the tile is chunk 4 * s_base + c of the map.  A thread's
+           chunks are NT apart, which leaves the swizzle term unchanged: one address each side, then fixed strides */
+        const int tid = threadIdx.x;
+        const u32 dst = smem_u32(buf) + 16u * hint_swizzle((u32)tid);
+        uint4 *dst_g = buf + hint_swizzle((u32)tid);
+        const uint4 *src = (const uint4 *)g.fh + (4 * (long long)s_base + tid);
         const int c_lo = -4 * s_base;                        /* first chunk inside the frame */
-        const int c_hi = 4 * (g.n_seg - s_base);             /* first chunk past its end */
-        for (int c = threadIdx.x; c < n_chunks; c += NT) {
-            const u32 pc = hint_swizzle((u32)c);
-            if (c >= c_lo) { if (c < c_hi) cp_async16(buf_s + 16u * pc, src + c); }
-            else buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
+        const u32 c_span = (u32)(4 * g.n_seg);               /* chunks of the frame */
+        static_assert(NT % 64 == 0, "the swizzle term must not change between a thread's chunks");
+#pragma unroll
+        for (int i = 0; i < (HBS * 4 + NT - 1) / NT; i++) {
+            const int c = tid + i * NT;
+            if (c < n_chunks) {
+                if ((u32)(c - c_lo) < c_span) cp_async16(dst + 16u * (u32)(i * NT), src + i * NT);
+                else if (c < c_lo) dst_g[i * NT] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
+            }
         }
     } else stage_hints_ragged(buf, g.fh, g.W, g.tpr, g.tpr_magic, g.n_seg, s_base, n_chunks);
 }

@@ -17,7 +17,7 @@
 #define COMPOSE_WINDOW_WORDS 8192    /* slice words staged in shared memory per pass (multiple of 4) */
 #endif
 #ifndef COMPOSE_ITEM_SLOTS
-#define COMPOSE_ITEM_SLOTS   512     /* work-queue items per round */
+#define COMPOSE_ITEM_SLOTS   1024    /* work-queue items per round */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
 #define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
