@@ -140,3 +140,60 @@ def test_ragged_and_extreme_widths(gpu, po, oracle, w, h):
     for flags in (0, abi.SKIP_SPEC | abi.PRED_SPEC):
         b = workloads.make_random(w, h, 2, seed=w * 31 + h, num_refs=3, flags=flags, n_regions=6)
         _compare(gpu, po, oracle, b)
+
+
+def _all_spliced_batch(w, h, n_frames, flags=0):
+    """Every macroblock of the frame spliced: several queue rounds per tile and tiles larger than the window."""
+    b = workloads.Batch(w, h)
+    b.name = "all spliced %dx%d" % (w, h)
+    headers, regs, infos, tabs, pays = [], [], [], [], []
+    for t in range(n_frames):
+        headers.append(workloads.p_header_bits(2 + t))
+        regs.append(workloads.region(0, 0, w, h, kind=abi.REGION_DYN, dyn_base=0))
+        i, tb, p = workloads.dyn_region_payload(7000 + t, w * h)
+        infos.append(i); tabs.append(tb); pays.append(p)
+    slot = (w * h * 80 + 4096 + 15) & ~15
+    return workloads._finish(b, headers, regs, 2, flags, slot, (infos, tabs, pays))
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (120, 68)])
+def test_all_spliced_frames_overflow_queue_and_window(gpu, po, oracle, w, h):
+    for flags in (0, abi.SKIP_SPEC | abi.PRED_SPEC):
+        _compare(gpu, po, oracle, _all_spliced_batch(w, h, 2, flags))
+
+
+def test_config5_full_size_properties(gpu, po, oracle):
+    """BASELINE config 5 at scale (32 streams x 64 frames = 2048 frames of 1920x1088) through the device-pointer
+    calls: structural properties on every frame, byte parity with the oracle on a sample."""
+    b = workloads.make_config5(32, 64)
+    n = b.n_frames
+    d_desc, d_rd, d_reg = gpu.to_device(b.desc), gpu.to_device(b.rdesc), gpu.to_device(b.regions)
+    d_info, d_dyn, d_tab = gpu.to_device(b.dyn_info), gpu.to_device(b.dyn), gpu.to_device(b.dyn_tab)
+    d_pay = gpu.to_device(np.concatenate([b.payload, np.zeros(16, np.uint8)]))
+    d_h = gpu.alloc(8 * b.hint_stride * n)
+    d_out, d_packed = gpu.alloc(b.slot_cap * n), gpu.alloc(b.slot_cap * n // 2)
+    d_sizes, d_offs = gpu.alloc(4 * n), gpu.alloc(8 * (n + 1))
+    outs = []
+    for _ in range(2):                                    # idempotence: the same batch twice gives the same bytes
+        gpu.raster_regions(d_rd, n, b.n_mbs, d_reg, d_info, d_h)
+        gpu.compose_batch(d_desc, n, d_h, d_dyn, d_tab, d_pay, d_out, d_sizes)
+        gpu.pack_frames(d_desc, d_sizes, n, d_out, d_packed, d_offs)
+        offs = d_offs.download(np.uint64)
+        outs.append((d_sizes.download(np.uint32), offs, d_packed.download(np.uint8, count=int(offs[-1]))))
+    (sizes, offs, stream), (sizes2, offs2, stream2) = outs
+    assert np.array_equal(sizes, sizes2) and np.array_equal(stream, stream2)
+    assert (sizes <= b.slot_cap).all() and (sizes > 5).all()
+    assert np.array_equal(offs[1:] - offs[:-1], sizes.astype(np.uint64))         # packed in append order, no gaps
+    starts = offs[:-1].astype(np.int64)
+    sc = np.stack([stream[starts + k] for k in range(5)], axis=1)
+    assert (sc == np.array([0, 0, 0, 1, 0x01], np.uint8)).all()                  # start code + NAL header of a P slice
+    # emulation prevention: behind the start code no 00 00 0x (x <= 2) anywhere inside a NAL unit
+    z = stream == 0
+    bad = np.nonzero(z[:-2] & z[1:-1] & (stream[2:] <= 2))[0]
+    assert np.isin(bad, np.concatenate([starts, starts + 1])).all()
+    assert (stream[(offs[1:] - 1).astype(np.int64)] != 0).all()                  # rbsp_stop_one_bit: no NAL ends in 00
+    hints = d_h.download(abi.HINT)
+    for f in np.random.default_rng(5).choice(n, 24, replace=False):
+        want = helpers.checker_frame(oracle, b, hints, int(f))
+        got = stream[int(offs[f]):int(offs[f + 1])]
+        assert np.array_equal(got, want), "frame %d" % f
