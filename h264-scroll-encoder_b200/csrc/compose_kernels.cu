@@ -492,9 +492,19 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
 __device__ __forceinline__ bool frame_is_spec(const H264GpuFrameDesc *__restrict__ descs, int f) {
     return ((__ldg((const u32 *)(descs + f) + 15) >> 16) & (H264GPU_SKIP_SPEC | H264GPU_PRED_SPEC)) != 0u;
 }
+/* first frame f, f + step, f + 2 step ... that belongs to this instantiation; called by whole warps with the same
+   arguments: the lanes look at 32 candidates at a time */
 template <bool SPEC>
 __device__ __forceinline__ int next_own_frame(const H264GpuFrameDesc *__restrict__ descs, int f, int n_frames, int step) {
-    while (f < n_frames && frame_is_spec(descs, f) != SPEC) f += step;
+    const int lane = threadIdx.x & 31;
+    while (f < n_frames) {
+        const long long mine = (long long)f + (long long)lane * step;
+        const bool own = mine < n_frames && frame_is_spec(descs, (int)mine) == SPEC;
+        const u32 m = __ballot_sync(FULL, own);
+        if (m) return f + (__ffs((int)m) - 1) * step;
+        if ((long long)f + 32ll * step >= n_frames) return n_frames;
+        f += 32 * step;
+    }
     return f;
 }
 
