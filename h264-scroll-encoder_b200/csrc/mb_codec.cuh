@@ -871,68 +871,6 @@ HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 
     }
 }
 
-/* four payload words (MSB-first) from the 16-byte aligned chunk `c` of the payload's address range;
-   words outside [lo, hi) (absolute word indices) read as 0 */
-HSD void pay_chunk(const u32 *base_al, u32 c, u32 lo, u32 hi, u32 (&w)[4]) {
-#if defined(__CUDA_ARCH__)
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (4u * c + 3u >= lo && 4u * c < hi) v = __ldg((const uint4 *)base_al + c);   /* inside the allocation: see DESIGN.md */
-    w[0] = __byte_perm(v.x, 0u, 0x0123u); w[1] = __byte_perm(v.y, 0u, 0x0123u);
-    w[2] = __byte_perm(v.z, 0u, 0x0123u); w[3] = __byte_perm(v.w, 0u, 0x0123u);
-#else
-    for (u32 t = 0; t < 4u; t++) { const u32 x = 4u * c + t; w[t] = (x >= lo && x < hi) ? bswap32(base_al[x]) : 0u; }
-#endif
-}
-
-/*
- * copy_bits (src/h264_writer.c:228-240) as one funnel-shift stream: `len` payload bits from payload bit `src`
- * to slice bit `dst`.  The stream is read from payload bit src - (dst & 31), so every output word is one
- * funnel shift of two consecutive payload words; the payload is fetched in 16-byte aligned chunks (one
- * 128-bit load per four words).  Whole window words are plain stores; the first and the last word are masked
- * and OR-ed in (first_or = extra bits for the first word, e.g. the mb_skip_run '1').
- */
-HSD void splice_stream(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 n_words, u32 src, u32 len, u32 first_or) {
-    const u32 s = dst & 31u;
-    if (src < s) {                                           /* the stream would start before the payload: rare, word by word */
-        splice_bits(win, wbase, wcap, dst, pw, n_words, src, len);
-        const u32 j = (dst >> 5) - wbase;
-        if (first_or && j < wcap) WIN_OR(&win[j], first_or);
-        return;
-    }
-    const u32 P = src - s, sh = P & 31u;
-    const u32 M = (s + len + 31u) >> 5;                      /* output words */
-    const u32 e = (s + len) & 31u;
-    const u32 fm = 0xFFFFFFFFu >> s, lm = e ? ~(0xFFFFFFFFu >> e) : 0xFFFFFFFFu;
-    const u32 j0 = (dst >> 5) - wbase;
-    const u32 a0 = (u32)(((uintptr_t)pw >> 2) & 3u);         /* words between the 16-byte boundary below the payload and its start */
-    const u32 *base_al = pw - a0;
-    const u32 X0 = (P >> 5) + a0, hi = n_words + a0;
-    u32 c = X0 >> 2;
-    u32 m = 4u * c - X0 - 1u;                                /* output word completed by the chunk's first payload word (wraps below 0) */
-    u32 prev = 0u;
-    for (; (int)m < (int)M; c++, m += 4u) {
-        u32 w[4];
-        pay_chunk(base_al, c, a0, hi, w);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (u32 t = 0; t < 4u; t++) {
-            const u32 mm = m + t;
-            if (mm < M) {
-                u32 v = fshl(prev, w[t], (int)sh);
-                const u32 j = j0 + mm;
-                if (mm - 1u < M - 2u) { if (j < wcap) win[j] = v; }          /* 1 <= mm <= M - 2: a whole word of this macroblock */
-                else {
-                    if (mm == 0u) v = (v & fm) | first_or;
-                    if (mm == M - 1u) v &= lm;
-                    if (j < wcap && v) WIN_OR(&win[j], v);
-                }
-            }
-            prev = w[t];
-        }
-    }
-}
-
 /* one queue item -> window */
 HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_refs, const u32 *pw, u32 n_words) {
     u32 bit = it.x & IT_BIT_MASK;
