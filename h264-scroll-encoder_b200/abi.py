@@ -17,6 +17,11 @@ REGION = np.dtype([("x0", "<i2"), ("y0", "<i2"), ("x1", "<i2"), ("y1", "<i2"),
 RASTER_DESC = np.dtype([("region_first", "<u4"), ("region_count", "<u4"), ("hint_off", "<u8"),
                         ("mb_w", "<u2"), ("mb_h", "<u2"), ("dyn_info_off", "<u4")])
 
+REWRITE_DESC = np.dtype([("hdr_bits", "<u8", (4,)), ("src_off", "<u8"), ("src_bytes", "<u8"), ("src_start_bit", "<u8"),
+                         ("n_bits", "<u8"), ("out_off", "<u8"), ("out_cap", "<u4"), ("hdr_nbits", "<u2"),
+                         ("nal_header", "u1"), ("reserved", "u1")])
+
+assert REWRITE_DESC.itemsize == 80
 assert HINT.itemsize == 8 and FRAME_DESC.itemsize == 64 and DYN_DESC.itemsize == 32
 assert REGION.itemsize == 16 and RASTER_DESC.itemsize == 24
 

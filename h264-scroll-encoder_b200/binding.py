@@ -17,7 +17,8 @@ GPU_SYMBOLS = [
     "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
     "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
-    "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints"]
+    "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
+    "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes"]
 REFERENCE_API_SYMBOLS = [
     # include/composer.h
     "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
@@ -68,6 +69,7 @@ def load_library(path=None):
     L.h264gpu_raster_regions.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     L.h264gpu_pack_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.h264gpu_canonicalize_hints.argtypes = [vp, sz, vp]
+    L.h264gpu_rewrite_slices.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
     L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
     L.h264gpu_launch_count.restype = C.c_uint64
     return L
@@ -165,6 +167,26 @@ class GpuComposer:
 
     def canonicalize_hints(self, d_hints, n_hints, stream=None):
         self.check(self.lib.h264gpu_canonicalize_hints(d_hints.ptr, n_hints, stream))
+
+    def rewrite_slices(self, desc, src, out_bytes):
+        """Host convenience around h264gpu_rewrite_slices: desc = abi.REWRITE_DESC array, src = uint8 array holding the
+        source RBSPs.  Returns (list of NAL byte arrays, sizes)."""
+        n = len(desc)
+        cb = int(self.lib.h264gpu_rewrite_chunk_bytes())
+        total = (40 + desc["hdr_nbits"].astype(np.int64) + desc["n_bits"].astype(np.int64) + 7) // 8
+        max_chunks = max(1, int(((total + cb - 1) // cb).max())) if n else 1
+        d_desc = self.to_device(desc)
+        d_src = self.to_device(np.concatenate([src, np.zeros(16, np.uint8)]))
+        d_out, d_sizes, d_cnt = self.alloc(out_bytes), self.alloc(4 * max(n, 1)), self.alloc(4 * max(n, 1) * max_chunks)
+        self.check(self.lib.h264gpu_memset(d_out.ptr, 0xAA, out_bytes, None))
+        self.check(self.lib.h264gpu_rewrite_slices(d_desc.ptr, n, max_chunks, d_src.ptr, d_out.ptr, d_sizes.ptr, d_cnt.ptr, None))
+        self.sync()
+        sizes = d_sizes.download(np.uint32, count=n)
+        out = d_out.download(np.uint8)
+        res = [out[int(d["out_off"]):int(d["out_off"]) + min(int(s), int(d["out_cap"]))].copy() for d, s in zip(desc, sizes)]
+        for b_ in (d_desc, d_src, d_out, d_sizes, d_cnt):
+            b_.free()
+        return res, sizes
 
     def pack_frames(self, d_desc, d_sizes, n, d_slots, d_packed, d_offsets, stream=None):
         self.check(self.lib.h264gpu_pack_frames(d_desc.ptr, d_sizes.ptr, n, d_slots.ptr, d_packed.ptr,

@@ -177,6 +177,18 @@ int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *str
     return H264GPU_OK;
 }
 
+int h264gpu_rewrite_chunk_bytes(void) { return h264scroll::rewrite_chunk_bytes(); }
+
+int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,
+                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, void *stream) {
+    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    if (n_slices < 0 || max_chunks < 0 || !d_desc || !d_src || !d_out || !d_sizes || !d_counts) return fail(H264GPU_ERR_ARG, "null argument");
+    cudaError_t e = h264scroll::launch_rewrite(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_counts, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "rewrite launch", e);
+    if (n_slices > 0 && max_chunks > 0) g_launches.fetch_add(3);
+    return H264GPU_OK;
+}
+
 int h264gpu_pack_frames(const H264GpuFrameDesc *d_desc, const uint32_t *d_sizes, int n_frames,
                         const uint8_t *d_slots, uint8_t *d_packed, uint64_t *d_offsets, void *stream) {
     if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");

@@ -294,9 +294,9 @@ constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without
  *   offsets   prefix sum of the counts (packed 16-bit fields, one scan for the EG rounds)
  *   store     clean groups leave as aligned or re-aligned 32/128-bit words; the listed groups that
  *             do insert (or are partial) go byte by byte, again one lane per group
- * Called by all threads after a barrier; ends with one.
+ * Called by all threads after a barrier; the caller puts one behind it.
  */
-__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar) {
+__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar, bool store = true) {
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 zrun_in = sm.zrun[zpar];
     const u32 cap = sm.cap;
@@ -348,6 +348,11 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
         u32 tlo, thi;
         block_excl_scan_x2(lo, hi, sm.scan2, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
         const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
+        if (!store) {                                        /* counting pass (slice rewrite): nothing leaves */
+            ins_total += t0 + t1 + t2 + t3;
+            if (q0 + EPASS < n_groups) __syncthreads();
+            continue;
+        }
         /* ---- store: clean groups ---- */
         u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
 #pragma unroll 1
@@ -391,7 +396,8 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
             emit_bytes(fout, cap, chunk_byte0 + 16u * (u32)q + sm.gpre[gl], ((const uint4 *)sm.win)[q], gg >> 16, (int)((gg >> 8) & 0xFFu));
         }
         ins_total += t0 + t1 + t2 + t3;
-        __syncthreads();                                     /* list, counts and offsets are reused by the next pass */
+        if (q0 + EPASS < n_groups) __syncthreads();          /* list, counts and offsets are reused by the next pass (the caller
+                                                                 puts a barrier behind the last one) */
     }
     return ins_total - ins_in;
 }
@@ -860,6 +866,118 @@ cudaError_t read_stage_cycles(unsigned long long *h8) {
 }
 #endif
 
+/* ------------------------------------------------------- slice rewrite
+ *
+ * h264_rewrite_idr_frame / h264_rewrite_as_non_idr_i_frame (src/h264_writer.c:242-350) on the device: the NAL unit
+ *     00 00 00 01 | nal_header | EBSP( new slice header bits | source RBSP bits [start, start + n) | zero padding )
+ * i.e. copy_bits (src/h264_writer.c:228-240) over megabytes plus nal_write_unit (src/nal.c:52-84).  The byte string in
+ * front of emulation prevention is cut into chunks of one window (32 KB); a CTA builds its chunk with funnel shifts
+ * and runs the composer's emit stage on it.  Where a chunk's bytes go depends on the insertions in all chunks before
+ * it, so the work is three launches: count per chunk, exclusive scan per slice, emit.
+ */
+constexpr int RW_CHUNK_BYTES = CH * 4;
+
+__device__ __forceinline__ u32 rewrite_word(const H264GpuRewriteDesc &d, const u64 (&hdr)[4], const u32 *__restrict__ src,
+                                            u32 n_src_words, u64 a /* string bit of the word's first bit */) {
+    const u64 p0 = 40u + d.hdr_nbits, e = p0 + d.n_bits;
+    u32 v = 0u;
+    if (a < p0) {
+        v = header_bits32(hdr, d.nal_header, (u32)a);
+        if (a + 32u > p0) v &= ~(FULL >> (u32)(p0 - a));
+    }
+    if (a + 32u > p0 && a < e) {
+        u32 pv;
+        if (a >= p0) pv = pay_ld32(src, n_src_words, (u32)(d.src_start_bit + (a - p0)));
+        else pv = pay_ld32(src, n_src_words, (u32)d.src_start_bit) >> (u32)(p0 - a);
+        if (a + 32u > e) pv &= ~(FULL >> (u32)(e - a));
+        v |= pv;
+    }
+    return v;
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
+rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices, int max_chunks,
+                      const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out,
+                      u32 *__restrict__ counts /* [n_slices][max_chunks]: inserts per chunk (in), bytes inserted before it (out of the scan) */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int sl = blockIdx.x / max_chunks, c = blockIdx.x - sl * max_chunks;
+    if (sl >= n_slices) return;
+    const H264GpuRewriteDesc d = descs[sl];
+    const u64 total_bits = 40u + d.hdr_nbits + d.n_bits;
+    const u64 total_bytes = (total_bits + 7u) >> 3;
+    const u64 byte0 = (u64)c * RW_CHUNK_BYTES;
+    if (byte0 >= total_bytes) return;                        /* whole CTA */
+    const int chunk_bytes = (int)min((u64)RW_CHUNK_BYTES, total_bytes - byte0);
+    const u64 hdr[4] = {d.hdr_bits[0], d.hdr_bits[1], d.hdr_bits[2], d.hdr_bits[3]};
+    const u32 *src = (const u32 *)(src_base + d.src_off);
+    const u32 n_src_words = (u32)((d.src_bytes + 3u) >> 2);
+    /* ---- the chunk (plus the read-ahead pad of the emit stage) as MSB-first words ---- */
+    const int n_words = (chunk_bytes + 3) >> 2;
+    for (int w = tid; w < CH + 8; w += NT)
+        sm.win[w] = w < n_words ? rewrite_word(d, hdr, src, n_src_words, 8u * byte0 + 32u * (u64)w) : 0u;
+    /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47) ---- */
+    if (tid < 32) {
+        u32 run = 0;
+        if (c > 0) {
+            u64 wi = byte0 / 4u;                             /* words before the chunk, newest first, 32 at a time */
+            bool open = true;
+            while (open && wi > 0) {
+                const u64 mine = wi > (u64)tid ? wi - 1u - (u64)tid : ~0ull;
+                u32 v = 0xFFFFFFFFu;
+                if (mine != ~0ull) {
+                    v = rewrite_word(d, hdr, src, n_src_words, 32u * mine);
+                    if (mine == 1u) v |= 0xFF000000u;        /* byte 4 (the NAL header) and the start code never take part */
+                    if (mine == 0u) v = 0xFFFFFFFFu;
+                }
+                const u32 nz = __ballot_sync(FULL, v != 0u);
+                if (nz) {
+                    const int l = __ffs((int)nz) - 1;        /* nearest word that holds a non-zero byte */
+                    const u32 vv = __shfl_sync(FULL, v, l);
+                    run += 4u * (u32)l + ((vv & 0xFFu) ? 0u : (vv & 0xFF00u) ? 1u : (vv & 0xFF0000u) ? 2u : 3u);
+                    open = false;
+                } else { run += 128u; wi = wi > 32u ? wi - 32u : 0u; }
+            }
+        }
+        if (tid == 0) {
+            sm.zrun[0] = run; sm.zrun[1] = 0; sm.n_list = 0;
+            sm.cap = d.out_cap; sm.fout = out + d.out_off;
+        }
+    }
+    __syncthreads();
+    u32 *cnt = counts + (size_t)sl * max_chunks + c;
+    const u32 before = STORE ? *cnt : 0u;
+    const u32 ins = emit_window(sm, (u32)byte0, chunk_bytes, before, 0u, STORE);
+    if (!STORE && tid == 0) *cnt = ins;
+}
+
+/* per slice: counts -> bytes inserted before each chunk; sizes[slice] = bytes of the whole NAL unit */
+__global__ void __launch_bounds__(32)
+rewrite_scan_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices, int max_chunks,
+                    u32 *__restrict__ counts, u32 *__restrict__ sizes) {
+    const int sl = blockIdx.x, lane = threadIdx.x;
+    if (sl >= n_slices) return;
+    const u64 total_bytes = (40u + descs[sl].hdr_nbits + descs[sl].n_bits + 7u) >> 3;
+    const int n_chunks = (int)((total_bytes + RW_CHUNK_BYTES - 1) / RW_CHUNK_BYTES);
+    u32 *cnt = counts + (size_t)sl * max_chunks;
+    u32 run = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+        const int c = c0 + lane;
+        const u32 v = c < n_chunks ? cnt[c] : 0u;
+        u32 inc = v;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const u32 t = __shfl_up_sync(FULL, inc, dd);
+            if (lane >= dd) inc += t;
+        }
+        if (c < n_chunks) cnt[c] = run + inc - v;
+        run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) sizes[sl] = (u32)total_bytes + run;
+}
+
 /* ------------------------------------------------------------ rasteriser */
 
 constexpr int RASTER_THREADS = 256;
@@ -1009,6 +1127,26 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
     compose_frames_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
     return cudaGetLastError();
 }
+
+cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks, const uint8_t *d_src,
+                           uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, cudaStream_t stream) {
+    if (n_slices <= 0 || max_chunks <= 0) return cudaSuccess;
+    static bool ready = false;
+    const int smem = (int)sizeof(ComposeSmem);
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(rewrite_slices_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(rewrite_slices_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        ready = true;
+    }
+    const unsigned grid = (unsigned)n_slices * (unsigned)max_chunks;
+    rewrite_slices_kernel<false><<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_counts);
+    rewrite_scan_kernel<<<n_slices, 32, 0, stream>>>(d_desc, n_slices, max_chunks, d_counts, d_sizes);
+    rewrite_slices_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_counts);
+    return cudaGetLastError();
+}
+
+int rewrite_chunk_bytes() { return RW_CHUNK_BYTES; }
 
 cudaError_t launch_canonicalize(H264GpuMbHint *d_hints, size_t n_hints, cudaStream_t stream) {
     if (n_hints == 0) return cudaSuccess;

@@ -34,6 +34,10 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
 
 cudaError_t launch_canonicalize(H264GpuMbHint *d_hints, size_t n_hints, cudaStream_t stream);
 
+cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks, const uint8_t *d_src,
+                           uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, cudaStream_t stream);
+int rewrite_chunk_bytes();
+
 cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs,
                           const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
                           H264GpuMbHint *d_hints, cudaStream_t stream);

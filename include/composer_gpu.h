@@ -196,6 +196,37 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
                          const uint8_t *h_payload, size_t payload_bytes,
                          uint8_t *h_out, size_t out_bytes, uint32_t *h_sizes);
 
+/* ---- slice rewrite (the reference's I-frame path) -------------------------
+ *
+ * h264_rewrite_idr_frame / h264_rewrite_as_non_idr_i_frame (src/h264_writer.c:242-350) for whole batches: every
+ * slice becomes   00 00 00 01 | nal_header | EBSP(hdr_bits | source RBSP bits [src_start_bit, +n_bits) | zero pad),
+ * which is copy_bits (src/h264_writer.c:228-240) + nal_write_unit (src/nal.c:52-84).  The host parses the source
+ * slice header and writes the new one (as for P slices); the device moves the megabytes.
+ */
+typedef struct {
+    uint64_t hdr_bits[4];   /* new slice header, MSB first (as in H264GpuFrameDesc)            */
+    uint64_t src_off;       /* byte offset of the source RBSP in d_src (multiple of 4)        */
+    uint64_t src_bytes;     /* its size; 8 more bytes must be readable behind it              */
+    uint64_t src_start_bit; /* first source bit to copy (mb data start of the parsed header)  */
+    uint64_t n_bits;        /* bits to copy (src_bytes * 8 - src_start_bit in the reference)  */
+    uint64_t out_off;       /* byte offset of the output slot (16-aligned)                    */
+    uint32_t out_cap;       /* slot capacity in bytes (multiple of 16)                        */
+    uint16_t hdr_nbits;     /* <= H264GPU_MAX_HDR_BITS                                        */
+    uint8_t  nal_header;    /* (nal_ref_idc << 5) | nal_unit_type                             */
+    uint8_t  reserved;
+} H264GpuRewriteDesc;       /* 80 bytes */
+
+/* bytes of the pre-emulation-prevention string one CTA handles; a slice of B string bytes needs ceil(B / this) chunks */
+int h264gpu_rewrite_chunk_bytes(void);
+
+/*
+ * All pointers are DEVICE pointers.  max_chunks >= chunks of the largest slice; d_counts = scratch of
+ * n_slices * max_chunks uint32.  d_sizes[i] = bytes the NAL unit needs (> out_cap: overflowed, out_cap bytes stored).
+ * Asynchronous on `stream`.
+ */
+int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,
+                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, void *stream);
+
 /* Count of kernels this library has launched since init (for bench accounting). */
 uint64_t h264gpu_launch_count(void);
 
