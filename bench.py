@@ -403,6 +403,111 @@ def main_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------ second workload: slice rewrite
+
+def main_rewrite(args):
+    """batched I-slice rewrite (new header + bit-shifted copy + emulation prevention).  Not the
+    north-star metric: `python bench.py --workload rewrite` prints its own line (bytes of source RBSP rewritten per s)."""
+    ge.load_package()
+    from h264_scroll_encoder_b200 import binding, abi
+    gc = binding.GpuComposer(0)
+    L = gc.lib
+    n, S = args.slices, args.slice_bytes
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, n * S, dtype=np.uint8)
+    src[rng.integers(0, len(src), len(src) // 64)] = 0
+    idx = rng.integers(0, len(src) - 1, len(src) // 256)
+    src[idx] = 0; src[idx + 1] = 0
+    hdr = "1000100010000" + "1" + "011" + "010"
+    cap = (S * 3 // 2 + 256 + 15) & ~15
+    desc = np.zeros(n, abi.REWRITE_DESC)
+    desc["hdr_bits"] = abi.hdr_words(hdr)
+    desc["src_off"] = np.arange(n, dtype=np.uint64) * np.uint64(S)
+    desc["src_bytes"], desc["src_start_bit"], desc["n_bits"] = S, 23, 8 * S - 23
+    desc["out_off"] = np.arange(n, dtype=np.uint64) * np.uint64(cap)
+    desc["out_cap"], desc["hdr_nbits"], desc["nal_header"] = cap, len(hdr), 0x65
+    cb = int(L.h264gpu_rewrite_chunk_bytes())
+    max_chunks = (S + 64 + cb - 1) // cb
+    d_desc, d_src = gc.to_device(desc), gc.to_device(np.concatenate([src, np.zeros(16, np.uint8)]))
+    d_out, d_sizes, d_cnt = gc.alloc(cap * n), gc.alloc(4 * n), gc.alloc(4 * n * max_chunks)
+    ev0, ev1 = L.h264gpu_event_create(), L.h264gpu_event_create()
+
+    def step():
+        gc.check(L.h264gpu_rewrite_slices(d_desc.ptr, n, max_chunks, d_src.ptr, d_out.ptr, d_sizes.ptr, d_cnt.ptr, None))
+    for _ in range(max(args.warmup, 3)):
+        step()
+    gc.sync()
+    l0 = gc.launch_count()
+    gc.check(L.h264gpu_event_record(ev0, None))
+    for _ in range(args.steps):
+        step()
+    gc.check(L.h264gpu_event_record(ev1, None))
+    ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / args.steps
+    launches = gc.launch_count() - l0
+    sizes = d_sizes.download(np.uint32)
+    assert (sizes <= cap).all()
+    out_bytes = int(sizes.sum())
+    # end to end: pinned source up, NAL units back
+    p_src = L.h264gpu_host_alloc(len(src)); np.ctypeslib.as_array((ctypes.c_uint8 * len(src)).from_address(p_src))[:] = src
+    p_out = L.h264gpu_host_alloc(cap * n)
+    def e2e():
+        gc.check(L.h264gpu_memcpy_h2d(d_src.ptr, p_src, len(src), None))
+        step()
+        gc.check(L.h264gpu_memcpy_d2h(p_out, d_out.ptr, cap * n, None))
+        gc.sync()
+    e2e(); t0 = time.perf_counter()
+    for _ in range(3):
+        e2e()
+    e2e_s = (time.perf_counter() - t0) / 3
+    peak, peak_kind = peaks()
+    achieved = (n * S + out_bytes) / (ms * 1e-3) / 1e9
+    line = {"metric": "rewritten_rbsp_bytes_per_second", "value": n * S / (ms * 1e-3), "unit": "B/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "gpu_launches": int(launches),
+            "config": {"workload": "slice rewrite (h264_rewrite_idr_frame on the device): %d I slices of %d bytes per step "
+                                   "(1280x720 I_PCM atlas size), %.0f MB in + %.0f MB out vs 126 MB L2"
+                                   % (n, S, n * S / 1e6, out_bytes / 1e6)},
+            "e2e": {"value": n * S / e2e_s, "unit": "B/s", "h2d_bytes_per_step": int(len(src)), "d2h_bytes_per_step": int(cap * n),
+                    "ms_per_step": 1e3 * e2e_s},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "rewrite_slices_kernel (count + emit passes)",
+                         "algorithmic_bytes_per_launch": int(n * S + out_bytes),
+                         "note": "the source is read twice (count pass, emit pass): traffic is 1.5x the algorithmic bytes"}}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_rewrite_baseline(src[:S].copy(), S)
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_rewrite_baseline(rbsp, S):
+    """The reference's own h264_rewrite_idr_frame (oracle/_ref/libref_composer.so) on one host core; falls back to this
+    library's host C implementation when the reference build is absent."""
+    from h264_scroll_encoder_b200 import binding
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_composer.so")
+    kind = "reference"
+    if os.path.exists(path):
+        R = ctypes.CDLL(path)
+    else:
+        R, kind = binding.load_library(), "port"
+    cfg, pcfg, nw = binding.ComposerConfig(), binding.ComposerConfig(), binding.NALWriter()
+    R.composer_config_init(ctypes.byref(cfg), 1280, 720); R.composer_config_init(ctypes.byref(pcfg), 1280, 720)
+    hdr = "1" + "0001000" + "1" + "0000" + "1" + "0" + "0" + "1" + ("010" if cfg.deblocking_filter_control_present_flag else "")
+    bits = np.concatenate([np.array([int(c) for c in hdr], np.uint8), np.unpackbits(rbsp)])[:8 * S]
+    rb = np.packbits(bits)
+    out, tmp = np.zeros(2 * S + 64, np.uint8), np.zeros(2 * S + 64, np.uint8)
+    R.h264_rewrite_idr_frame.restype = ctypes.c_size_t
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 5.0:
+        R.nal_writer_init(ctypes.byref(nw), ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(out.size),
+                          ctypes.c_void_p(tmp.ctypes.data), ctypes.c_size_t(tmp.size))
+        assert R.h264_rewrite_idr_frame(ctypes.byref(nw), ctypes.byref(cfg), ctypes.byref(pcfg), ctypes.c_void_p(rb.ctypes.data),
+                                        ctypes.c_size_t(len(rb))) > 0
+        reps += 1
+    wall = time.perf_counter() - t0
+    return {"value": reps * S / wall, "unit": "B/s", "cores": 1, "kind": kind,
+            "sample": "%d calls of h264_rewrite_idr_frame on one %d-byte slice, %.1f s wall" % (reps, S, wall)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,11 +517,17 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="compose", choices=["compose", "rewrite"],
+                    help="compose = the north-star metric (default); rewrite = batched I-slice rewrite (SURVEY 8f)")
+    ap.add_argument("--slices", type=int, default=128)
+    ap.add_argument("--slice-bytes", type=int, default=1382400)
     ap.add_argument("--e2e-zero-copy", action="store_true",
                     help="end-to-end path whose pack kernel writes into pinned host memory instead of a separate D2H copy")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="frame chunks the end-to-end path pipelines over streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload == "rewrite":
+        return main_rewrite(args)
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)
