@@ -177,7 +177,7 @@ class GpuComposer:
         max_chunks = max(1, int(((total + cb - 1) // cb).max())) if n else 1
         d_desc = self.to_device(desc)
         d_src = self.to_device(np.concatenate([src, np.zeros(16, np.uint8)]))
-        d_out, d_sizes, d_cnt = self.alloc(out_bytes), self.alloc(4 * max(n, 1)), self.alloc(4 * max(n, 1) * max_chunks)
+        d_out, d_sizes, d_cnt = self.alloc(out_bytes), self.alloc(4 * max(n, 1)), self.alloc(4 * (1 + max(n, 1) * max_chunks))
         self.check(self.lib.h264gpu_memset(d_out.ptr, 0xAA, out_bytes, None))
         self.check(self.lib.h264gpu_rewrite_slices(d_desc.ptr, n, max_chunks, d_src.ptr, d_out.ptr, d_sizes.ptr, d_cnt.ptr, None))
         self.sync()

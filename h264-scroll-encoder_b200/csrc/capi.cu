@@ -185,7 +185,7 @@ int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int m
     if (n_slices < 0 || max_chunks < 0 || !d_desc || !d_src || !d_out || !d_sizes || !d_counts) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_rewrite(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_counts, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "rewrite launch", e);
-    if (n_slices > 0 && max_chunks > 0) g_launches.fetch_add(3);
+    if (n_slices > 0 && max_chunks > 0) g_launches.fetch_add(1);
     return H264GPU_OK;
 }
 

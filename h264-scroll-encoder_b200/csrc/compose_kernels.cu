@@ -296,7 +296,26 @@ constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without
  *             do insert (or are partial) go byte by byte, again one lane per group
  * Called by all threads after a barrier; the caller puts one behind it.
  */
-__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar, bool store = true) {
+/* decoupled look-back over the chunks of one slice (slice rewrite): state word = flag << 30 | count; flag 1 = the
+   chunk's own insertions, 2 = inclusive sum over the slice so far.  Returns the insertions before chunk c. */
+__device__ __forceinline__ u32 chunk_lookback(volatile u32 *state, int c, u32 mine) {
+    if (c == 0) { state[0] = (2u << 30) | mine; return 0u; }
+    state[c] = (1u << 30) | mine;
+    __threadfence();
+    u32 sum = 0;
+    for (int p = c - 1;; ) {
+        const u32 v = state[p];
+        if ((v >> 30) == 0u) continue;                       /* not published yet: the chunk is running (tickets are taken in order) */
+        sum += v & 0x3FFFFFFFu;
+        if ((v >> 30) == 2u || p == 0) break;
+        p--;
+    }
+    state[c] = (2u << 30) | (sum + mine);
+    return sum;
+}
+
+__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar,
+                                        volatile u32 *lookback = nullptr, int lookback_c = 0) {
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 zrun_in = sm.zrun[zpar];
     const u32 cap = sm.cap;
@@ -306,7 +325,9 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
     const int n_groups = (chunk_bytes + 15) >> 4;
     for (int q0 = 0; q0 < n_groups; q0 += EPASS) {
         /* even with an insertion after every second byte the pass stays clear of the slot's end */
-        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) + ins_total + 4u <= cap;
+        /* (slice rewrite: the insertions before the chunk are not known yet - at most one per two bytes) */
+        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) +
+                           (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
         /* ---- classify ---- */
 #pragma unroll 1                                             /* (code size matters more than the loop overhead) */
         for (int r = 0; r < EG; r++) {
@@ -348,10 +369,12 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
         u32 tlo, thi;
         block_excl_scan_x2(lo, hi, sm.scan2, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
         const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
-        if (!store) {                                        /* counting pass (slice rewrite): nothing leaves */
-            ins_total += t0 + t1 + t2 + t3;
-            if (q0 + EPASS < n_groups) __syncthreads();
-            continue;
+        if (lookback) {
+            /* slice rewrite: where this chunk's bytes go depends on the insertions of the chunks before it (single pass
+               per chunk: EPASS groups).  One thread looks back, everybody picks the result up from shared memory */
+            if (tid == 0) sm.scan2[NW].x = chunk_lookback(lookback, lookback_c, t0 + t1 + t2 + t3);
+            __syncthreads();
+            ins_total = sm.scan2[NW].x;
         }
         /* ---- store: clean groups ---- */
         u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
@@ -895,15 +918,21 @@ __device__ __forceinline__ u32 rewrite_word(const H264GpuRewriteDesc &d, const u
     return v;
 }
 
-template <bool STORE>
+static_assert(RW_CHUNK_BYTES / 16 <= EPASS, "a chunk must be one emit pass (the look-back sits inside the pass)");
+
 __global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
 rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices, int max_chunks,
-                      const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out,
-                      u32 *__restrict__ counts /* [n_slices][max_chunks]: inserts per chunk (in), bytes inserted before it (out of the scan) */) {
+                      const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out, u32 *__restrict__ sizes,
+                      u32 *__restrict__ state /* [1 + n_slices * max_chunks], zeroed: ticket counter, then the look-back words */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    const int sl = blockIdx.x / max_chunks, c = blockIdx.x - sl * max_chunks;
+    /* chunks are handed out in launch order: whoever holds ticket k knows that every chunk below k is running or done */
+    if (tid == 0) sm.n_list = atomicAdd(state, 1u);
+    __syncthreads();
+    const int ticket = (int)sm.n_list;
+    __syncthreads();
+    const int sl = ticket / max_chunks, c = ticket - sl * max_chunks;
     if (sl >= n_slices) return;
     const H264GpuRewriteDesc d = descs[sl];
     const u64 total_bits = 40u + d.hdr_nbits + d.n_bits;
@@ -947,35 +976,10 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
         }
     }
     __syncthreads();
-    u32 *cnt = counts + (size_t)sl * max_chunks + c;
-    const u32 before = STORE ? *cnt : 0u;
-    const u32 ins = emit_window(sm, (u32)byte0, chunk_bytes, before, 0u, STORE);
-    if (!STORE && tid == 0) *cnt = ins;
-}
-
-/* per slice: counts -> bytes inserted before each chunk; sizes[slice] = bytes of the whole NAL unit */
-__global__ void __launch_bounds__(32)
-rewrite_scan_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices, int max_chunks,
-                    u32 *__restrict__ counts, u32 *__restrict__ sizes) {
-    const int sl = blockIdx.x, lane = threadIdx.x;
-    if (sl >= n_slices) return;
-    const u64 total_bytes = (40u + descs[sl].hdr_nbits + descs[sl].n_bits + 7u) >> 3;
-    const int n_chunks = (int)((total_bytes + RW_CHUNK_BYTES - 1) / RW_CHUNK_BYTES);
-    u32 *cnt = counts + (size_t)sl * max_chunks;
-    u32 run = 0;
-    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
-        const int c = c0 + lane;
-        const u32 v = c < n_chunks ? cnt[c] : 0u;
-        u32 inc = v;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            const u32 t = __shfl_up_sync(FULL, inc, dd);
-            if (lane >= dd) inc += t;
-        }
-        if (c < n_chunks) cnt[c] = run + inc - v;
-        run += __shfl_sync(FULL, inc, 31);
-    }
-    if (lane == 0) sizes[sl] = (u32)total_bytes + run;
+    volatile u32 *st = state + 1 + (size_t)sl * max_chunks;
+    /* (with a look-back the emit stage returns the insertions up to and including this chunk) */
+    const u32 ins_incl = emit_window(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
+    if (tid == 0 && byte0 + (u64)chunk_bytes >= total_bytes) sizes[sl] = (u32)total_bytes + ins_incl;   /* the slice's last chunk */
 }
 
 /* ------------------------------------------------------------ rasteriser */
@@ -1129,20 +1133,19 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
 }
 
 cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks, const uint8_t *d_src,
-                           uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, cudaStream_t stream) {
+                           uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream) {
     if (n_slices <= 0 || max_chunks <= 0) return cudaSuccess;
     static bool ready = false;
     const int smem = (int)sizeof(ComposeSmem);
     if (!ready) {
-        cudaError_t e = cudaFuncSetAttribute(rewrite_slices_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(rewrite_slices_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(rewrite_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         ready = true;
     }
     const unsigned grid = (unsigned)n_slices * (unsigned)max_chunks;
-    rewrite_slices_kernel<false><<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_counts);
-    rewrite_scan_kernel<<<n_slices, 32, 0, stream>>>(d_desc, n_slices, max_chunks, d_counts, d_sizes);
-    rewrite_slices_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_counts);
+    cudaError_t e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);   /* ticket + look-back words */
+    if (e != cudaSuccess) return e;
+    rewrite_slices_kernel<<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_state);
     return cudaGetLastError();
 }
 

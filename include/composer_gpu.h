@@ -220,12 +220,12 @@ typedef struct {
 int h264gpu_rewrite_chunk_bytes(void);
 
 /*
- * All pointers are DEVICE pointers.  max_chunks >= chunks of the largest slice; d_counts = scratch of
- * n_slices * max_chunks uint32.  d_sizes[i] = bytes the NAL unit needs (> out_cap: overflowed, out_cap bytes stored).
- * Asynchronous on `stream`.
+ * All pointers are DEVICE pointers.  max_chunks >= chunks of the largest slice; d_scratch = 1 + n_slices * max_chunks
+ * uint32 (chunk tickets and the look-back words that carry the insertion counts from chunk to chunk; zeroed by the
+ * call).  d_sizes[i] = bytes the NAL unit needs (> out_cap: overflowed, out_cap bytes stored).  Asynchronous on `stream`.
  */
 int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,
-                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, void *stream);
+                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream);
 
 /* Count of kernels this library has launched since init (for bench accounting). */
 uint64_t h264gpu_launch_count(void);
