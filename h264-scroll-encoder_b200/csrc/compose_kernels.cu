@@ -943,10 +943,50 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
     const u64 hdr[4] = {d.hdr_bits[0], d.hdr_bits[1], d.hdr_bits[2], d.hdr_bits[3]};
     const u32 *src = (const u32 *)(src_base + d.src_off);
     const u32 n_src_words = (u32)((d.src_bytes + 3u) >> 2);
-    /* ---- the chunk (plus the read-ahead pad of the emit stage) as MSB-first words ---- */
+    /* ---- the chunk (plus the read-ahead pad of the emit stage) as MSB-first words ----
+       The source words the chunk needs are copied to shared memory first (16-byte cp.async, everything in flight at
+       once: the hint tile buffer is free in this kernel); a word that lies wholly in the copied macroblock data is then
+       one funnel shift of two staged words with the same shift for the whole chunk.  Words that touch the header or
+       the end of the data go the general way. */
     const int n_words = (chunk_bytes + 3) >> 2;
-    for (int w = tid; w < CH + 8; w += NT)
-        sm.win[w] = w < n_words ? rewrite_word(d, hdr, src, n_src_words, 8u * byte0 + 32u * (u64)w) : 0u;
+    const u64 p0 = 40u + d.hdr_nbits, e_bit = p0 + d.n_bits, a0 = 8u * byte0;
+    const u64 a_lo = a0 > p0 ? a0 : p0;                      /* first string bit of the chunk that is macroblock data */
+    u32 *stage = (u32 *)sm.hbuf;
+    constexpr int STAGE_WORDS = HBS * 16;
+    static_assert(STAGE_WORDS >= CH + 16, "the hint tile buffer must hold a chunk of source words");
+    const u64 sbit_lo = d.src_start_bit + (a_lo - p0);       /* source bit of string bit a_lo */
+    const u64 src_w_lo = sbit_lo >> 5;                       /* first source word needed */
+    const uintptr_t g_addr = ((uintptr_t)(src + src_w_lo)) & ~(uintptr_t)15;          /* 16-byte aligned start of the copy */
+    const u32 w_skip = (u32)(((uintptr_t)(src + src_w_lo) - g_addr) >> 2);             /* staged words in front of src_w_lo */
+    const bool any_data = a_lo < e_bit && a_lo < a0 + 32u * (u64)n_words;
+    if (any_data) {
+        const uintptr_t g_end = (uintptr_t)src + (((uintptr_t)d.src_bytes + 3u) & ~(uintptr_t)3) + 16u;   /* readable bytes end here */
+        const u32 s_base = smem_u32(stage);
+        for (int c16 = tid; c16 < (CH + 16) / 4; c16 += NT) {
+            const uintptr_t g = g_addr + 16u * (uintptr_t)c16;
+            if (g + 16u <= g_end) cp_async16(s_base + 16u * (u32)c16, (const void *)g);
+            else ((uint4 *)stage)[c16] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    {
+        /* string bit a (>= p0) is source bit src_start_bit + a - p0: the word index moves with w, the shift does not.
+           Words [w_first, w_last) of the chunk lie wholly inside the copied data */
+        const int w_first = a0 >= p0 ? 0 : (int)((p0 - a0 + 31u) >> 5);
+        const int w_last = e_bit <= a0 ? 0 : (int)min((u64)n_words, (e_bit - a0) >> 5);
+        const u64 sb_first = d.src_start_bit + (a0 + 32u * (u64)w_first - p0);       /* (only meaningful when w_first < w_last) */
+        const int sh = (int)(sb_first & 31u);
+        const int k_off = (int)((sb_first >> 5) - src_w_lo) + (int)w_skip - w_first;  /* staged word of chunk word w: w + k_off */
+        for (int w = tid; w < CH + 8; w += NT) {
+            u32 v = 0u;
+            if (w >= w_first && w < w_last)
+                v = fshl(__byte_perm(stage[w + k_off], 0u, 0x0123u), __byte_perm(stage[w + k_off + 1], 0u, 0x0123u), sh);
+            else if (w < n_words) v = rewrite_word(d, hdr, src, n_src_words, a0 + 32u * (u64)w);
+            sm.win[w] = v;
+        }
+    }
     /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47) ---- */
     if (tid < 32) {
         u32 run = 0;

@@ -206,7 +206,7 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
 typedef struct {
     uint64_t hdr_bits[4];   /* new slice header, MSB first (as in H264GpuFrameDesc)            */
     uint64_t src_off;       /* byte offset of the source RBSP in d_src (multiple of 4)        */
-    uint64_t src_bytes;     /* its size; 8 more bytes must be readable behind it              */
+    uint64_t src_bytes;     /* its size; 16 more bytes must be readable behind it (d_src 16-aligned) */
     uint64_t src_start_bit; /* first source bit to copy (mb data start of the parsed header)  */
     uint64_t n_bits;        /* bits to copy (src_bytes * 8 - src_start_bit in the reference)  */
     uint64_t out_off;       /* byte offset of the output slot (16-aligned)                    */
