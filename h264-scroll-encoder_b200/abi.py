@@ -21,7 +21,9 @@ REWRITE_DESC = np.dtype([("hdr_bits", "<u8", (4,)), ("src_off", "<u8"), ("src_by
                          ("n_bits", "<u8"), ("out_off", "<u8"), ("out_cap", "<u4"), ("hdr_nbits", "<u2"),
                          ("nal_header", "u1"), ("reserved", "u1")])
 
-assert REWRITE_DESC.itemsize == 80
+UNESCAPE_DESC = np.dtype([("src_off", "<u8"), ("src_bytes", "<u8"), ("out_off", "<u8"), ("out_cap", "<u4"), ("reserved", "<u4")])
+
+assert REWRITE_DESC.itemsize == 80 and UNESCAPE_DESC.itemsize == 32
 assert HINT.itemsize == 8 and FRAME_DESC.itemsize == 64 and DYN_DESC.itemsize == 32
 assert REGION.itemsize == 16 and RASTER_DESC.itemsize == 24
 

@@ -18,7 +18,7 @@ GPU_SYMBOLS = [
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
     "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
     "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
-    "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes"]
+    "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes", "h264gpu_unescape_nals", "h264gpu_unescape_chunk_bytes"]
 REFERENCE_API_SYMBOLS = [
     # include/composer.h
     "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
@@ -70,6 +70,7 @@ def load_library(path=None):
     L.h264gpu_pack_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.h264gpu_canonicalize_hints.argtypes = [vp, sz, vp]
     L.h264gpu_rewrite_slices.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+    L.h264gpu_unescape_nals.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
     L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
     L.h264gpu_launch_count.restype = C.c_uint64
     return L
@@ -187,6 +188,33 @@ class GpuComposer:
         for b_ in (d_desc, d_src, d_out, d_sizes, d_cnt):
             b_.free()
         return res, sizes
+
+    def unescape_nals(self, payloads):
+        """Host convenience around h264gpu_unescape_nals: list of uint8 EBSP payloads -> list of RBSP arrays."""
+        from . import abi
+        n = len(payloads)
+        desc = np.zeros(n, abi.UNESCAPE_DESC)
+        off, parts = 0, []
+        for i, p in enumerate(payloads):
+            cap = (len(p) + 15) & ~15
+            desc[i]["src_off"], desc[i]["src_bytes"], desc[i]["out_off"], desc[i]["out_cap"] = off, len(p), off, max(cap, 16)
+            parts.append(np.concatenate([p, np.zeros(max(cap, 16) - len(p), np.uint8)]))
+            off += max(cap, 16)
+        cb = int(self.lib.h264gpu_unescape_chunk_bytes())
+        max_chunks = max(1, max((len(p) + cb - 1) // cb for p in payloads)) if n else 1
+        d_desc = self.to_device(desc)
+        d_src = self.to_device(np.concatenate(parts + [np.zeros(32, np.uint8)]))
+        d_out, d_sizes, d_st = self.alloc(off + 32), self.alloc(4 * max(n, 1)), self.alloc(4 * (1 + max(n, 1) * max_chunks))
+        self.check(self.lib.h264gpu_memset(d_out.ptr, 0xAA, off + 32, None))
+        self.check(self.lib.h264gpu_memset(d_sizes.ptr, 0, 4 * max(n, 1), None))
+        self.check(self.lib.h264gpu_unescape_nals(d_desc.ptr, n, max_chunks, d_src.ptr, d_out.ptr, d_sizes.ptr, d_st.ptr, None))
+        self.sync()
+        sizes = d_sizes.download(np.uint32, count=n)
+        out = d_out.download(np.uint8)
+        res = [out[int(d["out_off"]):int(d["out_off"]) + int(s)].copy() for d, s in zip(desc, sizes)]
+        for b_ in (d_desc, d_src, d_out, d_sizes, d_st):
+            b_.free()
+        return res
 
     def pack_frames(self, d_desc, d_sizes, n, d_slots, d_packed, d_offsets, stream=None):
         self.check(self.lib.h264gpu_pack_frames(d_desc.ptr, d_sizes.ptr, n, d_slots.ptr, d_packed.ptr,

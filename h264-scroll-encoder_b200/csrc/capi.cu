@@ -177,6 +177,18 @@ int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *str
     return H264GPU_OK;
 }
 
+int h264gpu_unescape_chunk_bytes(void) { return h264scroll::unescape_chunk_bytes(); }
+
+int h264gpu_unescape_nals(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks,
+                          const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream) {
+    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    if (n_nals < 0 || max_chunks < 0 || !d_desc || !d_src || !d_out || !d_sizes || !d_scratch) return fail(H264GPU_ERR_ARG, "null argument");
+    cudaError_t e = h264scroll::launch_unescape(d_desc, n_nals, max_chunks, d_src, d_out, d_sizes, d_scratch, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "unescape launch", e);
+    if (n_nals > 0 && max_chunks > 0) g_launches.fetch_add(1);
+    return H264GPU_OK;
+}
+
 int h264gpu_rewrite_chunk_bytes(void) { return h264scroll::rewrite_chunk_bytes(); }
 
 int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,

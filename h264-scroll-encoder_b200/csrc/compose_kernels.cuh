@@ -38,6 +38,10 @@ cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int m
                            uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, cudaStream_t stream);
 int rewrite_chunk_bytes();
 
+cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks, const uint8_t *d_src,
+                            uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream);
+int unescape_chunk_bytes();
+
 cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs,
                           const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
                           H264GpuMbHint *d_hints, cudaStream_t stream);

@@ -1,0 +1,221 @@
+/*
+ * unescape_kernels.cu - the input side of the splice on the device: EBSP -> RBSP for whole batches of NAL payloads
+ * (ebsp_to_rbsp, src/nal_parser.c:67-88).
+ *
+ * The reference walks the payload with a zero counter and drops a byte iff
+ *     zero_count >= 2  &&  byte == 0x03  &&  there is a next byte and it is <= 0x03,
+ * resetting the counter at every non-zero byte (dropped or not).  Since the dropped byte itself is non-zero, the rule is
+ * local: byte i goes iff b[i] == 3, b[i-1] == b[i-2] == 0 and b[i+1] <= 3 exists.  So: per 16-byte group a removal mask
+ * from byte masks, a block prefix sum of the counts, a decoupled look-back over the 32 KB chunks of a payload for the
+ * bytes removed before the chunk, and a compacting store (groups without removals leave as re-aligned words).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "composer_gpu.h"
+#include "compose_kernels.cuh"
+
+namespace h264scroll {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace {
+
+constexpr int UT = 512;                  /* threads per CTA */
+constexpr int UG = 4;                    /* 16-byte groups per thread */
+constexpr int UCHUNK = UT * UG * 16;     /* payload bytes per CTA (32 KB) */
+constexpr int UW = UT / 32;
+constexpr u32 UFULL = 0xFFFFFFFFu;
+
+struct __align__(16) UnescapeSmem {
+    uint4 halo_lo;                       /* the 16 bytes in front of the chunk (zero at the payload's start) */
+    uint4 data[UT * UG];                 /* the chunk */
+    uint4 halo_hi;                       /* the 16 bytes behind it */
+    u32 gi[UT * UG];                     /* per group: removal mask << 8 | removed bytes */
+    uint2 scan[UW + 1];
+    u32 ticket;
+    u32 base;
+};
+
+__device__ __forceinline__ u32 zero_bytes(u32 v) { return ~((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) | 0x7F7F7F7Fu); }
+/* 4-bit mask of the marked bytes (0x80 per byte) of a word loaded as it lies in memory: bit k = memory byte k */
+__device__ __forceinline__ u32 nib_le(u32 m) { return (((m >> 7) & 0x01010101u) * 0x10204080u) >> 28; }
+__device__ __forceinline__ u32 mask16(uint4 w, u32 x, u32 keep) {
+    return nib_le(zero_bytes((w.x & keep) ^ x)) | (nib_le(zero_bytes((w.y & keep) ^ x)) << 4) |
+           (nib_le(zero_bytes((w.z & keep) ^ x)) << 8) | (nib_le(zero_bytes((w.w & keep) ^ x)) << 12);
+}
+
+__device__ __forceinline__ void scan_x2(u32 &lo, u32 &hi, uint2 *s_scan, u32 &tot_lo, u32 &tot_hi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 il = lo, ih = hi;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 a = __shfl_up_sync(UFULL, il, d), b = __shfl_up_sync(UFULL, ih, d);
+        if (lane >= d) { il += a; ih += b; }
+    }
+    if (lane == 31) s_scan[warp] = make_uint2(il, ih);
+    __syncthreads();
+    const uint2 ws = lane < UW ? s_scan[lane] : make_uint2(0u, 0u);
+    u32 wl = ws.x, wh = ws.y;
+#pragma unroll
+    for (int d = 1; d < UW; d <<= 1) {
+        const u32 a = __shfl_up_sync(UFULL, wl, d), b = __shfl_up_sync(UFULL, wh, d);
+        if (lane >= d) { wl += a; wh += b; }
+    }
+    const u32 el = __shfl_sync(UFULL, wl - ws.x, warp), eh = __shfl_sync(UFULL, wh - ws.y, warp);
+    tot_lo = __shfl_sync(UFULL, wl, UW - 1);
+    tot_hi = __shfl_sync(UFULL, wh, UW - 1);
+    lo = el + il - lo;
+    hi = eh + ih - hi;
+}
+
+/* decoupled look-back over the chunks of one payload: word = flag << 30 | count (1: own count, 2: inclusive sum) */
+__device__ __forceinline__ u32 lookback(volatile u32 *state, int c, u32 mine) {
+    if (c == 0) { state[0] = (2u << 30) | mine; return 0u; }
+    state[c] = (1u << 30) | mine;
+    __threadfence();
+    u32 sum = 0;
+    for (int p = c - 1;;) {
+        const u32 v = state[p];
+        if ((v >> 30) == 0u) continue;
+        sum += v & 0x3FFFFFFFu;
+        if ((v >> 30) == 2u || p == 0) break;
+        p--;
+    }
+    state[c] = (2u << 30) | (sum + mine);
+    return sum;
+}
+
+__global__ void __launch_bounds__(UT, 2)
+unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int max_chunks,
+                const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out, u32 *__restrict__ sizes,
+                u32 *__restrict__ state /* [1 + n_nals * max_chunks], zeroed */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UnescapeSmem &sm = *reinterpret_cast<UnescapeSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) sm.ticket = atomicAdd(state, 1u);          /* chunks in launch order: everything below a ticket is running or done */
+    __syncthreads();
+    const int ticket = (int)sm.ticket;
+    const int nal = ticket / max_chunks, c = ticket - nal * max_chunks;
+    if (nal >= n_nals) return;
+    const H264GpuUnescapeDesc d = descs[nal];
+    const u64 byte0 = (u64)c * UCHUNK;
+    if (byte0 >= d.src_bytes) return;
+    const int chunk_bytes = (int)min((u64)UCHUNK, d.src_bytes - byte0);
+    const uint8_t *src = src_base + d.src_off + byte0;       /* 16-byte aligned */
+    uint8_t *dst = out + d.out_off;
+    /* ---- stage the chunk and 16 bytes either side ---- */
+    {
+        const u32 s_data = (u32)__cvta_generic_to_shared(sm.data);
+        const int n16 = (chunk_bytes + 15) >> 4;             /* the last 16 bytes may reach past the payload: readable by contract */
+        for (int i = tid; i < UT * UG; i += UT) {
+            if (i < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_data + 16u * (u32)i), "l"(src + 16 * (size_t)i) : "memory");
+            else sm.data[i] = make_uint4(UFULL, UFULL, UFULL, UFULL);
+        }
+        if (tid == 0) sm.halo_lo = byte0 ? *(const uint4 *)(src - 16) : make_uint4(UFULL, UFULL, UFULL, UFULL);
+        if (tid == 32) sm.halo_hi = byte0 + (u64)chunk_bytes < d.src_bytes ? *(const uint4 *)(src + UCHUNK) : make_uint4(UFULL, UFULL, UFULL, UFULL);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    /* ---- removal masks ---- */
+    u32 rm[UG], cnt[UG];
+#pragma unroll
+    for (int r = 0; r < UG; r++) {
+        const int g = tid + UT * r;
+        const int vb = min(max(chunk_bytes - 16 * g, 0), 16);
+        rm[r] = 0u;
+        if (vb > 0) {
+            const uint4 w = sm.data[g];
+            const u32 prev = (&sm.halo_lo)[g].w;             /* the word in front of the group (halo_lo sits right before data) */
+            const u32 next = (&sm.data[0])[g + 1].x;         /* the word behind it (halo_hi right after data) */
+            const u32 valid = vb == 16 ? 0xFFFFu : (1u << vb) - 1u;
+            const u32 t = mask16(w, 0x03030303u, UFULL) & valid;
+            if (t) {
+                const u32 z = mask16(w, 0u, UFULL), l3 = mask16(w, 0u, 0xFCFCFCFCu);
+                const u32 zp = nib_le(zero_bytes(prev)) >> 2;            /* zero flags of the two bytes in front: bit 0 = byte -2, bit 1 = byte -1 */
+                const u32 z1 = (z << 1) | (zp >> 1), z2 = (z << 2) | zp; /* byte j-1 zero, byte j-2 zero */
+                /* a next byte must exist: inside the payload (bytes past its end were staged as 0xFF or are masked here) */
+                const u64 left = d.src_bytes - (byte0 + 16u * (u64)g);   /* payload bytes from the group's first byte on */
+                u32 nx = (l3 >> 1) | ((nib_le(zero_bytes(next & 0xFCFCFCFCu)) & 1u) << 15);
+                if (left <= 16u) nx &= (1u << (u32)(left - 1u)) - 1u;   /* byte j + 1 exists only for j + 1 < left */
+                rm[r] = t & z1 & z2 & nx;
+            }
+        }
+        cnt[r] = (u32)__popc(rm[r]);
+        sm.gi[g] = (rm[r] << 8) | cnt[r];
+    }
+    u32 lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16), tlo, thi;
+    scan_x2(lo, hi, sm.scan, tlo, thi);
+    const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
+    if (tid == 0) sm.base = lookback(state + 1 + (size_t)nal * max_chunks, c, t0 + t1 + t2 + t3);
+    __syncthreads();
+    const u32 base = sm.base;
+    const u32 before[UG] = {base + (lo & 0xFFFFu), base + t0 + (lo >> 16), base + t0 + t1 + (hi & 0xFFFFu), base + t0 + t1 + t2 + (hi >> 16)};
+    const u32 cap = d.out_cap;
+    /* ---- compacting store ---- */
+#pragma unroll
+    for (int r = 0; r < UG; r++) {
+        const int g = tid + UT * r;
+        const int vb = min(max(chunk_bytes - 16 * g, 0), 16);
+        if (vb == 0) continue;
+        const u64 D64 = byte0 + 16u * (u64)g - before[r];    /* output byte of the group's first byte */
+        const u32 D = (u32)D64;
+        const uint4 w = sm.data[g];
+        const bool roomy = D64 + 20u <= cap;
+        if (cnt[r] == 0u && vb == 16 && roomy) {
+            const u32 s = (4u - (D & 3u)) & 3u;              /* bytes in front of the first aligned output word */
+            u32 *o32 = (u32 *)(dst + D + s);
+            if (s == 0u) {
+                if ((D & 15u) == 0u) *(uint4 *)o32 = w;
+                else { o32[0] = w.x; o32[1] = w.y; o32[2] = w.z; o32[3] = w.w; }
+            } else {
+                /* the word shared with a neighbour is stored whole only when that neighbour is a plain full group too */
+                const bool prev_plain = g > 0 && sm.gi[g - 1] == 0u;
+                const bool next_plain = g + 1 < UT * UG && sm.gi[g + 1] == 0u && chunk_bytes - 16 * (g + 1) >= 16;
+                const u32 wn = (&sm.data[0])[g + 1].x;
+                const u32 sel = 0x3210u + 0x1111u * s;
+                o32[0] = __byte_perm(w.x, w.y, sel);
+                o32[1] = __byte_perm(w.y, w.z, sel);
+                o32[2] = __byte_perm(w.z, w.w, sel);
+                const u32 o3 = __byte_perm(w.w, wn, sel);
+                if (next_plain) o32[3] = o3;
+                else for (u32 k = 0; k < 4u - s; k++) dst[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
+                if (!prev_plain) for (u32 k = 0; k < s; k++) dst[D + k] = (uint8_t)(w.x >> (8u * k));
+            }
+        } else {
+            const u32 ws[4] = {w.x, w.y, w.z, w.w};
+            u64 pos = D64;
+            for (int k = 0; k < vb; k++) {
+                if ((rm[r] >> k) & 1u) continue;
+                if (pos < cap) dst[pos] = (uint8_t)(ws[k >> 2] >> (8 * (k & 3)));
+                pos++;
+            }
+        }
+    }
+    if (tid == 0 && byte0 + (u64)chunk_bytes >= d.src_bytes) sizes[nal] = (u32)(d.src_bytes - (base + t0 + t1 + t2 + t3));
+    (void)lane;
+}
+
+}  // namespace
+
+cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks, const uint8_t *d_src,
+                            uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream) {
+    if (n_nals <= 0 || max_chunks <= 0) return cudaSuccess;
+    static bool ready = false;
+    const int smem = (int)sizeof(UnescapeSmem);
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(unescape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        ready = true;
+    }
+    const unsigned grid = (unsigned)n_nals * (unsigned)max_chunks;
+    cudaError_t e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);
+    if (e != cudaSuccess) return e;
+    unescape_kernel<<<grid, UT, smem, stream>>>(d_desc, n_nals, max_chunks, d_src, d_out, d_sizes, d_state);
+    return cudaGetLastError();
+}
+
+int unescape_chunk_bytes() { return UCHUNK; }
+
+}  /* namespace h264scroll */

@@ -227,6 +227,26 @@ int h264gpu_rewrite_chunk_bytes(void);
 int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,
                            const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream);
 
+/* ---- EBSP -> RBSP (the input side of the splice) ---------------------------
+ *
+ * ebsp_to_rbsp (src/nal_parser.c:67-88) for whole batches of NAL payloads: drops every emulation prevention byte
+ * (a 0x03 behind two zero bytes and in front of a byte <= 0x03).
+ */
+typedef struct {
+    uint64_t src_off;       /* byte offset of the EBSP payload in d_src (multiple of 16)      */
+    uint64_t src_bytes;     /* its size; 16 more bytes must be readable behind it             */
+    uint64_t out_off;       /* byte offset of the RBSP in d_out (multiple of 16)              */
+    uint32_t out_cap;       /* capacity in bytes (src_bytes always suffices)                  */
+    uint32_t reserved;
+} H264GpuUnescapeDesc;      /* 32 bytes */
+
+int h264gpu_unescape_chunk_bytes(void);   /* payload bytes one CTA handles */
+
+/* Device pointers; max_chunks >= chunks of the largest payload; d_scratch = 1 + n_nals * max_chunks uint32 (zeroed by
+ * the call); d_sizes[i] = RBSP bytes.  Asynchronous on `stream`. */
+int h264gpu_unescape_nals(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks,
+                          const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream);
+
 /* Count of kernels this library has launched since init (for bench accounting). */
 uint64_t h264gpu_launch_count(void);
 
