@@ -507,6 +507,66 @@ def cpu_rewrite_baseline(rbsp, S):
             "sample": "%d calls of h264_rewrite_idr_frame on one %d-byte slice, %.1f s wall" % (reps, S, wall)}
 
 
+def main_unescape(args):
+    """batched EBSP -> RBSP (ebsp_to_rbsp on the device).  `python bench.py --workload unescape`."""
+    ge.load_package()
+    from h264_scroll_encoder_b200 import binding, abi
+    gc = binding.GpuComposer(0)
+    L = gc.lib
+    n, S = args.slices, (args.slice_bytes + 15) & ~15
+    rng = np.random.default_rng(9)
+    src = rng.integers(0, 256, n * S, dtype=np.uint8)
+    idx = rng.integers(0, len(src) - 4, len(src) // 512)
+    src[idx] = 0; src[idx + 1] = 0; src[idx + 2] = 3; src[idx + 3] = 1          # an emulation prevention byte every ~512 bytes
+    desc = np.zeros(n, abi.UNESCAPE_DESC)
+    desc["src_off"] = np.arange(n, dtype=np.uint64) * np.uint64(S)
+    desc["src_bytes"], desc["out_cap"] = S, S
+    desc["out_off"] = desc["src_off"]
+    cb = int(L.h264gpu_unescape_chunk_bytes())
+    max_chunks = (S + cb - 1) // cb
+    d_desc, d_src = gc.to_device(desc), gc.to_device(np.concatenate([src, np.zeros(32, np.uint8)]))
+    d_out, d_sizes, d_st = gc.alloc(n * S + 32), gc.alloc(4 * n), gc.alloc(4 * (1 + n * max_chunks))
+    ev0, ev1 = L.h264gpu_event_create(), L.h264gpu_event_create()
+
+    def step():
+        gc.check(L.h264gpu_unescape_nals(d_desc.ptr, n, max_chunks, d_src.ptr, d_out.ptr, d_sizes.ptr, d_st.ptr, None))
+    for _ in range(max(args.warmup, 3)):
+        step()
+    gc.sync()
+    l0 = gc.launch_count()
+    gc.check(L.h264gpu_event_record(ev0, None))
+    for _ in range(args.steps):
+        step()
+    gc.check(L.h264gpu_event_record(ev1, None))
+    ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / args.steps
+    launches = gc.launch_count() - l0
+    out_bytes = int(d_sizes.download(np.uint32).sum())
+    peak, peak_kind = peaks()
+    achieved = (n * S + out_bytes) / (ms * 1e-3) / 1e9
+    line = {"metric": "unescaped_ebsp_bytes_per_second", "value": n * S / (ms * 1e-3), "unit": "B/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "gpu_launches": int(launches),
+            "config": {"workload": "EBSP -> RBSP (ebsp_to_rbsp on the device): %d payloads of %d bytes per step, %.0f MB in + %.0f MB out "
+                                   "vs 126 MB L2" % (n, S, n * S / 1e6, out_bytes / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "unescape_kernel",
+                         "algorithmic_bytes_per_launch": int(n * S + out_bytes)}}
+    if not args.no_cpu:
+        path = os.path.join(ROOT, "oracle", "_ref", "libref_composer.so")
+        R, kind = (ctypes.CDLL(path), "reference") if os.path.exists(path) else (binding.load_library(), "port")
+        R.ebsp_to_rbsp.restype = ctypes.c_size_t
+        one, out = src[:S].copy(), np.zeros(S + 8, np.uint8)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 5.0:
+            R.ebsp_to_rbsp(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(one.ctypes.data), ctypes.c_size_t(S))
+            reps += 1
+        wall = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": reps * S / wall, "unit": "B/s", "cores": 1, "kind": kind,
+                                "sample": "%d calls of ebsp_to_rbsp on one %d-byte payload, %.1f s wall" % (reps, S, wall)}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -516,7 +576,7 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="compose", choices=["compose", "rewrite"],
+    ap.add_argument("--workload", default="compose", choices=["compose", "rewrite", "unescape"],
                     help="compose = the north-star metric (default); rewrite = batched I-slice rewrite (SURVEY 8f)")
     ap.add_argument("--slices", type=int, default=128)
     ap.add_argument("--slice-bytes", type=int, default=1382400)
@@ -527,6 +587,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.workload == "rewrite":
         return main_rewrite(args)
+    if args.workload == "unescape":
+        return main_unescape(args)
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

@@ -21,9 +21,15 @@ typedef uint64_t u64;
 
 namespace {
 
-constexpr int UT = 512;                  /* threads per CTA */
+#ifndef UNESCAPE_THREADS
+#define UNESCAPE_THREADS 256
+#endif
+#ifndef UNESCAPE_MIN_CTAS
+#define UNESCAPE_MIN_CTAS 8
+#endif
+constexpr int UT = UNESCAPE_THREADS;     /* threads per CTA */
 constexpr int UG = 4;                    /* 16-byte groups per thread */
-constexpr int UCHUNK = UT * UG * 16;     /* payload bytes per CTA (32 KB) */
+constexpr int UCHUNK = UT * UG * 16;     /* payload bytes per CTA */
 constexpr int UW = UT / 32;
 constexpr u32 UFULL = 0xFFFFFFFFu;
 
@@ -86,7 +92,7 @@ __device__ __forceinline__ u32 lookback(volatile u32 *state, int c, u32 mine) {
     return sum;
 }
 
-__global__ void __launch_bounds__(UT, 2)
+__global__ void __launch_bounds__(UT, UNESCAPE_MIN_CTAS)
 unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int max_chunks,
                 const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out, u32 *__restrict__ sizes,
                 u32 *__restrict__ state /* [1 + n_nals * max_chunks], zeroed */) {
