@@ -279,8 +279,8 @@ def main_ours(args):
     h_out = L.h264gpu_host_alloc(b.slot_cap * n // 2)
     h_offs = L.h264gpu_host_alloc(8 * (chunk_frames + 1) * n_chunks)
     offs_view = np.ctypeslib.as_array((ctypes.c_uint64 * ((chunk_frames + 1) * n_chunks)).from_address(h_offs))
-    streams = [L.h264gpu_stream_create() for _ in range(min(4, n_chunks))]
-    LAG = 2
+    streams = [L.h264gpu_stream_create() for _ in range(min(args.e2e_streams, n_chunks))]
+    LAG = args.e2e_lag
 
     zero_copy = args.e2e_zero_copy      # measured slower than the copy engine (8.8 vs 7.3 ms per step): off by default
     h_out_c = L.h264gpu_host_alloc(chunk_cap * n_chunks) if zero_copy else None
@@ -582,6 +582,8 @@ def main():
     ap.add_argument("--slice-bytes", type=int, default=1382400)
     ap.add_argument("--e2e-zero-copy", action="store_true",
                     help="end-to-end path whose pack kernel writes into pinned host memory instead of a separate D2H copy")
+    ap.add_argument("--e2e-streams", type=int, default=4)
+    ap.add_argument("--e2e-lag", type=int, default=2, help="chunks in flight before the first packed chunk is fetched")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="frame chunks the end-to-end path pipelines over streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

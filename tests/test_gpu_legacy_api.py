@@ -62,3 +62,35 @@ def test_single_frame_calls_match_batched(gpu, oracle):
     want, _ = oracle.legacy_stream(1280, 720, offs)
     assert np.array_equal(a, want) and np.array_equal(b, want)
     assert cfg_a.frame_num == cfg_b.frame_num and cfg_a.num_waypoints == cfg_b.num_waypoints
+
+
+def test_config1_scroll_encoder_twin_p_frames(gpu):
+    """BASELINE config 1 (experiments/scroll-encoder, 1280x720, 248 frames from offset 496, speed 1): that program emits
+    the waypoint frame INSTEAD of the scroll frame (experiments/scroll-encoder/src/main.c:418-424).  Its P NAL units,
+    recorded from the compiled reference CLI (tests/golden/reference_cli.json), through this library's frame writers."""
+    gold = json.load(open(os.path.join(os.path.dirname(GOLDEN), "reference_cli.json")))["config1_scroll_encoder_1280x720_248"]
+    lib = gpu.lib
+    cfg = binding.ComposerConfig()
+    lib.composer_config_init(C.byref(cfg), 1280, 720)
+    lib.composer_config_set_sps_params(C.byref(cfg), 4, 2, 4)
+    lib.composer_config_set_pps_params(C.byref(cfg), 1, 1)
+    cfg.frame_num = 2
+    out = np.zeros(16 << 20, np.uint8)
+    nw = binding.NALWriter()
+    lib.nal_writer_init(C.byref(nw), C.c_void_p(out.ctypes.data), C.c_size_t(out.size), None, C.c_size_t(0))
+    lib.h264_write_scroll_p_frame.restype = C.c_size_t
+    lib.h264_write_waypoint_p_frame.restype = C.c_size_t
+    max_off = 720 - 16
+    headers = set()
+    for i in range(248):
+        pos = (i + 496) % (2 * max_off)
+        off = pos if pos < max_off else 2 * max_off - pos
+        before = nw.output_pos
+        if lib.h264_needs_waypoint(C.byref(cfg), off):
+            assert lib.h264_write_waypoint_p_frame(C.byref(nw), C.byref(cfg), off) > 0
+        else:
+            assert lib.h264_write_scroll_p_frame(C.byref(nw), C.byref(cfg), off) > 0
+        headers.add(int(out[before + 4]))
+    got = out[:nw.output_pos]
+    assert sorted(headers) == gold["p_nal_headers"]
+    assert hashlib.sha256(got.tobytes()).hexdigest() == gold["p_stream_sha256"]
