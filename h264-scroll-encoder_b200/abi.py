@@ -23,7 +23,9 @@ REWRITE_DESC = np.dtype([("hdr_bits", "<u8", (4,)), ("src_off", "<u8"), ("src_by
 
 UNESCAPE_DESC = np.dtype([("src_off", "<u8"), ("src_bytes", "<u8"), ("out_off", "<u8"), ("out_cap", "<u4"), ("reserved", "<u4")])
 
-assert REWRITE_DESC.itemsize == 80 and UNESCAPE_DESC.itemsize == 32
+NAL_UNIT = np.dtype([("offset", "<u4"), ("size", "<u4"), ("nal_ref_idc", "u1"), ("nal_unit_type", "u1"), ("reserved", "u1", (2,))])
+
+assert REWRITE_DESC.itemsize == 80 and UNESCAPE_DESC.itemsize == 32 and NAL_UNIT.itemsize == 12
 assert HINT.itemsize == 8 and FRAME_DESC.itemsize == 64 and DYN_DESC.itemsize == 32
 assert REGION.itemsize == 16 and RASTER_DESC.itemsize == 24
 

@@ -18,7 +18,8 @@ GPU_SYMBOLS = [
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
     "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
     "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
-    "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes", "h264gpu_unescape_nals", "h264gpu_unescape_chunk_bytes"]
+    "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes", "h264gpu_unescape_nals", "h264gpu_unescape_chunk_bytes",
+    "h264gpu_parse_annexb", "h264gpu_parse_annexb_scratch_words"]
 REFERENCE_API_SYMBOLS = [
     # include/composer.h
     "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
@@ -71,6 +72,8 @@ def load_library(path=None):
     L.h264gpu_canonicalize_hints.argtypes = [vp, sz, vp]
     L.h264gpu_rewrite_slices.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
     L.h264gpu_unescape_nals.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+    L.h264gpu_parse_annexb.argtypes = [vp, sz, vp, C.c_uint32, vp, vp]
+    L.h264gpu_parse_annexb_scratch_words.argtypes = [sz, C.c_uint32]; L.h264gpu_parse_annexb_scratch_words.restype = sz
     L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
     L.h264gpu_launch_count.restype = C.c_uint64
     return L
@@ -188,6 +191,21 @@ class GpuComposer:
         for b_ in (d_desc, d_src, d_out, d_sizes, d_cnt):
             b_.free()
         return res, sizes
+
+    def parse_annexb(self, stream_bytes, max_nals):
+        """Host convenience around h264gpu_parse_annexb: uint8 stream -> (abi.NAL_UNIT records, count found)."""
+        from . import abi
+        n = len(stream_bytes)
+        d_data = self.to_device(np.concatenate([stream_bytes, np.full(32, 0xFF, np.uint8)]))
+        words = int(self.lib.h264gpu_parse_annexb_scratch_words(n, max_nals))
+        d_units, d_scr = self.alloc(12 * max(max_nals, 1)), self.alloc(4 * words)
+        self.check(self.lib.h264gpu_parse_annexb(d_data.ptr, n, d_units.ptr, max_nals, d_scr.ptr, None))
+        self.sync()
+        count = int(d_scr.download(np.uint32, count=max_nals + 1)[max_nals]) if n and max_nals else 0
+        units = d_units.download(abi.NAL_UNIT, count=min(count, max_nals))
+        for b_ in (d_data, d_units, d_scr):
+            b_.free()
+        return units, count
 
     def unescape_nals(self, payloads):
         """Host convenience around h264gpu_unescape_nals: list of uint8 EBSP payloads -> list of RBSP arrays."""

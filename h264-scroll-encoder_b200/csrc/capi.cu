@@ -177,6 +177,18 @@ int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *str
     return H264GPU_OK;
 }
 
+size_t h264gpu_parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals) { return h264scroll::parse_annexb_scratch_words(n_bytes, max_nals); }
+
+int h264gpu_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
+                         uint32_t *d_scratch, void *stream) {
+    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    if (!d_data || !d_units || !d_scratch) return fail(H264GPU_ERR_ARG, "null argument");
+    cudaError_t e = h264scroll::launch_parse_annexb(d_data, n_bytes, d_units, max_nals, d_scratch, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "annexb scan launch", e);
+    if (n_bytes && max_nals) g_launches.fetch_add(2);
+    return H264GPU_OK;
+}
+
 int h264gpu_unescape_chunk_bytes(void) { return h264scroll::unescape_chunk_bytes(); }
 
 int h264gpu_unescape_nals(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks,

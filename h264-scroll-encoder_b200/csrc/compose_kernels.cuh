@@ -42,6 +42,10 @@ cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int m
                             uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream);
 int unescape_chunk_bytes();
 
+cudaError_t launch_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
+                                uint32_t *d_scratch, cudaStream_t stream);
+size_t parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals);
+
 cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs,
                           const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
                           H264GpuMbHint *d_hints, cudaStream_t stream);

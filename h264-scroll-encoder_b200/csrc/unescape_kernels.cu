@@ -203,6 +203,90 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
     (void)lane;
 }
 
+
+/* ------------------------------------------------------------ Annex-B scan
+ *
+ * nal_parser_next (src/nal_parser.c:14-65) for a whole stream: a NAL unit starts behind every 00 00 01 (a 4-byte start
+ * code is the same pattern one byte later, so both give the same position) and ends before the next start code, minus
+ * trailing zero bytes.  Pass 1 finds the start positions in stream order (a CTA counts the patterns in its 16 KB,
+ * looks back for the number before it, writes its positions); pass 2 turns them into {offset, size, header} records.
+ */
+constexpr int PT = 256;                  /* threads per CTA: 16 bytes each... */
+constexpr int PG = 4;                    /* ...times 4 */
+constexpr int PCHUNK = PT * PG * 16;
+
+__global__ void __launch_bounds__(PT)
+annexb_starts_kernel(const uint8_t *__restrict__ data, unsigned long long n_bytes, u32 *__restrict__ starts, u32 max_nals,
+                     u32 *__restrict__ state /* [1 + chunks]: ticket, look-back words; zeroed */) {
+    __shared__ u32 s_ticket, s_base;
+    __shared__ u32 s_warp[PT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(state, 1u);
+    __syncthreads();
+    const int c = (int)s_ticket;
+    const u64 byte0 = (u64)c * PCHUNK;
+    if (byte0 >= n_bytes) return;
+    /* a thread owns PG consecutive 16-byte groups: pattern starts i in [g0, g0 + 16 PG), bytes i, i+1, i+2 */
+    const u64 t0 = byte0 + (u64)tid * (16 * PG);
+    u32 found[PG];
+    u32 cnt = 0;
+#pragma unroll
+    for (int r = 0; r < PG; r++) {
+        const u64 g0 = t0 + 16u * (u64)r;
+        found[r] = 0u;
+        if (g0 < n_bytes) {
+            const uint4 w = *(const uint4 *)(data + g0);      /* the buffer is readable 16 bytes past its end */
+            const u32 nx = *(const u32 *)(data + g0 + 16);
+            const u32 z = mask16(w, 0u, UFULL) | ((nib_le(zero_bytes(nx)) & 3u) << 16);           /* bytes 0..17 == 0 */
+            const u32 o = mask16(w, 0x01010101u, UFULL) | ((nib_le(zero_bytes(nx ^ 0x01010101u)) & 3u) << 16);   /* == 1 */
+            u32 m = z & (z >> 1) & (o >> 2) & 0xFFFFu;        /* bit i: bytes i, i+1 zero and byte i+2 one */
+            const u64 left = n_bytes - g0;                    /* the pattern needs i + 2 < left */
+            if (left < 18u) m &= left > 2u ? (1u << (u32)(left - 2u)) - 1u : 0u;
+            found[r] = m;
+            cnt += (u32)__popc(m);
+        }
+    }
+    /* block exclusive scan of the counts (stream order = thread order) */
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(UFULL, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    u32 wbase = 0, total = 0;
+    for (int w = 0; w < PT / 32; w++) { if (w < warp) wbase += s_warp[w]; total += s_warp[w]; }
+    if (tid == 0) s_base = lookback(state + 1, c, total);
+    __syncthreads();
+    u32 k = s_base + wbase + inc - cnt;
+#pragma unroll
+    for (int r = 0; r < PG; r++) {
+        u32 m = found[r];
+        while (m) {
+            const int i = __ffs((int)m) - 1;
+            m &= m - 1u;
+            if (k < max_nals) starts[k] = (u32)(t0 + 16u * (u64)r + (u64)i + 3u);
+            k++;
+        }
+    }
+    if (tid == PT - 1 && byte0 + PCHUNK >= n_bytes) starts[max_nals] = k;      /* the last chunk knows the count */
+}
+
+__global__ void __launch_bounds__(256)
+annexb_units_kernel(const uint8_t *__restrict__ data, unsigned long long n_bytes, const u32 *__restrict__ starts, u32 max_nals,
+                    H264GpuNalUnit *__restrict__ units) {
+    const u32 n = min(starts[max_nals], max_nals);
+    for (u32 k = blockIdx.x * 256u + threadIdx.x; k < n; k += gridDim.x * 256u) {
+        const u64 b = starts[k];
+        u64 e = k + 1u < n ? (u64)starts[k + 1u] - 3u : n_bytes;
+        while (e > b && data[e - 1u] == 0) e--;              /* "remove trailing zeros before next start code" */
+        H264GpuNalUnit u;
+        u.offset = (u32)b + 1u;                              /* payload behind the header byte, as NALUnit.data */
+        u.size = e > b ? (u32)(e - b - 1u) : 0u;
+        u.nal_ref_idc = e > b ? (data[b] >> 5) & 3u : 0u;
+        u.nal_unit_type = e > b ? data[b] & 31u : 0u;
+        units[k] = u;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks, const uint8_t *d_src,
@@ -223,5 +307,21 @@ cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int m
 }
 
 int unescape_chunk_bytes() { return UCHUNK; }
+
+cudaError_t launch_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
+                                uint32_t *d_scratch /* 2 + max_nals + chunks */, cudaStream_t stream) {
+    if (n_bytes == 0 || max_nals == 0) return cudaSuccess;
+    const unsigned chunks = (unsigned)((n_bytes + PCHUNK - 1) / PCHUNK);
+    uint32_t *starts = d_scratch, *state = d_scratch + max_nals + 1;
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t) * ((size_t)max_nals + 2 + chunks), stream);
+    if (e != cudaSuccess) return e;
+    annexb_starts_kernel<<<chunks, PT, 0, stream>>>(d_data, (unsigned long long)n_bytes, starts, max_nals, state);
+    unsigned g2 = (max_nals + 255u) / 256u;
+    if (g2 > 148u * 8u) g2 = 148u * 8u;
+    annexb_units_kernel<<<g2, 256, 0, stream>>>(d_data, (unsigned long long)n_bytes, starts, max_nals, d_units);
+    return cudaGetLastError();
+}
+
+size_t parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals) { return (size_t)max_nals + 2 + (n_bytes + PCHUNK - 1) / PCHUNK; }
 
 }  /* namespace h264scroll */

@@ -247,6 +247,24 @@ int h264gpu_unescape_chunk_bytes(void);   /* payload bytes one CTA handles */
 int h264gpu_unescape_nals(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks,
                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream);
 
+/* ---- Annex-B scan -----------------------------------------------------------
+ *
+ * nal_parser_next (src/nal_parser.c:28-65) over a whole stream: one record per NAL unit, in stream order.
+ */
+typedef struct {
+    uint32_t offset;        /* of the payload behind the NAL header byte (NALUnit.data - stream start) */
+    uint32_t size;          /* payload bytes, trailing zero bytes removed (NALUnit.size)              */
+    uint8_t  nal_ref_idc, nal_unit_type, reserved[2];
+} H264GpuNalUnit;           /* 12 bytes */
+
+/* words of scratch h264gpu_parse_annexb needs for a stream of n_bytes and up to max_nals units */
+size_t h264gpu_parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals);
+
+/* d_data must be readable 20 bytes past n_bytes and 16-byte aligned.  The unit count lands in d_scratch[max_nals]
+ * (it may exceed max_nals: then only the first max_nals records were written).  Asynchronous on `stream`. */
+int h264gpu_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
+                         uint32_t *d_scratch, void *stream);
+
 /* Count of kernels this library has launched since init (for bench accounting). */
 uint64_t h264gpu_launch_count(void);
 

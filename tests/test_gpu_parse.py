@@ -1,0 +1,64 @@
+"""
+GPU Annex-B scan (nal_parser_next, src/nal_parser.c:28-65, over a whole stream) against this library's host C parser
+and, where oracle/_ref is built, the reference's.
+"""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+
+import helpers
+from h264_scroll_encoder_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+class NALUnit(C.Structure):
+    _fields_ = [("nal_ref_idc", C.c_int), ("nal_unit_type", C.c_int), ("data", C.c_void_p), ("size", C.c_size_t),
+                ("rbsp_size", C.c_size_t)]
+
+
+class NALParser(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+def _cpu_units(lib, stream):
+    p, u, out = NALParser(), NALUnit(), []
+    lib.nal_parser_init(C.byref(p), C.c_void_p(stream.ctypes.data), C.c_size_t(len(stream)))
+    while lib.nal_parser_next(C.byref(p), C.byref(u)):
+        out.append((u.data - stream.ctypes.data, u.size, u.nal_ref_idc, u.nal_unit_type))
+    return out
+
+
+def _check(gpu, stream, max_nals=None):
+    stream = np.ascontiguousarray(stream, np.uint8)
+    libs = [gpu.lib]
+    ref = os.path.join(helpers.ROOT, "oracle", "_ref", "libref_composer.so")
+    if os.path.exists(ref):
+        libs.append(C.CDLL(ref))
+    want = _cpu_units(libs[0], stream)
+    for lib in libs[1:]:
+        assert _cpu_units(lib, stream) == want
+    units, count = gpu.parse_annexb(stream, max_nals or max(len(want), 1) + 3)
+    got = [(int(u["offset"]), int(u["size"]), int(u["nal_ref_idc"]), int(u["nal_unit_type"])) for u in units]
+    assert count == len(want)
+    assert got == want[:len(got)]
+
+
+def test_parse_hand_made_streams(gpu):
+    sc3, sc4 = [0, 0, 1], [0, 0, 0, 1]
+    _check(gpu, np.array(sc4 + [0x67, 1, 2, 3] + sc4 + [0x68, 9] + sc3 + [0x65, 7, 7, 0, 0] + sc4 + [0x41, 5], np.uint8))
+    _check(gpu, np.array(sc3 + [0x01, 0xFF] * 20 + [0, 0, 0] + sc3 + [0x61, 3, 0, 0, 3, 1, 9], np.uint8))      # trailing zeros, an EPB inside
+    _check(gpu, np.array([9, 9, 9] + sc4 + [0x65] + [0xAB] * 40000 + sc4 + [0x41, 1], np.uint8))              # garbage in front, several chunks
+    _check(gpu, np.array(sc4 + [0x65, 1], np.uint8))
+
+
+def test_parse_composed_stream(gpu, po):
+    # the packed Annex-B stream of a config-5 batch, start codes at arbitrary alignment, thousands of chunks
+    b = workloads.make_config5(4, 16)
+    hints = helpers.dense_hints(po, b)
+    frames, _ = gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload)
+    stream = np.concatenate(frames)
+    _check(gpu, stream)
+    units, count = gpu.parse_annexb(stream, 10)              # fewer records than units: the count still tells
+    assert count == b.n_frames and len(units) == 10
