@@ -38,6 +38,9 @@ struct __align__(16) UnescapeSmem {
     uint4 data[UT * UG];                 /* the chunk */
     uint4 halo_hi;                       /* the 16 bytes behind it */
     u32 gi[UT * UG];                     /* per group: removal mask << 8 | removed bytes */
+    u32 gpre[UT * UG];                   /* bytes removed before a listed group */
+    unsigned short list[UT * UG];        /* groups that go byte by byte */
+    u32 n_list;
     uint2 scan[UW + 1];
     u32 ticket;
     u32 base;
@@ -99,7 +102,7 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UnescapeSmem &sm = *reinterpret_cast<UnescapeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) sm.ticket = atomicAdd(state, 1u);          /* chunks in launch order: everything below a ticket is running or done */
+    if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_list = 0; }   /* chunks in launch order: everything below a ticket is running or done */
     __syncthreads();
     const int ticket = (int)sm.ticket;
     const int nal = ticket / max_chunks, c = ticket - nal * max_chunks;
@@ -136,8 +139,14 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
             const u32 prev = (&sm.halo_lo)[g].w;             /* the word in front of the group (halo_lo sits right before data) */
             const u32 next = (&sm.data[0])[g + 1].x;         /* the word behind it (halo_hi right after data) */
             const u32 valid = vb == 16 ? 0xFFFFu : (1u << vb) - 1u;
-            const u32 t = mask16(w, 0x03030303u, UFULL) & valid;
-            if (t) {
+            /* cheap exact tests first: a removal needs a 0x03 byte in the group and a zero byte in it or right in front */
+            const u32 x3 = 0x03030303u;
+            const u32 has3 = (((w.x ^ x3) - 0x01010101u) & ~(w.x ^ x3)) | (((w.y ^ x3) - 0x01010101u) & ~(w.y ^ x3)) |
+                             (((w.z ^ x3) - 0x01010101u) & ~(w.z ^ x3)) | (((w.w ^ x3) - 0x01010101u) & ~(w.w ^ x3));
+            const u32 has0 = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) | ((w.z - 0x01010101u) & ~w.z) |
+                             ((w.w - 0x01010101u) & ~w.w) | ((prev - 0x01010101u) & ~prev & 0x80000000u);
+            if ((has3 & 0x80808080u) && (has0 & 0x80808080u)) {
+                const u32 t = mask16(w, 0x03030303u, UFULL) & valid;
                 const u32 z = mask16(w, 0u, UFULL), l3 = mask16(w, 0u, 0xFCFCFCFCu);
                 const u32 zp = nib_le(zero_bytes(prev)) >> 2;            /* zero flags of the two bytes in front: bit 0 = byte -2, bit 1 = byte -1 */
                 const u32 z1 = (z << 1) | (zp >> 1), z2 = (z << 2) | zp; /* byte j-1 zero, byte j-2 zero */
@@ -190,13 +199,24 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
                 if (!prev_plain) for (u32 k = 0; k < s; k++) dst[D + k] = (uint8_t)(w.x >> (8u * k));
             }
         } else {
-            const u32 ws[4] = {w.x, w.y, w.z, w.w};
-            u64 pos = D64;
-            for (int k = 0; k < vb; k++) {
-                if ((rm[r] >> k) & 1u) continue;
-                if (pos < cap) dst[pos] = (uint8_t)(ws[k >> 2] >> (8 * (k & 3)));
-                pos++;
-            }
+            /* a removal inside, the payload's last partial group, or the end of the output buffer in reach: byte by byte,
+               but not here - one such group would hold its whole warp up.  They are listed and dealt out below */
+            sm.gpre[g] = before[r];
+            sm.list[atomicAdd(&sm.n_list, 1u)] = (unsigned short)g;
+        }
+    }
+    __syncthreads();
+    for (u32 i = (u32)tid; i < sm.n_list; i += UT) {
+        const int g = sm.list[i];
+        const int vb = min(chunk_bytes - 16 * g, 16);
+        const uint4 w = sm.data[g];
+        const u32 ws[4] = {w.x, w.y, w.z, w.w};
+        const u32 rmg = sm.gi[g] >> 8;
+        u64 pos = byte0 + 16u * (u64)g - sm.gpre[g];
+        for (int k = 0; k < vb; k++) {
+            if ((rmg >> k) & 1u) continue;
+            if (pos < cap) dst[pos] = (uint8_t)(ws[k >> 2] >> (8 * (k & 3)));
+            pos++;
         }
     }
     if (tid == 0 && byte0 + (u64)chunk_bytes >= d.src_bytes) sizes[nal] = (u32)(d.src_bytes - (base + t0 + t1 + t2 + t3));
