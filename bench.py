@@ -339,7 +339,20 @@ def main_ours(args):
             gc.check(L.h264gpu_stream_sync(st))
         return total
 
-    e2e_step = e2e_step_zero_copy if zero_copy else e2e_step_staged
+    # The same pipeline behind ONE C-ABI call (h264gpu_compose_regions_host): the library cuts the batch into chunks and
+    # drives streams, events and copies itself, so no Python sits between the enqueues.  This is the call a host
+    # application makes; the two functions above are kept for comparison (--e2e-python).
+    hb, hb_keep = gc.make_host_batch(b, pinned=True)
+    h_stream_cap = b.slot_cap * n // 2
+    h_offs_all = L.h264gpu_host_alloc(8 * (n + 1))
+    h_sizes_all = L.h264gpu_host_alloc(4 * n)
+    offs_all_view = np.ctypeslib.as_array((ctypes.c_uint64 * (n + 1)).from_address(h_offs_all))
+
+    def e2e_step_capi():
+        gc.compose_regions_host(hb, h_out, h_stream_cap, h_offs_all, h_sizes_all, n_chunks)
+        return int(offs_all_view[n])
+
+    e2e_step = e2e_step_zero_copy if zero_copy else (e2e_step_staged if args.e2e_python else e2e_step_capi)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -352,6 +365,14 @@ def main_ours(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert ablate or d2h == s_out, "packed stream size differs from the sum of the frame sizes"
     e2e_launches = 5 * n_chunks                                  # raster + compose (2 instantiations) + pack (2 kernels) per chunk
+    if e2e_step is e2e_step_capi and not ablate:
+        # the stream the call returned is the concatenation of the slots the kernel-only run left on the device
+        fo = np.array(offs_all_view, dtype=np.uint64)
+        assert np.array_equal(fo[1:] - fo[:-1], sizes.astype(np.uint64)), "end-to-end frame sizes differ from the kernel-only run"
+        hv = np.ctypeslib.as_array((ctypes.c_uint8 * d2h).from_address(h_out))
+        for f in (0, n // 2, n - 1):
+            slot = d_out.download(np.uint8, count=int(sizes[f]), offset=int(b.desc["out_off"][f]))
+            assert np.array_equal(hv[int(fo[f]):int(fo[f + 1])], slot), "end-to-end stream differs from the device slots"
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------
     ms_step, e2e_step_s = ms / args.steps, e2e_s
@@ -375,10 +396,11 @@ def main_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks)), "ms_per_step": 1e3 * e2e_step_s,
+                    "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks) + (4 * n if e2e_step is e2e_step_capi else 0)), "ms_per_step": 1e3 * e2e_step_s,
                     "chunks": n_chunks, "gpu_launches_per_step": e2e_launches,
                     "path": ("pinned host region lists + payload -> H2D -> raster -> compose -> pack writes the Annex-B stream "
                              "into pinned host memory (D2H inside the kernel)" if zero_copy else
+                             ("one h264gpu_compose_regions_host call: " if e2e_step is e2e_step_capi else "") +
                              "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream")
                             + ", in %d frame chunks over %d streams" % (n_chunks, len(streams))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -582,6 +604,7 @@ def main():
     ap.add_argument("--slice-bytes", type=int, default=1382400)
     ap.add_argument("--e2e-zero-copy", action="store_true",
                     help="end-to-end path whose pack kernel writes into pinned host memory instead of a separate D2H copy")
+    ap.add_argument("--e2e-python", action="store_true", help="drive the end-to-end pipeline from Python (chunk by chunk) instead of the single C-ABI call")
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--e2e-lag", type=int, default=2, help="chunks in flight before the first packed chunk is fetched")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="frame chunks the end-to-end path pipelines over streams")

@@ -17,7 +17,7 @@ GPU_SYMBOLS = [
     "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
     "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
-    "h264gpu_compose_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
+    "h264gpu_compose_host", "h264gpu_compose_regions_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
     "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes", "h264gpu_unescape_nals", "h264gpu_unescape_chunk_bytes",
     "h264gpu_parse_annexb", "h264gpu_parse_annexb_scratch_words"]
 REFERENCE_API_SYMBOLS = [
@@ -43,6 +43,17 @@ REFERENCE_API_SYMBOLS = [
 
 class GpuError(RuntimeError):
     pass
+
+
+class HostBatch(C.Structure):
+    """H264GpuHostBatch (include/composer_gpu.h)."""
+    _fields_ = [("desc", C.c_void_p), ("n_frames", C.c_int), ("rdesc", C.c_void_p),
+                ("regions", C.c_void_p), ("n_regions", C.c_size_t),
+                ("dyn_info", C.c_void_p), ("n_dyn_info", C.c_size_t),
+                ("dyn", C.c_void_p), ("n_dyn", C.c_int),
+                ("dyn_tab", C.c_void_p), ("n_tab", C.c_size_t),
+                ("payload", C.c_void_p), ("payload_bytes", C.c_size_t),
+                ("n_hints", C.c_size_t), ("slots_bytes", C.c_size_t), ("max_mbs_per_frame", C.c_int)]
 
 
 def load_library(path=None):
@@ -75,6 +86,7 @@ def load_library(path=None):
     L.h264gpu_parse_annexb.argtypes = [vp, sz, vp, C.c_uint32, vp, vp]
     L.h264gpu_parse_annexb_scratch_words.argtypes = [sz, C.c_uint32]; L.h264gpu_parse_annexb_scratch_words.restype = sz
     L.h264gpu_compose_host.argtypes = [vp, ci, vp, sz, vp, ci, vp, sz, vp, sz, vp, sz, vp]
+    L.h264gpu_compose_regions_host.argtypes = [C.POINTER(HostBatch), vp, sz, vp, vp, ci]
     L.h264gpu_launch_count.restype = C.c_uint64
     return L
 
@@ -157,6 +169,43 @@ class GpuComposer:
                                            _ptr(out), out.size, _ptr(sizes))
         self.check(rc)
         return [out[int(d["out_off"]):int(d["out_off"]) + int(s)].copy() for d, s in zip(desc, sizes)], sizes
+
+    def pinned_copy(self, arr):
+        """A copy of `arr` in pinned host memory (h264gpu_host_alloc); returns (pointer, numpy view)."""
+        arr = np.ascontiguousarray(arr)
+        nb = max(arr.nbytes, 16)
+        p = self.lib.h264gpu_host_alloc(nb)
+        if not p:
+            raise GpuError("pinned allocation of %d bytes failed: %s" % (nb, self.err()))
+        v = np.ctypeslib.as_array((C.c_uint8 * nb).from_address(p))
+        v[:arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        return p, v
+
+    def make_host_batch(self, b, pinned=True):
+        """workloads.Batch -> (HostBatch, keep-alive list).  pinned=True copies the arrays into pinned memory once."""
+        keep = []
+        def ptr(a):
+            if a is None or a.size == 0:
+                return None
+            a = np.ascontiguousarray(a)
+            if pinned:
+                p, v = self.pinned_copy(a); keep.append((p, v)); return p
+            keep.append(a); return a.ctypes.data
+        hb = HostBatch()
+        hb.desc, hb.n_frames, hb.rdesc = ptr(b.desc), b.n_frames, ptr(b.rdesc)
+        hb.regions, hb.n_regions = ptr(b.regions), len(b.regions)
+        hb.dyn_info, hb.n_dyn_info = ptr(b.dyn_info), len(b.dyn_info)
+        hb.dyn, hb.n_dyn = ptr(b.dyn), len(b.dyn)
+        hb.dyn_tab, hb.n_tab = ptr(b.dyn_tab), len(b.dyn_tab)
+        hb.payload, hb.payload_bytes = ptr(b.payload), b.payload.size
+        hb.n_hints = int((b.desc["hint_off"] + b.desc["mb_w"].astype(np.int64) * b.desc["mb_h"]).max())
+        hb.slots_bytes = int((b.desc["out_off"] + b.desc["out_cap"]).max())
+        hb.max_mbs_per_frame = int((b.desc["mb_w"].astype(np.int64) * b.desc["mb_h"]).max())
+        return hb, keep
+
+    def compose_regions_host(self, hb, h_stream, stream_cap, h_offsets, h_sizes=None, n_chunks=0):
+        """h264gpu_compose_regions_host: host region lists + payload -> packed Annex-B stream in host memory."""
+        self.check(self.lib.h264gpu_compose_regions_host(C.byref(hb), h_stream, stream_cap, h_offsets, h_sizes, n_chunks))
 
     # ---- device-pointer calls --------------------------------------------------------------------
     def compose_batch(self, d_desc, n, d_hints, d_dyn, d_tab, d_payload, d_out, d_sizes, stream=None):

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <atomic>
 #include <mutex>
+#include <chrono>
 #include "composer_gpu.h"
 #include "compose_kernels.cuh"
 
@@ -42,6 +43,8 @@ struct Scratch {
 } g_scratch;
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void pipe_release();
 
 }  // namespace
 
@@ -80,6 +83,7 @@ void h264gpu_shutdown(void) {
     if (g_scratch.d) cudaFree(g_scratch.d);
     if (g_scratch.pin) cudaFreeHost(g_scratch.pin);
     g_scratch = Scratch();
+    pipe_release();
     g_device = -1;
 }
 
@@ -287,6 +291,254 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
     for (int f = 0; f < n_frames; f++)
         if (h_sizes[f] > h_desc[f].out_cap) return fail(H264GPU_ERR_OVERFLOW, "a frame exceeded its output slot");
     return H264GPU_OK;
+}
+
+}  /* extern "C" */
+
+/* ---- host batch -> packed stream, pipelined over frame chunks -------------------------------- */
+
+namespace {
+
+constexpr int PIPE_STREAMS = 3;            /* upload, kernels, download */
+constexpr int PIPE_LAG = 2;            /* chunks enqueued before the first packed chunk is fetched */
+constexpr int PIPE_MAX_CHUNKS = 64;
+
+struct Pipe {
+    cudaStream_t st[PIPE_STREAMS] = {};
+    cudaEvent_t ready[PIPE_MAX_CHUNKS] = {};      /* chunk c: packed, its frame offsets are on the host */
+    cudaEvent_t uploaded[PIPE_MAX_CHUNKS] = {};   /* chunk c: inputs are on the device */
+    bool made = false;
+    char *dev = nullptr;  size_t dev_cap = 0;
+    char *pin = nullptr;  size_t pin_cap = 0;
+} g_pipe;
+
+cudaError_t pipe_setup(size_t dev_bytes, size_t pin_bytes) {
+    cudaError_t e = cudaSuccess;
+    if (!g_pipe.made) {
+        for (int i = 0; i < PIPE_STREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&g_pipe.st[i], cudaStreamNonBlocking);
+        for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.ready[i], cudaEventDisableTiming);
+        for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.uploaded[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        g_pipe.made = true;
+    }
+    if (dev_bytes > g_pipe.dev_cap) {
+        if (g_pipe.dev) cudaFree(g_pipe.dev);
+        g_pipe.dev = nullptr; g_pipe.dev_cap = 0;
+        e = cudaMalloc((void **)&g_pipe.dev, dev_bytes);
+        if (e != cudaSuccess) return e;
+        g_pipe.dev_cap = dev_bytes;
+    }
+    if (pin_bytes > g_pipe.pin_cap) {
+        if (g_pipe.pin) cudaFreeHost(g_pipe.pin);
+        g_pipe.pin = nullptr; g_pipe.pin_cap = 0;
+        e = cudaMallocHost((void **)&g_pipe.pin, pin_bytes);
+        if (e != cudaSuccess) return e;
+        g_pipe.pin_cap = pin_bytes;
+    }
+    return cudaSuccess;
+}
+
+void pipe_release() {
+    if (g_pipe.made) {
+        for (int i = 0; i < PIPE_STREAMS; i++) if (g_pipe.st[i]) cudaStreamDestroy(g_pipe.st[i]);
+        for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.ready[i]) cudaEventDestroy(g_pipe.ready[i]);
+        for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.uploaded[i]) cudaEventDestroy(g_pipe.uploaded[i]);
+    }
+    if (g_pipe.dev) cudaFree(g_pipe.dev);
+    if (g_pipe.pin) cudaFreeHost(g_pipe.pin);
+    g_pipe = Pipe();
+}
+
+}  // namespace
+
+extern "C" {
+
+int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, size_t stream_cap,
+                                 uint64_t *h_offsets, uint32_t *h_sizes, int n_chunks) {
+    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    if (!b || !h_stream || !h_offsets) return fail(H264GPU_ERR_ARG, "null argument");
+    const int n = b->n_frames;
+    h_offsets[0] = 0;
+    if (n <= 0) return H264GPU_OK;
+    if (!b->desc || !b->rdesc || !b->regions) return fail(H264GPU_ERR_ARG, "null argument");
+    if (n_chunks <= 0) n_chunks = 8;
+    if (n_chunks > n) n_chunks = n;
+    if (n_chunks > PIPE_MAX_CHUNKS) n_chunks = PIPE_MAX_CHUNKS;
+
+    /* ---- validation: ranges and alignment ---- */
+    for (int f = 0; f < n; f++) {
+        const H264GpuFrameDesc &d = b->desc[f];
+        const H264GpuRasterDesc &r = b->rdesc[f];
+        if (d.mb_w == 0 || d.mb_h == 0 || d.mb_w > H264GPU_MAX_MB_W) return fail(H264GPU_ERR_ARG, "frame width out of range");
+        if ((d.hint_off & 1) || (d.out_off & 15) || (d.out_cap & 15)) return fail(H264GPU_ERR_ARG, "misaligned frame descriptor");
+        if (d.hint_off + (size_t)d.mb_w * d.mb_h > b->n_hints) return fail(H264GPU_ERR_ARG, "hints out of range");
+        if (d.out_off + d.out_cap > b->slots_bytes) return fail(H264GPU_ERR_ARG, "output slot out of range");
+        if (r.hint_off != d.hint_off || r.mb_w != d.mb_w || r.mb_h != d.mb_h) return fail(H264GPU_ERR_ARG, "raster and frame descriptor disagree");
+        if (r.region_count > H264GPU_MAX_REGIONS || (uint64_t)r.region_first + r.region_count > b->n_regions) return fail(H264GPU_ERR_ARG, "regions out of range");
+        if (r.dyn_info_off > b->n_dyn_info) return fail(H264GPU_ERR_ARG, "dyn_info out of range");
+        if (d.dyn_id != H264GPU_NO_DYN) {
+            if (!b->dyn || (int)d.dyn_id >= b->n_dyn) return fail(H264GPU_ERR_ARG, "dyn id out of range");
+            const H264GpuDynDesc &y = b->dyn[d.dyn_id];
+            if (y.table_off + y.n_mbs + 1 > b->n_tab || y.payload_off + y.payload_bytes > b->payload_bytes) return fail(H264GPU_ERR_ARG, "dyn table / payload out of range");
+        }
+    }
+
+    std::lock_guard<std::mutex> lk(g_mu);
+    int bounds[PIPE_MAX_CHUNKS + 1];
+    int chunk_frames = 0;
+    for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n * c / n_chunks);
+    for (int c = 0; c < n_chunks; c++) chunk_frames = bounds[c + 1] - bounds[c] > chunk_frames ? bounds[c + 1] - bounds[c] : chunk_frames;
+    /* packed bytes of a chunk never exceed its slots */
+    size_t chunk_cap = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        size_t s = 0;
+        for (int f = bounds[c]; f < bounds[c + 1]; f++) s += b->desc[f].out_cap;
+        chunk_cap = s > chunk_cap ? s : chunk_cap;
+    }
+    chunk_cap = align_up(chunk_cap, 256);
+
+    /* device layout (whole batch resident, arrays at the offsets the descriptors use) */
+    const size_t o_desc = 0;
+    const size_t o_rd = align_up(o_desc + sizeof(H264GpuFrameDesc) * n, 256);
+    const size_t o_reg = align_up(o_rd + sizeof(H264GpuRasterDesc) * n, 256);
+    const size_t o_info = align_up(o_reg + sizeof(H264GpuRegion) * b->n_regions, 256);
+    const size_t o_dyn = align_up(o_info + sizeof(H264GpuMbHint) * b->n_dyn_info, 256);
+    const size_t o_tab = align_up(o_dyn + sizeof(H264GpuDynDesc) * (size_t)(b->n_dyn > 0 ? b->n_dyn : 0), 256);
+    const size_t o_pay = align_up(o_tab + sizeof(uint32_t) * b->n_tab, 256);
+    const size_t o_hint = align_up(o_pay + b->payload_bytes + 32, 256);
+    const size_t o_sz = align_up(o_hint + sizeof(H264GpuMbHint) * b->n_hints, 256);
+    const size_t o_offs = align_up(o_sz + sizeof(uint32_t) * n, 256);
+    const size_t o_slots = align_up(o_offs + 8 * (size_t)(chunk_frames + 1) * n_chunks, 256);
+    const size_t o_packed = align_up(o_slots + b->slots_bytes, 256);
+    const size_t dev_total = o_packed + chunk_cap * n_chunks;
+    const size_t p_offs = 0, p_sz = align_up(8 * (size_t)(chunk_frames + 1) * n_chunks, 256);
+    cudaError_t e = pipe_setup(dev_total, p_sz + sizeof(uint32_t) * n);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_NOMEM, "pipeline scratch", e);
+    char *D = g_pipe.dev;
+    uint64_t *pin_offs = (uint64_t *)(g_pipe.pin + p_offs);
+    uint32_t *pin_sz = (uint32_t *)(g_pipe.pin + p_sz);
+
+    /* item range [lo, hi) of each input array that the frames of a chunk refer to (frame-ordered layouts make
+       these ranges tile the arrays; any other layout still works, it just uploads some items more than once) */
+    struct Range { size_t lo = ~(size_t)0, hi = 0; void add(size_t a, size_t z) { if (z > a) { lo = a < lo ? a : lo; hi = z > hi ? z : hi; } } };
+    struct ChunkRanges { Range reg, info, dyn, tab, pay; };
+    auto ranges_of = [&](int f0, int f1) {
+        ChunkRanges R;
+        for (int f = f0; f < f1; f++) {
+            const H264GpuRasterDesc &r = b->rdesc[f];
+            R.reg.add(r.region_first, (size_t)r.region_first + r.region_count);
+            for (uint32_t i = 0; i < r.region_count; i++) {
+                const H264GpuRegion &g = b->regions[r.region_first + i];
+                if (g.kind != H264GPU_REGION_DYN || g.mb_x1 <= g.mb_x0 || g.mb_y1 <= g.mb_y0) continue;
+                size_t z = (size_t)r.dyn_info_off + g.dyn_base + (size_t)(g.mb_x1 - g.mb_x0) * (size_t)(g.mb_y1 - g.mb_y0);
+                R.info.add(r.dyn_info_off, z < b->n_dyn_info ? z : b->n_dyn_info);
+            }
+            const uint32_t id = b->desc[f].dyn_id;
+            if (id != H264GPU_NO_DYN) {
+                const H264GpuDynDesc &y = b->dyn[id];
+                R.dyn.add(id, (size_t)id + 1);
+                R.tab.add(y.table_off, y.table_off + y.n_mbs + 1);
+                R.pay.add(y.payload_off, y.payload_off + y.payload_bytes);
+            }
+        }
+        return R;
+    };
+    auto up = [&](size_t dev_off, const void *src, size_t item, size_t i0, size_t i1, cudaStream_t st) -> cudaError_t {
+        if (i1 <= i0 || !src) return cudaSuccess;
+        return cudaMemcpyAsync(D + dev_off + item * i0, (const char *)src + item * i0, item * (i1 - i0), cudaMemcpyHostToDevice, st);
+    };
+
+    /* H264GPU_PIPE_DEBUG=1: device-side timeline of every chunk on stderr (experiments) */
+    static const bool dbg = getenv("H264GPU_PIPE_DEBUG") != nullptr;
+    static cudaEvent_t dbg_ev[PIPE_MAX_CHUNKS][4], dbg_t0;
+    static bool dbg_made = false;
+    if (dbg && !dbg_made) {
+        cudaEventCreate(&dbg_t0);
+        for (int i = 0; i < PIPE_MAX_CHUNKS; i++) for (int k = 0; k < 4; k++) cudaEventCreate(&dbg_ev[i][k]);
+        dbg_made = true;
+    }
+    size_t total = 0;
+    int rc = H264GPU_OK;
+    e = cudaMemsetAsync(D + o_pay + (b->payload_bytes & ~(size_t)3), 0, 32, g_pipe.st[0]);   /* the splice reads whole words (+ read-ahead) */
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_pipe.st[0]);
+    if (dbg) cudaEventRecord(dbg_t0, g_pipe.st[0]);
+    const auto h0 = std::chrono::steady_clock::now();
+    auto hms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); };
+    double h_enq[PIPE_MAX_CHUNKS] = {}, h_enq_done[PIPE_MAX_CHUNKS] = {}, h_ready[PIPE_MAX_CHUNKS] = {}, h_d2h[PIPE_MAX_CHUNKS] = {};
+    /* three role streams - upload, kernels, download - so that each copy engine works through one copy at a time in
+       chunk order (copies of several chunks in flight on one engine share its bandwidth and finish late).  The pack
+       kernel writes the chunk's frame offsets straight into pinned host memory (12 KB: not worth a copy that would
+       queue behind the previous chunk's stream on the download engine). */
+    cudaStream_t s_in = g_pipe.st[0], s_k = g_pipe.st[1], s_out = g_pipe.st[2];
+    if (e == cudaSuccess) e = up(o_desc, b->desc, sizeof(H264GpuFrameDesc), 0, n, s_in);
+    if (e == cudaSuccess) e = up(o_rd, b->rdesc, sizeof(H264GpuRasterDesc), 0, n, s_in);
+    if (e == cudaSuccess) e = up(o_reg, b->regions, sizeof(H264GpuRegion), 0, b->n_regions, s_in);
+    if (e == cudaSuccess) e = up(o_dyn, b->dyn, sizeof(H264GpuDynDesc), 0, (size_t)(b->n_dyn > 0 ? b->n_dyn : 0), s_in);
+    for (int c = 0; c < n_chunks + PIPE_LAG && e == cudaSuccess && rc == H264GPU_OK; c++) {
+        if (c < n_chunks) {
+            const int f0 = bounds[c], f1 = bounds[c + 1];
+            const ChunkRanges R = ranges_of(f0, f1);
+            if (dbg) { h_enq[c] = hms(); cudaEventRecord(dbg_ev[c][0], s_in); }
+            /* (every copy costs the upload engine tens of microseconds while the download engine is busy: the small
+               arrays went up whole in front of the loop, a chunk is three copies) */
+            e = up(o_info, b->dyn_info, sizeof(H264GpuMbHint), R.info.lo, R.info.hi, s_in);
+            if (e == cudaSuccess) e = up(o_tab, b->dyn_tab, sizeof(uint32_t), R.tab.lo, R.tab.hi, s_in);
+            if (e == cudaSuccess) e = up(o_pay, b->payload, 1, R.pay.lo, R.pay.hi, s_in);
+            if (e == cudaSuccess) e = cudaEventRecord(g_pipe.uploaded[c], s_in);
+            if (dbg) cudaEventRecord(dbg_ev[c][1], s_in);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, g_pipe.uploaded[c], 0);
+            if (e == cudaSuccess) e = h264scroll::launch_raster((const H264GpuRasterDesc *)(D + o_rd) + f0, f1 - f0, b->max_mbs_per_frame,
+                                                                (const H264GpuRegion *)(D + o_reg), (const H264GpuMbHint *)(D + o_info),
+                                                                (H264GpuMbHint *)(D + o_hint), s_k);
+            if (e == cudaSuccess) e = h264scroll::launch_compose((const H264GpuFrameDesc *)(D + o_desc) + f0, f1 - f0, (const H264GpuMbHint *)(D + o_hint),
+                                                                 (const H264GpuDynDesc *)(D + o_dyn), (const uint32_t *)(D + o_tab),
+                                                                 (const uint8_t *)(D + o_pay), (uint8_t *)(D + o_slots), (uint32_t *)(D + o_sz) + f0,
+                                                                 g_sm_count, s_k);
+            if (e == cudaSuccess) e = h264scroll::launch_pack((const H264GpuFrameDesc *)(D + o_desc) + f0, (const uint32_t *)(D + o_sz) + f0, f1 - f0,
+                                                              (const uint8_t *)(D + o_slots), (uint8_t *)(D + o_packed) + chunk_cap * c,
+                                                              (unsigned long long *)(pin_offs + (size_t)(chunk_frames + 1) * c), s_k);
+            g_launches.fetch_add(5);
+            if (e == cudaSuccess) e = cudaEventRecord(g_pipe.ready[c], s_k);
+            if (dbg) { cudaEventRecord(dbg_ev[c][2], s_k); h_enq_done[c] = hms(); }
+        }
+        const int d = c - PIPE_LAG;
+        if (d >= 0 && e == cudaSuccess) {
+            const int f0 = bounds[d], f1 = bounds[d + 1];
+            e = cudaEventSynchronize(g_pipe.ready[d]);
+            if (e != cudaSuccess) break;
+            if (dbg) h_ready[d] = hms();
+            const volatile uint64_t *lo = pin_offs + (size_t)(chunk_frames + 1) * d;
+            const size_t tot = (size_t)lo[f1 - f0];
+            for (int f = f0; f < f1; f++) h_offsets[f] = total + lo[f - f0];
+            if (total + tot > stream_cap) rc = fail(H264GPU_ERR_OVERFLOW, "the packed stream exceeds stream_cap");
+            if (rc == H264GPU_OK && tot)
+                e = cudaMemcpyAsync(h_stream + total, D + o_packed + chunk_cap * d, tot, cudaMemcpyDeviceToHost, s_out);
+            if (dbg) { cudaEventRecord(dbg_ev[d][3], s_out); h_d2h[d] = hms(); }
+            total += tot;
+            h_offsets[f1] = total;
+        }
+    }
+    /* the frames' own sizes (a frame that overflowed its slot reports more than the slot holds) */
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pin_sz, D + o_sz, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s_k);
+    cudaError_t e2 = cudaSuccess;
+    for (int i = 0; i < PIPE_STREAMS; i++) { cudaError_t t = cudaStreamSynchronize(g_pipe.st[i]); if (t != cudaSuccess) e2 = t; }
+    if (e == cudaSuccess && e2 == cudaSuccess) {
+        for (int f = 0; f < n; f++) {
+            if (pin_sz[f] > b->desc[f].out_cap && rc == H264GPU_OK) rc = fail(H264GPU_ERR_OVERFLOW, "a frame exceeded its output slot");
+            if (h_sizes) h_sizes[f] = pin_sz[f];
+        }
+    }
+    if (dbg && e == cudaSuccess && e2 == cudaSuccess) {
+        for (int c = 0; c < n_chunks; c++) {
+            float t[4];
+            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], dbg_t0, dbg_ev[c][k]);
+            fprintf(stderr, "chunk %2d: h2d %.3f..%.3f  kernels ..%.3f  d2h ..%.3f ms | host: enqueue %.3f..%.3f ready %.3f d2h enqueued %.3f\n",
+                    c, t[0], t[1], t[2], t[3], h_enq[c], h_enq_done[c], h_ready[c], h_d2h[c]);
+        }
+    }
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "pipelined compose", e);
+    if (e2 != cudaSuccess) return fail(H264GPU_ERR_CUDA, "pipelined compose (sync)", e2);
+    return rc;
 }
 
 #if defined(COMPOSE_TIMING) && COMPOSE_TIMING

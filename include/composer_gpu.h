@@ -196,6 +196,37 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
                          const uint8_t *h_payload, size_t payload_bytes,
                          uint8_t *h_out, size_t out_bytes, uint32_t *h_sizes);
 
+/*
+ * Host batch -> packed Annex-B stream, pipelined (the whole path behind composer_write_scroll_frames /
+ * a hinted batch, src/composer.c:255-264): the batch is cut into frame chunks; while chunk c is uploaded,
+ * chunk c-1 is rasterised, composed and packed and the stream of chunk c-2 is on its way back (PCIe is full
+ * duplex).  Every input array is indexed by the batch's own descriptors (absolute offsets); a chunk uploads
+ * the range of each array its frames refer to, so arrays laid out in frame order cross the bus exactly once
+ * (any other layout still works).  desc[f].out_off / out_cap describe
+ * device-side slots only (any non-overlapping 16-aligned layout); the result arrives packed:
+ *   h_stream   the frames' NAL units back to back in frame order, h_offsets[f] = first byte of frame f,
+ *              h_offsets[n_frames] = stream size (n_frames + 1 entries)
+ *   h_sizes    may be NULL; bytes per frame
+ * Host buffers should come from h264gpu_host_alloc (pinned): pageable memory works but does not overlap.
+ * Device and pinned scratch, streams and events are cached between calls.  n_chunks <= 0 picks a default.
+ * Returns H264GPU_ERR_OVERFLOW if a frame exceeded its slot or the stream exceeds stream_cap.
+ */
+typedef struct {
+    const H264GpuFrameDesc  *desc;     int    n_frames;
+    const H264GpuRasterDesc *rdesc;    /* n_frames */
+    const H264GpuRegion     *regions;  size_t n_regions;
+    const H264GpuMbHint     *dyn_info; size_t n_dyn_info;   /* may be NULL / 0 */
+    const H264GpuDynDesc    *dyn;      int    n_dyn;        /* may be NULL / 0 */
+    const uint32_t          *dyn_tab;  size_t n_tab;
+    const uint8_t           *payload;  size_t payload_bytes;
+    size_t n_hints;                    /* macroblocks the dense maps span (max hint_off + mb_w * mb_h) */
+    size_t slots_bytes;                /* bytes the output slots span (max out_off + out_cap)          */
+    int    max_mbs_per_frame;
+} H264GpuHostBatch;
+
+int h264gpu_compose_regions_host(const H264GpuHostBatch *batch, uint8_t *h_stream, size_t stream_cap,
+                                 uint64_t *h_offsets, uint32_t *h_sizes, int n_chunks);
+
 /* ---- slice rewrite (the reference's I-frame path) -------------------------
  *
  * h264_rewrite_idr_frame / h264_rewrite_as_non_idr_i_frame (src/h264_writer.c:242-350) for whole batches: every
