@@ -97,6 +97,32 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs of the NUMA node GPU `index` hangs off, BEFORE any pinned memory is allocated:
+    the end-to-end path moves ~0.5 GB per step per GPU through pinned host buffers, and with several ranks on a
+    two-socket host buffers on the wrong node cross the socket link twice.  Returns the node (or None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:                                             # noqa: BLE001
+        return None
+
+
 # --------------------------------------------------------------------------------------- reference arm
 
 def cpu_sample(po, streams=2, frames=8):
@@ -190,6 +216,7 @@ def main_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     gc = binding.GpuComposer(local)      # raises if the CUDA library or a B200 is missing: no fallback
     L = gc.lib
 
@@ -397,7 +424,7 @@ def main_ours(args):
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks) + (4 * n if e2e_step is e2e_step_capi else 0)), "ms_per_step": 1e3 * e2e_step_s,
-                    "chunks": n_chunks, "gpu_launches_per_step": e2e_launches,
+                    "chunks": n_chunks, "gpu_launches_per_step": e2e_launches, "host_numa_node": numa_node,
                     "path": ("pinned host region lists + payload -> H2D -> raster -> compose -> pack writes the Annex-B stream "
                              "into pinned host memory (D2H inside the kernel)" if zero_copy else
                              ("one h264gpu_compose_regions_host call: " if e2e_step is e2e_step_capi else "") +
@@ -604,6 +631,7 @@ def main():
     ap.add_argument("--slice-bytes", type=int, default=1382400)
     ap.add_argument("--e2e-zero-copy", action="store_true",
                     help="end-to-end path whose pack kernel writes into pinned host memory instead of a separate D2H copy")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not move the process to the GPU's NUMA node")
     ap.add_argument("--e2e-python", action="store_true", help="drive the end-to-end pipeline from Python (chunk by chunk) instead of the single C-ABI call")
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--e2e-lag", type=int, default=2, help="chunks in flight before the first packed chunk is fetched")
