@@ -43,6 +43,10 @@ constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
 constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
 constexpr u32 FULL = 0xFFFFFFFFu;
 constexpr int EG = 4;                    /* emit: 16-byte groups per thread per pass */
+#ifndef COMPOSE_PAYBUF16
+#define COMPOSE_PAYBUF16 1664            /* 16-byte chunks of staged payload per CTA (26 KB: a 25x25-MB region at ~300 bits per MB) */
+#endif
+constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
 constexpr int EPASS = EG * NT;           /* emit: groups per pass */
 static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
 
@@ -63,8 +67,17 @@ struct __align__(16) ComposeSmem {
         uint4 items[LCAP];               /* work queue (compose stages) */
         u32 gi[EPASS];                   /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
     };
-    u32 gpre[EPASS];                     /* emit: bytes inserted before a listed group */
-    unsigned short elist[EPASS];         /* emit: pass-local indices of the listed groups */
+    union {
+        struct {
+            u32 gpre[EPASS];             /* emit: bytes inserted before a listed group */
+            unsigned short elist[EPASS]; /* emit: pass-local indices of the listed groups */
+        };
+        uint4 paybuf[PAYBUF16];          /* the frame's pre-encoded payload, staged with cp.async at frame start and dead
+                                            by the time the frame's emit stage runs (an emit in the middle of a frame
+                                            invalidates it: pay_staged = 0, the splice reads global memory again) */
+    };
+    const u32 *pay_smem;                 /* payload word i of the frame = pay_smem[i] for i < pay_staged */
+    u32 pay_staged;
     u32 n_list;
     u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
     uint2 scan2[NW + 1];
@@ -142,6 +155,7 @@ __device__ __forceinline__ void cp_async8(u32 dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 /* geometry of a frame as the tile loop needs it */
@@ -234,11 +248,18 @@ __device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in)
 
 /* a group with insertions, the frame's last bytes, or one next to the slot's end: byte by byte */
 __device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w, u32 ins, int vb) {
-    const u32 ws[4] = {w.x, w.y, w.z, w.w};
-    for (int k = 0; k < vb; k++) {
-        if ((ins >> k) & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-        if (pos < cap) fout[pos] = (uint8_t)(ws[k >> 2] >> (24 - 8 * (k & 3)));
-        pos++;
+#pragma unroll 1
+    for (int j = 0; j < 4 && vb > 0; j++, vb -= 4) {         /* word by word: the group rotates through w.x (no indexed registers) */
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < vb) {
+                if (ins & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
+                if (pos < cap) fout[pos] = (uint8_t)(w.x >> (24 - 8 * k));
+                pos++;
+                ins >>= 1;
+            }
+        }
+        w.x = w.y; w.y = w.z; w.z = w.w;
     }
 }
 
@@ -458,12 +479,14 @@ __device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (
 
 /* the queue's consumer side: one lane per item.  Out of line: its loops get their own register allocation */
 __device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wbase, int num_refs) {
-    const u32 *pw = sm.pay_words;
-    const u32 n_words = sm.n_pay_words;
+    const u32 *pw = sm.pay_words, *ps = sm.pay_smem;
+    const u32 n_words = sm.n_pay_words, staged = sm.pay_staged;
     for (u32 i = threadIdx.x; i < n_round; i += NT) {
         const uint4 q = sm.items[i];
         Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
-        consume_item(it, sm.win, wbase, (u32)CH, num_refs, pw, n_words);
+        /* a spliced macroblock whose payload words (and the read-ahead word) are all staged reads shared memory */
+        const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
+        consume_item(it, sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
     }
 }
 
@@ -589,12 +612,28 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
                 pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
                 n_pay_words = (y1.y + 3u) >> 2;
-                /* the payload is first touched by the queue stage: have it on its way to L2 now */
-                for (u32 o = 128u * (u32)tid; o < 4u * n_pay_words; o += 128u * NT) prefetch_l2((const uint8_t *)pay_words + o);
             }
+            /* the payload goes to shared memory (whole 16-byte chunks of it; what does not fit, and the odd bytes at its
+               end, stay in global memory and are only sent on their way to L2): the splice then reads it at shared-memory
+               latency.  Its cp.async group is committed behind the group of this frame's first hint tile, so the tile
+               loop waits for "all but the last group" until the queue stage needs the payload */
+            u32 staged = 0;
+            const u32 *pay_smem = nullptr;
+            if (pay_words != nullptr && PAYBUF16 > 0) {
+                const uintptr_t a0 = (uintptr_t)pay_words & ~(uintptr_t)15;
+                const u32 w_skip = (u32)(((uintptr_t)pay_words - a0) >> 2);
+                const u32 n16 = min((w_skip + n_pay_words) >> 2, (u32)PAYBUF16);
+                const u32 dst = smem_u32(sm.paybuf);
+                for (u32 c = (u32)tid; c < n16; c += NT) cp_async16(dst + 16u * c, (const void *)(a0 + 16u * (uintptr_t)c));
+                staged = 4u * n16 > w_skip ? 4u * n16 - w_skip : 0u;
+                pay_smem = (const u32 *)sm.paybuf + w_skip;
+                for (u32 o = 16u * n16 + 128u * (u32)tid; o < 4u * (w_skip + n_pay_words); o += 128u * NT) prefetch_l2((const uint8_t *)a0 + o);
+            }
+            cp_async_commit();
             if (tid == 0) {                                    /* read again only after this frame's first barrier */
                 sm.zrun[0] = 0; sm.zrun[1] = 0;
                 sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
+                sm.pay_smem = pay_smem; sm.pay_staged = staged;
                 sm.cap = cap; sm.fout = out + out_off;
             }
         }
@@ -619,7 +658,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
             /* ---- stage: this tile's hints have landed ---------- */
             STAGE_MARK(7);                                      /* frame setup / loop glue */
-            cp_async_wait_all();
+            if (tile0) cp_async_wait_but_last(); else cp_async_wait_all();   /* (the payload's group may still be in flight) */
             __syncthreads();
             STAGE_MARK(0);                                      /* wait for the hint tile (and for the slowest warp of the tile before) */
 
@@ -736,6 +775,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 if (!tile0 && w_last - wbase >= (u32)CH && wf_al > wbase) {
                     __syncthreads();
                     const u32 src = wf_al - wbase;
+                    if (tid == 0) sm.pay_staged = 0;                       /* the emit stage reuses the payload buffer */
                     ins_total += emit_window(sm, wbase << 2, (int)(src << 2), ins_total, zpar);
                     zpar ^= 1u;
                     __syncthreads();                                       /* window consumed */
@@ -836,6 +876,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                         if (owns_trailer && slot < (u32)LCAP)
                             sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
                     }
+                    cp_async_wait_but_last();                              /* the staged payload has landed (the next hint tile may still be on its way) */
                     __syncthreads();
                     STAGE_MARK(6);                              /* queue: push + wait for the slowest writer */
                     consume_round(sm, min((u32)LCAP, total_items - r0), wbase, num_refs);
@@ -850,6 +891,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
                 const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
+                if (tid == 0) sm.pay_staged = 0;                               /* the emit stage reuses the payload buffer */
                 ins_total += emit_window(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
                 if (chunk_bytes > 0) zpar ^= 1u;
                 __syncthreads();                                               /* window fully consumed */

@@ -803,7 +803,7 @@ HSD void win_or64(u32 *win, u32 wbase, u32 wcap, u32 bit, u64 v, u32 n) {
 /* payload word wi as an MSB-first word (payload bytes are a bit stream: big-endian words) */
 HSD u32 pay_word(const u32 *pw, u32 n_words, u32 wi) {
 #if defined(__CUDA_ARCH__)
-    return wi < n_words ? __byte_perm(__ldg(pw + wi), 0u, 0x0123u) : 0u;
+    return wi < n_words ? __byte_perm(pw[wi], 0u, 0x0123u) : 0u;      /* (generic load: the payload may sit in shared memory) */
 #else
     return wi < n_words ? bswap32(pw[wi]) : 0u;
 #endif
@@ -811,7 +811,7 @@ HSD u32 pay_word(const u32 *pw, u32 n_words, u32 wi) {
 /* the same without the bounds check */
 HSD u32 pay_raw(const u32 *p) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(__ldg(p), 0u, 0x0123u);
+    return __byte_perm(*p, 0u, 0x0123u);
 #else
     return bswap32(*p);
 #endif
