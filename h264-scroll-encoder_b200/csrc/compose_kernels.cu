@@ -433,11 +433,26 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
         }
         __syncthreads();
         /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
-        for (u32 i = (u32)tid; i < nl; i += NT) {
-            const int gl = sm.elist[i], q = q0 + gl;
+        for (u32 i = (u32)tid; i < 4u * nl; i += NT) {        /* four lanes per group, a word each: the phase is as long as its longest lane */
+            const int gl = sm.elist[i >> 2], q = q0 + gl;
+            const u32 sub = i & 3u;
             const u32 gg = sm.gi[gl];
             if (roomy && gg == GI_CLEAN) continue;           /* turned out clean: stored above */
-            emit_bytes(fout, cap, chunk_byte0 + 16u * (u32)q + sm.gpre[gl], ((const uint4 *)sm.win)[q], gg >> 16, (int)((gg >> 8) & 0xFFu));
+            const u32 ins = gg >> 16;
+            const int vbs = (int)((gg >> 8) & 0xFFu) - 4 * (int)sub;           /* valid bytes from this word on */
+            if (vbs <= 0) continue;
+            const u32 wv = sm.win[4 * q + (int)sub];
+            u32 pos = chunk_byte0 + 16u * (u32)q + sm.gpre[gl] + 4u * sub + (u32)__popc(ins & ((1u << (4u * sub)) - 1u));
+            u32 is = ins >> (4u * sub);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < vbs) {
+                    if (is & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
+                    if (pos < cap) fout[pos] = (uint8_t)(wv >> (24 - 8 * k));
+                    pos++;
+                    is >>= 1;
+                }
+            }
         }
         ins_total += t0 + t1 + t2 + t3;
         if (q0 + EPASS < n_groups) __syncthreads();          /* list, counts and offsets are reused by the next pass (the caller

@@ -7,6 +7,7 @@ h264gpu_raster_regions, or by the numpy checker in oracle/pyoracle.py).
 All randomness is the splitmix64-style `mix(seed, a, b)` of Appendix B, so every consumer regenerates
 identical inputs from (config, stream, frame).
 """
+import os
 import numpy as np
 from . import abi
 
@@ -140,6 +141,8 @@ def dyn_region_payload(key, n_dyn):
     words = mix(0xBEEF, key, np.arange(n_words, dtype=np.uint64))
     pay = words.astype(">u8").view(np.uint8).copy()          # MSB-first bytes
     zero = np.nonzero(mix(0xD15C, key, j) % np.uint64(20) == 0)[0]
+    if os.environ.get("H264SCROLL_NO_ZERO_MBS"):              # experiments: how much the emulation-prevention slow path costs
+        zero = zero[:0]
     for z in zero:                                            # all-zero MBs force 00 00 0x sequences
         b0, b1 = int(tab[z]), int(tab[z + 1])
         y0, y1 = (b0 + 7) // 8, b1 // 8
