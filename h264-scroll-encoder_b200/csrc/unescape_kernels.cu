@@ -206,17 +206,21 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
         }
     }
     __syncthreads();
-    for (u32 i = (u32)tid; i < sm.n_list; i += UT) {
-        const int g = sm.list[i];
-        const int vb = min(chunk_bytes - 16 * g, 16);
-        const uint4 w = sm.data[g];
-        const u32 ws[4] = {w.x, w.y, w.z, w.w};
+    for (u32 i = (u32)tid; i < 4u * sm.n_list; i += UT) {   /* four lanes per group, a word each: the phase is as long as its longest lane */
+        const int g = sm.list[i >> 2];
+        const u32 sub = i & 3u;
+        const int vbs = min(chunk_bytes - 16 * g, 16) - 4 * (int)sub;    /* valid bytes from this word on */
+        if (vbs <= 0) continue;
+        const u32 wv = ((const u32 *)sm.data)[4 * g + (int)sub];
         const u32 rmg = sm.gi[g] >> 8;
-        u64 pos = byte0 + 16u * (u64)g - sm.gpre[g];
-        for (int k = 0; k < vb; k++) {
-            if ((rmg >> k) & 1u) continue;
-            if (pos < cap) dst[pos] = (uint8_t)(ws[k >> 2] >> (8 * (k & 3)));
-            pos++;
+        u64 pos = byte0 + 16u * (u64)g - sm.gpre[g] + 4u * sub - (u32)__popc(rmg & ((1u << (4u * sub)) - 1u));
+        u32 rs = rmg >> (4u * sub);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < vbs) {
+                if (!(rs & 1u)) { if (pos < cap) dst[pos] = (uint8_t)(wv >> (8 * k)); pos++; }
+                rs >>= 1;
+            }
         }
     }
     if (tid == 0 && byte0 + (u64)chunk_bytes >= d.src_bytes) sizes[nal] = (u32)(d.src_bytes - (base + t0 + t1 + t2 + t3));
