@@ -429,7 +429,7 @@ def main_ours(args):
                              "into pinned host memory (D2H inside the kernel)" if zero_copy else
                              ("one h264gpu_compose_regions_host call: " if e2e_step is e2e_step_capi else "") +
                              "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream")
-                            + ", in %d frame chunks over %d streams" % (n_chunks, len(streams))},
+                            + ", in %d frame chunks over %d streams" % (n_chunks, 3 if e2e_step is e2e_step_capi else len(streams))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "compose_frames_kernel",
                          "algorithmic_bytes_per_launch": int(b_alg), "bytes_per_mb": b_alg / total_mbs,
