@@ -45,9 +45,9 @@ def test_every_declared_symbol_is_exported(lib, header):
 
 def test_header_pod_sizes_match_numpy_mirrors():
     text = open(os.path.join(INC, "composer_gpu.h")).read()
-    src = '#include "composer_gpu.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu\\n",' \
+    src = '#include "composer_gpu.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(H264GpuMbHint),sizeof(H264GpuFrameDesc),sizeof(H264GpuDynDesc),sizeof(H264GpuRegion),' \
-          'sizeof(H264GpuRasterDesc));return 0;}\n'
+          'sizeof(H264GpuRasterDesc),sizeof(H264GpuHostBatch));return 0;}\n'
     import subprocess
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -55,7 +55,7 @@ def test_header_pod_sizes_match_numpy_mirrors():
         subprocess.run(["gcc", "-I" + INC, os.path.join(td, "s.c"), "-o", os.path.join(td, "s")], check=True)
         out = subprocess.run([os.path.join(td, "s")], capture_output=True, text=True, check=True).stdout.split()
     assert [int(x) for x in out] == [abi.HINT.itemsize, abi.FRAME_DESC.itemsize, abi.DYN_DESC.itemsize,
-                                     abi.REGION.itemsize, abi.RASTER_DESC.itemsize]
+                                     abi.REGION.itemsize, abi.RASTER_DESC.itemsize, C.sizeof(binding.HostBatch)]
     assert "extern \"C\"" in text
 
 
@@ -77,6 +77,11 @@ def test_no_cpu_fallback_without_a_device(lib):
     rc = lib.h264gpu_compose_host(desc.ctypes.data, 1, hints.ctypes.data, 4, None, 0, None, 0, None, 0,
                                   out.ctypes.data, out.size, sizes.ctypes.data)
     assert rc == -1
+    hb = binding.HostBatch()                            # the pipelined host-batch call refuses as well
+    hb.n_frames = 1
+    offs = np.zeros(2, np.uint64)
+    assert lib.h264gpu_compose_regions_host(C.byref(hb), out.ctypes.data, out.size, offs.ctypes.data, None, 0) == -1
+    assert not out.any()
     with pytest.raises(binding.GpuError):
         binding.GpuComposer(0)
     # the reference-shaped frame writer reports failure (0 bytes) instead of producing bytes on the CPU
