@@ -260,6 +260,16 @@ def main_ours(args):
     barrier()
     clocks = sampler.stop()
 
+    # ---- the rasteriser on its own: region lists -> dense hint maps, output-bound (8 B/MB written) ----
+    for _ in range(2):
+        gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
+    gc.check(L.h264gpu_event_record(ev0, None))
+    for _ in range(5):
+        gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
+    gc.check(L.h264gpu_event_record(ev1, None))
+    raster_ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / 5
+    raster_bytes = 8 * total_mbs + b.regions.nbytes + b.rdesc.nbytes + b.dyn_info.nbytes     # map written, lists and dyn-info read
+
     if hasattr(L, "h264gpu_debug_stage_cycles"):                  # timing-instrumented experiment build only
         cyc = (ctypes.c_uint64 * 16)()
         L.h264gpu_debug_stage_cycles(cyc)
@@ -435,6 +445,9 @@ def main_ours(args):
                          "algorithmic_bytes_per_launch": int(b_alg), "bytes_per_mb": b_alg / total_mbs,
                          "kernel_ms": ms / args.steps},
         }
+        line["raster"] = {"kernel": "raster_regions_kernel", "ms": raster_ms, "algorithmic_bytes": int(raster_bytes),
+                          "achieved": raster_bytes / (raster_ms * 1e-3) / 1e9, "unit": "GB/s",
+                          "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:

@@ -1083,42 +1083,93 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
 
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_MAX_REGIONS = H264GPU_MAX_REGIONS;
+#ifndef COMPOSE_RASTER_SUB
+#define COMPOSE_RASTER_SUB 2
+#endif
+constexpr int RASTER_SUB = COMPOSE_RASTER_SUB;
 
+/*
+ * A warp paints one row at a time: the regions that touch the row are found once (one region per lane, ballot),
+ * then every lane carries two neighbouring macroblocks through those regions in list order - a later region simply
+ * overwrites an earlier one, which is "later occludes earlier" - and stores them as one 16-byte word.  No division,
+ * no per-macroblock walk over regions that do not touch the row.
+ */
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_regions_kernel(const H264GpuRasterDesc *__restrict__ rdescs, int n_frames,
                       const H264GpuRegion *__restrict__ regions,
                       const H264GpuMbHint *__restrict__ dyn_info,
                       H264GpuMbHint *__restrict__ hints) {
+    constexpr int NWR = RASTER_THREADS / 32, NBLK = RASTER_MAX_REGIONS / 32;
     __shared__ uint4 s_reg[RASTER_MAX_REGIONS];
+    __shared__ u32 s_act[NWR][NBLK];
     const int f = blockIdx.x;
     if (f >= n_frames) return;
     const H264GpuRasterDesc rd = rdescs[f];
-    const int W = rd.mb_w, N = W * (int)rd.mb_h;
+    const int W = rd.mb_w, H = rd.mb_h;
     const int nreg = min((int)rd.region_count, RASTER_MAX_REGIONS);
+    const int nblk = (nreg + 31) >> 5;
     for (int r = threadIdx.x; r < nreg; r += RASTER_THREADS)
         s_reg[r] = __ldg((const uint4 *)(regions + rd.region_first) + r);
     __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2 *dst = (uint2 *)hints + rd.hint_off;
     const uint2 *dinfo = (const uint2 *)dyn_info + rd.dyn_info_off;
-    for (int g = blockIdx.y * RASTER_THREADS + threadIdx.x; g < N; g += gridDim.y * RASTER_THREADS) {
-        const int y = g / W, x = g - y * W;
-        uint2 h = make_uint2(0u, 0u);                      /* uncovered: (ref 0, mv 0) */
-        for (int r = nreg - 1; r >= 0; r--) {              /* later regions occlude earlier ones */
-            const uint4 q = s_reg[r];
-            const int x0 = (int16_t)(q.x & 0xFFFF), y0 = (int16_t)(q.x >> 16);
-            const int x1 = (int16_t)(q.y & 0xFFFF), y1 = (int16_t)(q.y >> 16);
-            if (x >= x0 && x < x1 && y >= y0 && y < y1) {
-                const u32 kind = (q.w >> 8) & 0xFFu;
-                if (kind == H264GPU_MB_INTER) h = make_uint2(q.z, q.w & 0xFFFFu);
-                else {
-                    const u32 local = (u32)((y - y0) * (x1 - x0) + (x - x0));
-                    h = __ldg(dinfo + (q.w >> 16) + local);
-                    h = make_uint2(canonical_hint_x(h.x, h.y), canonical_hint_y(h.y));
+    for (int y = blockIdx.y * NWR + warp; y < H; y += gridDim.y * NWR) {
+        for (int k = 0; k < nblk; k++) {                    /* which regions touch this row */
+            const int r = 32 * k + lane;
+            bool hit = false;
+            if (r < nreg) {
+                const uint4 q = s_reg[r];
+                hit = y >= (int16_t)(q.x >> 16) && y < (int16_t)(q.y >> 16) && (int16_t)(q.y & 0xFFFF) > (int16_t)(q.x & 0xFFFF);
+            }
+            const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (lane == 0) s_act[warp][k] = m;
+        }
+        __syncwarp();
+        const long long row0 = (long long)y * W;
+        for (int xb = 0; xb < W; xb += 64 * RASTER_SUB) {
+            /* RASTER_SUB runs of 64 macroblocks per pass (two per lane and run: a warp's stores stay contiguous) */
+            uint2 h[RASTER_SUB][2];
+#pragma unroll
+            for (int u = 0; u < RASTER_SUB; u++) { h[u][0] = make_uint2(0u, 0u); h[u][1] = make_uint2(0u, 0u); }   /* uncovered: (ref 0, mv 0) */
+            const int x = xb + 2 * lane;
+            for (int k = 0; k < nblk; k++) {
+                u32 m = s_act[warp][k];
+                while (m) {
+                    const uint4 q = s_reg[32 * k + __ffs((int)m) - 1];
+                    m &= m - 1u;
+                    const int x0 = (int16_t)(q.x & 0xFFFF), x1 = (int16_t)(q.y & 0xFFFF);
+                    if (((q.w >> 8) & 0xFFu) == H264GPU_MB_INTER) {
+                        const uint2 v = make_uint2(q.z, q.w & 0xFFFFu);
+#pragma unroll
+                        for (int u = 0; u < RASTER_SUB; u++) {
+                            const int xu = x + 64 * u;
+                            if (xu >= x0 && xu < x1) h[u][0] = v;
+                            if (xu + 1 >= x0 && xu + 1 < x1) h[u][1] = v;
+                        }
+                    } else {                                 /* per-macroblock hints of a spliced rectangle */
+                        const long long base = (long long)(q.w >> 16) + (long long)(y - (int16_t)(q.x >> 16)) * (x1 - x0) - x0;
+#pragma unroll
+                        for (int u = 0; u < RASTER_SUB; u++) {
+                            const int xu = x + 64 * u;
+                            if (xu >= x0 && xu < x1) { const uint2 d = __ldg(dinfo + base + xu); h[u][0] = make_uint2(canonical_hint_x(d.x, d.y), canonical_hint_y(d.y)); }
+                            if (xu + 1 >= x0 && xu + 1 < x1) { const uint2 d = __ldg(dinfo + base + xu + 1); h[u][1] = make_uint2(canonical_hint_x(d.x, d.y), canonical_hint_y(d.y)); }
+                        }
+                    }
                 }
-                break;
+            }
+#pragma unroll
+            for (int u = 0; u < RASTER_SUB; u++) {
+                const int xu = x + 64 * u;
+                const long long g = row0 + xu;
+                if (xu + 1 < W && !((rd.hint_off + g) & 1)) *(uint4 *)(dst + g) = make_uint4(h[u][0].x, h[u][0].y, h[u][1].x, h[u][1].y);
+                else {
+                    if (xu < W) dst[g] = h[u][0];
+                    if (xu + 1 < W) dst[g + 1] = h[u][1];
+                }
             }
         }
-        dst[g] = h;
+        __syncwarp();                                        /* the row's region masks are replaced next */
     }
 }
 
@@ -1260,9 +1311,10 @@ cudaError_t launch_raster(const H264GpuRasterDesc *d_rdesc, int n_frames, int ma
                           const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
                           H264GpuMbHint *d_hints, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    int bx = (max_mbs + RASTER_THREADS * 4 - 1) / (RASTER_THREADS * 4);
+    /* rows are dealt out to warps; frames are at most ~max_mbs rows tall, a CTA takes 16 rows per grid row */
+    int bx = (max_mbs + 16 * 120 - 1) / (16 * 120);
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
+    if (bx > 32) bx = 32;
     dim3 grid(n_frames, bx);
     raster_regions_kernel<<<grid, RASTER_THREADS, 0, stream>>>(d_rdesc, n_frames, d_regions, d_dyn_info, d_hints);
     return cudaGetLastError();
