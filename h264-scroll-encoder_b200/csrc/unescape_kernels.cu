@@ -195,8 +195,18 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
                 o32[2] = __byte_perm(w.z, w.w, sel);
                 const u32 o3 = __byte_perm(w.w, wn, sel);
                 if (next_plain) o32[3] = o3;
-                else for (u32 k = 0; k < 4u - s; k++) dst[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
-                if (!prev_plain) for (u32 k = 0; k < s; k++) dst[D + k] = (uint8_t)(w.x >> (8u * k));
+                else {                                       /* (1..3 bytes, no loop: the kernel is issue bound) */
+                    uint8_t *t = dst + D + s + 12u;
+                    t[0] = (uint8_t)o3;
+                    if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
+                    if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
+                }
+                if (!prev_plain) {
+                    uint8_t *h = dst + D;
+                    h[0] = (uint8_t)w.x;
+                    if (s > 1u) h[1] = (uint8_t)(w.x >> 8);
+                    if (s > 2u) h[2] = (uint8_t)(w.x >> 16);
+                }
             }
         } else {
             /* a removal inside, the payload's last partial group, or the end of the output buffer in reach: byte by byte,
