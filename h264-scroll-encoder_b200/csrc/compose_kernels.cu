@@ -427,8 +427,18 @@ __device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int ch
                 dst[2] = __byte_perm(w.z, w.w, sel);
                 const u32 o3 = __byte_perm(w.w, wn, sel);
                 if (next_clean) dst[3] = o3;
-                else for (u32 k = 0; k < 4u - s; k++) fout[D + s + 12u + k] = (uint8_t)(o3 >> (8u * k));
-                if (!prev_clean) for (u32 k = 0; k < s; k++) fout[D + k] = (uint8_t)(w.x >> (24u - 8u * k));
+                else {                                       /* (1..3 bytes, no loop) */
+                    uint8_t *t = fout + D + s + 12u;
+                    t[0] = (uint8_t)o3;
+                    if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
+                    if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
+                }
+                if (!prev_clean) {
+                    uint8_t *h = fout + D;
+                    h[0] = (uint8_t)(w.x >> 24);
+                    if (s > 1u) h[1] = (uint8_t)(w.x >> 16);
+                    if (s > 2u) h[2] = (uint8_t)(w.x >> 8);
+                }
             }
         }
         __syncthreads();
