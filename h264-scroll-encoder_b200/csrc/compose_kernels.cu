@@ -1046,12 +1046,35 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
         const u64 sb_first = d.src_start_bit + (a0 + 32u * (u64)w_first - p0);       /* (only meaningful when w_first < w_last) */
         const int sh = (int)(sb_first & 31u);
         const int k_off = (int)((sb_first >> 5) - src_w_lo) + (int)w_skip - w_first;  /* staged word of chunk word w: w + k_off */
-        for (int w = tid; w < CH + 8; w += NT) {
-            u32 v = 0u;
-            if (w >= w_first && w < w_last)
-                v = fshl(__byte_perm(stage[w + k_off], 0u, 0x0123u), __byte_perm(stage[w + k_off + 1], 0u, 0x0123u), sh);
-            else if (w < n_words) v = rewrite_word(d, hdr, src, n_src_words, a0 + 32u * (u64)w);
-            sm.win[w] = v;
+        /* four window words per thread and step: five staged words, each byte-swapped once, four funnel shifts, one
+           16-byte store; a group that touches the header or the end of the data goes word by word */
+        static_assert((CH + 8) % 4 == 0, "the window is built in groups of four words");
+        for (int w = 4 * tid; w < CH + 8; w += 4 * NT) {
+            if (w >= w_first && w + 4 <= w_last) {
+                /* the five staged words sit in two aligned 16-byte chunks (conflict-free loads); which five is the same
+                   for every thread: (w + k_off) & 3 does not depend on w */
+                const int b = w + k_off;
+                const uint4 A = ((const uint4 *)stage)[b >> 2], B = ((const uint4 *)stage)[(b >> 2) + 1];
+                u32 s0, s1, s2, s3, s4;
+                switch (b & 3) {
+                    case 0:  s0 = A.x; s1 = A.y; s2 = A.z; s3 = A.w; s4 = B.x; break;
+                    case 1:  s0 = A.y; s1 = A.z; s2 = A.w; s3 = B.x; s4 = B.y; break;
+                    case 2:  s0 = A.z; s1 = A.w; s2 = B.x; s3 = B.y; s4 = B.z; break;
+                    default: s0 = A.w; s1 = B.x; s2 = B.y; s3 = B.z; s4 = B.w; break;
+                }
+                s0 = __byte_perm(s0, 0u, 0x0123u); s1 = __byte_perm(s1, 0u, 0x0123u); s2 = __byte_perm(s2, 0u, 0x0123u);
+                s3 = __byte_perm(s3, 0u, 0x0123u); s4 = __byte_perm(s4, 0u, 0x0123u);
+                *(uint4 *)(sm.win + w) = make_uint4(fshl(s0, s1, sh), fshl(s1, s2, sh), fshl(s2, s3, sh), fshl(s3, s4, sh));
+            } else {
+#pragma unroll 1
+                for (int j = w; j < w + 4; j++) {
+                    u32 v = 0u;
+                    if (j >= w_first && j < w_last)
+                        v = fshl(__byte_perm(stage[j + k_off], 0u, 0x0123u), __byte_perm(stage[j + k_off + 1], 0u, 0x0123u), sh);
+                    else if (j < n_words) v = rewrite_word(d, hdr, src, n_src_words, a0 + 32u * (u64)j);
+                    sm.win[j] = v;
+                }
+            }
         }
     }
     /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47) ---- */
