@@ -999,8 +999,11 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
     __syncthreads();
     const int ticket = (int)sm.n_list;
     __syncthreads();
-    const int sl = ticket / max_chunks, c = ticket - sl * max_chunks;
-    if (sl >= n_slices) return;
+    /* tickets walk chunk-major over the slices (chunk c of every slice before chunk c + 1 of any): the CTAs in flight then
+       work on a few chunk indices of many slices, so a chunk's predecessors are long done - an inclusive look-back word
+       one or two steps back - instead of all being in flight with it */
+    const int c = ticket / n_slices, sl = ticket - c * n_slices;
+    if (c >= max_chunks) return;
     const H264GpuRewriteDesc d = descs[sl];
     const u64 total_bits = 40u + d.hdr_nbits + d.n_bits;
     const u64 total_bytes = (total_bits + 7u) >> 3;

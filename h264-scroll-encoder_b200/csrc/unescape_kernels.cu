@@ -105,8 +105,11 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
     if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_list = 0; }   /* chunks in launch order: everything below a ticket is running or done */
     __syncthreads();
     const int ticket = (int)sm.ticket;
-    const int nal = ticket / max_chunks, c = ticket - nal * max_chunks;
-    if (nal >= n_nals) return;
+    /* tickets walk chunk-major over the payloads (chunk c of every payload before chunk c + 1 of any): the CTAs in flight
+       then work on a few chunk indices of many payloads, so a chunk's predecessors are long done - an inclusive look-back
+       word one or two steps back - instead of all being in flight with it */
+    const int c = ticket / n_nals, nal = ticket - c * n_nals;
+    if (c >= max_chunks) return;
     const H264GpuUnescapeDesc d = descs[nal];
     const u64 byte0 = (u64)c * UCHUNK;
     if (byte0 >= d.src_bytes) return;
