@@ -1039,6 +1039,35 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
         }
     }
     cp_async_commit();
+    /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47): one warp looks them
+       up while the staging copies are in flight ---- */
+    if (tid < 32) {
+        u32 run = 0;
+        if (c > 0) {
+            u64 wi = byte0 / 4u;                             /* words before the chunk, newest first, 32 at a time */
+            bool open = true;
+            while (open && wi > 0) {
+                const u64 mine = wi > (u64)tid ? wi - 1u - (u64)tid : ~0ull;
+                u32 v = 0xFFFFFFFFu;
+                if (mine != ~0ull) {
+                    v = rewrite_word(d, hdr, src, n_src_words, 32u * mine);
+                    if (mine == 1u) v |= 0xFF000000u;        /* byte 4 (the NAL header) and the start code never take part */
+                    if (mine == 0u) v = 0xFFFFFFFFu;
+                }
+                const u32 nz = __ballot_sync(FULL, v != 0u);
+                if (nz) {
+                    const int l = __ffs((int)nz) - 1;        /* nearest word that holds a non-zero byte */
+                    const u32 vv = __shfl_sync(FULL, v, l);
+                    run += 4u * (u32)l + ((vv & 0xFFu) ? 0u : (vv & 0xFF00u) ? 1u : (vv & 0xFF0000u) ? 2u : 3u);
+                    open = false;
+                } else { run += 128u; wi = wi > 32u ? wi - 32u : 0u; }
+            }
+        }
+        if (tid == 0) {
+            sm.zrun[0] = run; sm.zrun[1] = 0; sm.n_list = 0;
+            sm.cap = d.out_cap; sm.fout = out + d.out_off;
+        }
+    }
     cp_async_wait_all();
     __syncthreads();
     {
@@ -1078,34 +1107,6 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
                     sm.win[j] = v;
                 }
             }
-        }
-    }
-    /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47) ---- */
-    if (tid < 32) {
-        u32 run = 0;
-        if (c > 0) {
-            u64 wi = byte0 / 4u;                             /* words before the chunk, newest first, 32 at a time */
-            bool open = true;
-            while (open && wi > 0) {
-                const u64 mine = wi > (u64)tid ? wi - 1u - (u64)tid : ~0ull;
-                u32 v = 0xFFFFFFFFu;
-                if (mine != ~0ull) {
-                    v = rewrite_word(d, hdr, src, n_src_words, 32u * mine);
-                    if (mine == 1u) v |= 0xFF000000u;        /* byte 4 (the NAL header) and the start code never take part */
-                    if (mine == 0u) v = 0xFFFFFFFFu;
-                }
-                const u32 nz = __ballot_sync(FULL, v != 0u);
-                if (nz) {
-                    const int l = __ffs((int)nz) - 1;        /* nearest word that holds a non-zero byte */
-                    const u32 vv = __shfl_sync(FULL, v, l);
-                    run += 4u * (u32)l + ((vv & 0xFFu) ? 0u : (vv & 0xFF00u) ? 1u : (vv & 0xFF0000u) ? 2u : 3u);
-                    open = false;
-                } else { run += 128u; wi = wi > 32u ? wi - 32u : 0u; }
-            }
-        }
-        if (tid == 0) {
-            sm.zrun[0] = run; sm.zrun[1] = 0; sm.n_list = 0;
-            sm.cap = d.out_cap; sm.fout = out + d.out_off;
         }
     }
     __syncthreads();
