@@ -197,3 +197,14 @@ def test_config5_full_size_properties(gpu, po, oracle):
         want = helpers.checker_frame(oracle, b, hints, int(f))
         got = stream[int(offs[f]):int(offs[f + 1])]
         assert np.array_equal(got, want), "frame %d" % f
+
+
+@pytest.mark.parametrize("w,h,seed", [(120, 68, 1), (120, 68, 2), (120, 68, 3), (240, 135, 4), (96, 200, 5), (64, 64, 6)])
+def test_multi_tile_frames_that_outgrow_the_window(gpu, po, oracle, w, h, seed):
+    """Several tiles per frame, queue items carried from tile to tile, and frames larger than one 32 KB window (the
+    window is emitted in the middle of the frame, in front of a tile or in the middle of one)."""
+    b = workloads.make_random(w, h, 2, seed=900 + seed, num_refs=2, p_dyn=0.5, n_regions=24, zero_payload_pct=5)
+    hints = helpers.dense_hints(po, b)
+    want = [helpers.checker_frame(oracle, b, hints, f) for f in range(b.n_frames)]
+    assert max(len(x) for x in want) > 20000
+    _compare(gpu, po, oracle, b, hints)
