@@ -318,7 +318,7 @@ cudaError_t pipe_setup(size_t dev_bytes, size_t pin_bytes) {
         for (int i = 0; i < PIPE_STREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&g_pipe.st[i], cudaStreamNonBlocking);
         for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.ready[i], cudaEventDisableTiming);
         for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.uploaded[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) { pipe_release(); return e; }      /* (nothing half-made is kept) */
         g_pipe.made = true;
     }
     if (dev_bytes > g_pipe.dev_cap) {
@@ -339,11 +339,9 @@ cudaError_t pipe_setup(size_t dev_bytes, size_t pin_bytes) {
 }
 
 void pipe_release() {
-    if (g_pipe.made) {
-        for (int i = 0; i < PIPE_STREAMS; i++) if (g_pipe.st[i]) cudaStreamDestroy(g_pipe.st[i]);
-        for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.ready[i]) cudaEventDestroy(g_pipe.ready[i]);
-        for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.uploaded[i]) cudaEventDestroy(g_pipe.uploaded[i]);
-    }
+    for (int i = 0; i < PIPE_STREAMS; i++) if (g_pipe.st[i]) cudaStreamDestroy(g_pipe.st[i]);
+    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.ready[i]) cudaEventDestroy(g_pipe.ready[i]);
+    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.uploaded[i]) cudaEventDestroy(g_pipe.uploaded[i]);
     if (g_pipe.dev) cudaFree(g_pipe.dev);
     if (g_pipe.pin) cudaFreeHost(g_pipe.pin);
     g_pipe = Pipe();
