@@ -208,3 +208,26 @@ def test_multi_tile_frames_that_outgrow_the_window(gpu, po, oracle, w, h, seed):
     want = [helpers.checker_frame(oracle, b, hints, f) for f in range(b.n_frames)]
     assert max(len(x) for x in want) > 20000
     _compare(gpu, po, oracle, b, hints)
+
+
+@pytest.mark.parametrize("flags", [0, abi.SKIP_SPEC | abi.PRED_SPEC])
+def test_nothing_is_written_outside_a_frames_bytes(gpu, po, oracle, flags):
+    """Canaries: the kernel stores whole 16-byte groups where it can; no byte of a slot behind the frame's last byte, and
+    no byte of the arena outside the slots, may change (compute-sanitizer is not available on the GPU pool)."""
+    b = workloads.make_random(77, 41, 6, seed=31 + flags, num_refs=3, flags=flags, p_dyn=0.3, n_regions=18, zero_payload_pct=20)
+    hints = helpers.dense_hints(po, b)
+    d_desc, d_h = gpu.to_device(b.desc), gpu.to_device(hints)
+    d_dyn, d_tab = gpu.to_device(b.dyn), gpu.to_device(b.dyn_tab)
+    d_pay = gpu.to_device(np.concatenate([b.payload, np.zeros(16, np.uint8)]))
+    arena = b.slot_cap * b.n_frames + 4096
+    d_out, d_sizes = gpu.alloc(arena), gpu.alloc(4 * b.n_frames)
+    gpu.check(gpu.lib.h264gpu_memset(d_out.ptr, 0xAA, arena, None))
+    gpu.compose_batch(d_desc, b.n_frames, d_h, d_dyn, d_tab, d_pay, d_out, d_sizes)
+    gpu.sync()
+    out, sizes = d_out.download(np.uint8), d_sizes.download(np.uint32)
+    for f in range(b.n_frames):
+        o, n = int(b.desc["out_off"][f]), int(sizes[f])
+        want = helpers.checker_frame(oracle, b, hints, f)
+        assert n == len(want) and np.array_equal(out[o:o + n], want)
+        assert (out[o + n:o + b.slot_cap] == 0xAA).all(), "frame %d wrote behind its last byte" % f
+    assert (out[b.slot_cap * b.n_frames:] == 0xAA).all()
