@@ -237,6 +237,10 @@ class GpuComposer:
         sizes = d_sizes.download(np.uint32, count=n)
         out = d_out.download(np.uint8)
         res = [out[int(d["out_off"]):int(d["out_off"]) + min(int(s), int(d["out_cap"]))].copy() for d, s in zip(desc, sizes)]
+        for d, s in zip(desc, sizes):                    # canaries: nothing behind a slice's last byte inside its slot
+            o, c = int(d["out_off"]), int(d["out_cap"])
+            if int(s) < c and not (out[o + int(s):o + c] == 0xAA).all():
+                raise GpuError("h264gpu_rewrite_slices wrote behind the end of a slice")
         for b_ in (d_desc, d_src, d_out, d_sizes, d_cnt):
             b_.free()
         return res, sizes
@@ -279,6 +283,10 @@ class GpuComposer:
         sizes = d_sizes.download(np.uint32, count=n)
         out = d_out.download(np.uint8)
         res = [out[int(d["out_off"]):int(d["out_off"]) + int(s)].copy() for d, s in zip(desc, sizes)]
+        for d, s in zip(desc, sizes):                    # canaries: nothing behind a payload's last byte inside its slot
+            o, c = int(d["out_off"]), int(d["out_cap"])
+            if int(s) < c and not (out[o + int(s):o + c] == 0xAA).all():
+                raise GpuError("h264gpu_unescape_nals wrote behind the end of a payload")
         for b_ in (d_desc, d_src, d_out, d_sizes, d_st):
             b_.free()
         return res
