@@ -1,162 +1,100 @@
 /*
  * compose_kernels.cu - sm_100a kernels of the P-slice composer.
  *
- * compose_frames_kernel (v4): one CTA composes one frame at a time (grid-stride over frames).
- * A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns one
- * segment, a tile is up to 256 consecutive segments.
+ * compose_frames_kernel (v7): a persistent CTA composes one frame after the other (grid-stride over frames) with two
+ * warp-specialised groups that run as a pipeline over double-buffered slice windows in shared memory:
  *
- *   stage    the hints of the tile plus the row above it are copied global -> shared with
- *            16-byte cp.async into a swizzled layout (every thread later reads its own 64 bytes
- *            with conflict-free 128-bit loads); the copy of the next tile - of the next frame
- *            when this one ends - is in flight while the current tile is composed
- *   decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test,
- *            mvd, closed-form Exp-Golomb -> a <= 32-bit code + length in registers.  Where a whole
- *            warp sits in uniform motion the constant code is taken instead
- *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
- *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
- *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
- *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word
- *            integer (picked per warp), shifts it to its slice bit offset and stores whole words;
- *            partial first/last words of neighbouring threads are merged by shuffle
- *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice
- *            trailer - becomes 16-byte work items that are spread over all lanes of the CTA:
- *            one lane splices one pre-encoded MB (copy_bits, src/h264_writer.c:228) with funnel
- *            shifts, whole words as plain stores, edge words with shared-memory atomicOr
- *   emit     emulation prevention (src/nal.c:24-50) on 16-byte groups: zero-byte masks,
- *            a bit-parallel run-parity rule, prefix sum of the insert counts; groups
- *            without insertions leave as re-aligned 32-bit words (one byte-permute each)
+ *   CODER warps  (hints -> bits)   A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns
+ *                one segment, a tile is up to NC consecutive segments.
+ *     stage    the hints of the tile plus the row above it are copied global -> shared into a swizzled layout
+ *              (conflict-free 128-bit reads for threads that each own 64 bytes); the copy of the next tile - of the
+ *              next frame when this one ends - is in flight while the current tile is composed.  The frame's
+ *              payload bit-offset table arrives by one bulk copy through the TMA unit (cp.async.bulk + mbarrier),
+ *              the payload itself is pulled into L2 by a bulk prefetch.
+ *     decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test, mvd, closed-form
+ *              Exp-Golomb -> a <= 32-bit code + length in registers; the constant code where a whole warp sits in
+ *              uniform motion (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
+ *     skiprun  SPEC mode only: group prefix-max of "last coded MB" -> mb_skip_run prefixes
+ *     scan     group prefix sum of the threads' bit counts -> slice bit offsets
+ *     write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word integer, shifts it
+ *              to its slice bit offset and stores whole words into the window; partial first/last words of neighbouring
+ *              threads are merged by shuffle
+ *     push     everything else - spliced MBs, long codes, separately prefixed codes, the slice trailer - becomes a
+ *              16-byte work item in the window's queue
+ *     hand-over  when the frame ends (or the window / the queue is full) the window goes to the packer warps through an
+ *              mbarrier and the coders go on in the other window
  *
- * The Annex-B start code, the NAL header byte and the host-written slice header are
- * the first bits of the same bit string, so the window image is the output image.
+ *   PACKER warps (bits -> Annex-B bytes)
+ *     splice   one lane per item: a pre-encoded MB is copied from the payload with funnel shifts (copy_bits,
+ *              src/h264_writer.c:228), whole words as plain stores, edge words with shared-memory atomicOr
+ *     emit     emulation prevention (src/nal.c:24-50) on 16-byte groups: zero-byte masks, a bit-parallel run-parity
+ *              rule, one prefix sum of the insert counts per pass; groups without insertions leave as re-aligned
+ *              32/128-bit words, groups with insertions byte-wise by a whole warp (one byte per lane)
+ *     clear    the window is zeroed with one st.bulk and handed back
+ *
+ * The Annex-B start code, the NAL header byte and the host-written slice header are the first bits of the same bit
+ * string, so the window image is the output image.
  */
 #include <cuda_runtime.h>
 #include "mb_codec.cuh"
+#include "kernel_util.cuh"
 #include "compose_kernels.cuh"
 
 namespace h264scroll {
 
-constexpr int NT = COMPOSE_THREADS;      /* threads per CTA */
-constexpr int MPT = 8;                   /* macroblocks per segment / thread */
-constexpr int NW = NT / 32;
-constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass */
-constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
-constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
+constexpr int NT = COMPOSE_THREADS;          /* threads per CTA */
+constexpr int NC = COMPOSE_CODER_THREADS;    /* coder threads (warps 0 .. NC/32-1) */
+constexpr int NP = NT - NC;                  /* packer threads */
+constexpr int MPT = 8;                       /* macroblocks per segment / coder thread */
+constexpr int NWC = NC / 32, NWP = NP / 32;
+constexpr int CH = COMPOSE_WINDOW_WORDS;     /* window: slice words staged per buffer */
+constexpr int LCAP = COMPOSE_ITEM_SLOTS;     /* queue items per window hand-over */
+constexpr int HBS = COMPOSE_HINT_SLOTS;      /* 64-byte segment slots per staged hint tile */
+constexpr int TABCAP = COMPOSE_TAB_WORDS;    /* staged entries of the frame's payload bit-offset table */
 constexpr u32 FULL = 0xFFFFFFFFu;
-constexpr int EG = 4;                    /* emit: 16-byte groups per thread per pass */
-#ifndef COMPOSE_PAYBUF16
-#define COMPOSE_PAYBUF16 1664            /* 16-byte chunks of staged payload per CTA (26 KB: a 25x25-MB region at ~300 bits per MB) */
-#endif
-constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
-constexpr int EPASS = EG * NT;           /* emit: groups per pass */
-static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
+constexpr int EG = 4;                        /* emit: 16-byte groups per packer thread per pass */
+constexpr int EPASS = EG * NP;               /* emit: groups per pass */
+constexpr int BAR_CODER = 1, BAR_PACKER = 2; /* named barriers of the two groups */
+static_assert(NC % 64 == 0 && NP % 32 == 0 && NP >= 32, "group sizes");
+static_assert(NWC <= 32 && NWP <= 32, "a warp scans the group's warp totals");
+static_assert(CH % 4 == 0 && TABCAP % 4 == 0, "16-byte granules");
 
-#ifndef COMPOSE_TIMING
-#define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
-#endif
-#if COMPOSE_TIMING
-__device__ unsigned long long g_stage_cycles[8];
-#define STAGE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); stage_acc[i] += t_ - stage_t; stage_t = t_; } } while (0)
-#else
-#define STAGE_MARK(i) do { } while (0)
-#endif
+/* hand-over flags */
+#define SLOT_EMIT   1u     /* emit window bytes [0, chunk_bytes) after splicing, then clear the window */
+#define SLOT_FIRST  2u     /* the frame's first emit: the emulation-prevention state starts over */
+#define SLOT_LAST   4u     /* the frame's last emit: write sizes[f] */
+#define SLOT_EXIT   8u     /* no more work */
 
-struct __align__(16) ComposeSmem {
-    u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
-    uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks) */
-    union {
-        uint4 items[LCAP];               /* work queue (compose stages) */
-        u32 gi[EPASS];                   /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
-    };
-    union {
-        struct {
-            u32 gpre[EPASS];             /* emit: bytes inserted before a listed group */
-            unsigned short elist[EPASS]; /* emit: pass-local indices of the listed groups */
-        };
-        uint4 paybuf[PAYBUF16];          /* the frame's pre-encoded payload, staged with cp.async at frame start and dead
-                                            by the time the frame's emit stage runs (an emit in the middle of a frame
-                                            invalidates it: pay_staged = 0, the splice reads global memory again) */
-    };
-    const u32 *pay_smem;                 /* payload word i of the frame = pay_smem[i] for i < pay_staged */
-    u32 pay_staged;
-    u32 n_list;
-    u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
-    uint2 scan2[NW + 1];
-    u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
-    u32 n_items[2];                      /* queued items, double buffered per tile */
-    /* per-frame constants only the queue and emit stages need: kept out of the register file */
-    const u32 *tab;                      /* the frame's payload bit-offset table */
-    const u32 *pay_words;                /* the frame's payload */
+struct SlotMeta {
+    uint8_t *fout;               /* the frame's output slot */
+    const u32 *pay_words;        /* the frame's payload */
+    u32 *size_ptr;               /* &sizes[f] */
     u32 n_pay_words;
-    u32 cap;                             /* output slot capacity */
-    uint8_t *fout;                       /* output slot */
+    u32 cap;                     /* output slot capacity */
+    u32 buf;                     /* which window */
+    u32 n_items;
+    u32 flags;
+    u32 wbase;                   /* frame word held by window word 0 */
+    u32 chunk_bytes;             /* bytes to emit (frame bytes [4 * wbase, 4 * wbase + chunk_bytes)) */
+    u32 clear_words;             /* window words the coders may have written */
+    u32 carry;                   /* != 0: window words [carry, carry + 4) go on in the other window (OR-ed into its first four) */
+    u32 total_bytes;             /* SLOT_LAST: RBSP-side size of the frame's NAL unit (before insertions) */
+    int num_refs;
 };
 
-/*
- * Exclusive prefix sum over the CTA; every thread gets its offset and the total.  One barrier:
- * consecutive scans must alternate between the two s_scan buffers.
- */
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_scan, u32 &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
-    const u32 wsum = lane < NW ? s_scan[lane] : 0u;    /* every warp scans the NW warp totals itself */
-    u32 winc = wsum;
-#pragma unroll
-    for (int d = 1; d < NW; d <<= 1) {
-        u32 t = __shfl_up_sync(FULL, winc, d);
-        if (lane >= d) winc += t;
-    }
-    const u32 wexc = __shfl_sync(FULL, winc - wsum, warp);
-    total = __shfl_sync(FULL, winc, NW - 1);
-    return wexc + inc - v;
-}
-
-/* exclusive prefix max over the CTA (identity -1 as int); `total` = max over all threads */
-__device__ __noinline__ int block_excl_scan_max(int v, int *s_scan, int &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc = max(inc, t);
-    }
-    if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
-    const int wv = lane < NW ? s_scan[lane] : -1;
-    int winc = wv;
-#pragma unroll
-    for (int d = 1; d < NW; d <<= 1) {
-        int t = __shfl_up_sync(FULL, winc, d);
-        if (lane >= d) winc = max(winc, t);
-    }
-    int wexc = __shfl_up_sync(FULL, winc, 1);
-    if (lane == 0) wexc = -1;
-    wexc = __shfl_sync(FULL, wexc, warp);
-    total = __shfl_sync(FULL, winc, NW - 1);
-    int exc = __shfl_up_sync(FULL, inc, 1);
-    if (lane == 0) exc = -1;
-    return max(wexc, exc);
-}
-
-/* ---- asynchronous global -> shared copies ---------------------------------------------- */
-
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(u32 dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(u32 dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+struct __align__(128) ComposeSmem {
+    u32 win[2][CH + 8];                  /* slice words [wbase, wbase + CH) of a frame, MSB first (+ read-ahead pad); zero where unwritten */
+    uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks) */
+    uint4 items[2][LCAP];                /* work queues, one per hand-over slot */
+    u32 tab[TABCAP];                     /* the frame's payload bit-offset table (bulk copy) */
+    SlotMeta meta[2];
+    u64 full[2], empty[2];               /* hand-over ring: coders -> packers, packers -> coders */
+    u64 tab_full;
+    u32 scan[2][NWC + 1];                /* coders: double buffered, one barrier per group scan */
+    uint2 escan[2][NWP + 1];             /* packers: the emit stage's scan */
+    u32 tile_items[2];                   /* coders: items of the current / next tile */
+    u32 zrun_out;                        /* packers: zero bytes closing the bytes emitted so far (rbsp_to_ebsp state) */
+};
 
 /* geometry of a frame as the tile loop needs it */
 struct FrameGeo {
@@ -178,7 +116,7 @@ __device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict_
     g.H = (int)(d3.z >> 16);
     g.tpr = (g.W + MPT - 1) / MPT;
     g.n_seg = g.tpr * g.H;
-    g.seg_max = min(NT, HBS - g.tpr - 1);
+    g.seg_max = min(NC, HBS - g.tpr - 1);
     g.tpr_magic = 0xFFFFFFFFu / (u32)g.tpr + 1u;
     return g;
 }
@@ -190,12 +128,12 @@ __device__ __forceinline__ int seg_row(const FrameGeo &g, int s) {
 /*
  * Stage the hints of segments [s0 - tpr - 1, s0 + n) into buf: slot q holds segment s0 - tpr - 1 + q
  * (8 hints, the tail of a row's last segment stays unwritten), chunks swizzled.  Segments before the
- * frame's first are filled with the "unavailable" hint.
+ * frame's first are filled with the "unavailable" hint.  Called by the coder threads (ctid = 0 .. NC-1).
  */
 /* frames whose width is not a multiple of 8 macroblocks: chunk by chunk, with its row and column (rare: out of line) */
 __device__ __noinline__ void stage_hints_ragged(uint4 *buf, const uint2 *fh, int W, int tpr, u32 tpr_magic, int n_seg, int s_base, int n_chunks) {
     const u32 buf_s = smem_u32(buf);
-    for (int c = threadIdx.x; c < n_chunks; c += NT) {
+    for (int c = threadIdx.x; c < n_chunks; c += NC) {
         const u32 pc = hint_swizzle((u32)c);
         const int s = s_base + (c >> 2);
         if (s < 0) { buf[pc] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL); continue; }
@@ -210,28 +148,31 @@ __device__ __noinline__ void stage_hints_ragged(uint4 *buf, const uint2 *fh, int
     }
 }
 
-__device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s0, int n) {
-    const int s_base = s0 - g.tpr - 1;
-    const int n_chunks = 4 * (n + g.tpr + 1);
-    if ((g.W & 7) == 0) {
+/* (out of line: one copy of the copy loop in the instruction stream, whoever calls it) */
+__device__ __noinline__ void stage_hints_tile(uint4 *buf, const uint2 *fh, int W, int tpr, u32 tpr_magic, int n_seg, int s0, int n) {
+    const int s_base = s0 - tpr - 1;
+    const int n_chunks = 4 * (n + tpr + 1);
+    if ((W & 7) == 0) {
         /* segments tile the dense map exactly: chunk c of the tile is chunk 4 * s_base + c of the map.  A thread's
-           chunks are NT apart, which leaves the swizzle term unchanged: one address each side, then fixed strides */
+           chunks are NC apart, which leaves the swizzle term unchanged: one address each side, then fixed strides */
         const int tid = threadIdx.x;
         const u32 dst = smem_u32(buf) + 16u * hint_swizzle((u32)tid);
         uint4 *dst_g = buf + hint_swizzle((u32)tid);
-        const uint4 *src = (const uint4 *)g.fh + (4 * (long long)s_base + tid);
+        const uint4 *src = (const uint4 *)fh + (4 * (long long)s_base + tid);
         const int c_lo = -4 * s_base;                        /* first chunk inside the frame */
-        const u32 c_span = (u32)(4 * g.n_seg);               /* chunks of the frame */
-        static_assert(NT % 64 == 0, "the swizzle term must not change between a thread's chunks");
+        const u32 c_span = (u32)(4 * n_seg);                 /* chunks of the frame */
 #pragma unroll
-        for (int i = 0; i < (HBS * 4 + NT - 1) / NT; i++) {
-            const int c = tid + i * NT;
+        for (int i = 0; i < (HBS * 4 + NC - 1) / NC; i++) {
+            const int c = tid + i * NC;
             if (c < n_chunks) {
-                if ((u32)(c - c_lo) < c_span) cp_async16(dst + 16u * (u32)(i * NT), src + i * NT);
-                else if (c < c_lo) dst_g[i * NT] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
+                if ((u32)(c - c_lo) < c_span) cp_async16(dst + 16u * (u32)(i * NC), src + i * NC);
+                else if (c < c_lo) dst_g[i * NC] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
             }
         }
-    } else stage_hints_ragged(buf, g.fh, g.W, g.tpr, g.tpr_magic, g.n_seg, s_base, n_chunks);
+    } else stage_hints_ragged(buf, fh, W, tpr, tpr_magic, n_seg, s_base, n_chunks);
+}
+__device__ __forceinline__ void stage_hints(uint4 *buf, const FrameGeo &g, int s0, int n) {
+    stage_hints_tile(buf, g.fh, g.W, g.tpr, g.tpr_magic, g.n_seg, s0, n);
 }
 
 /* hint i (0..7) of slot q / 16-byte chunk of a staged tile */
@@ -243,53 +184,13 @@ __device__ __forceinline__ uint4 staged_chunk(const uint4 *buf, int q, int sub) 
     return buf[hint_swizzle((u32)(4 * q + sub))];
 }
 
+/* ===================================================================== packer side */
+
 /* out of line: the backward scan is rare */
 __device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in) { return zeros_before(win, b, zrun_in); }
 
-/* a group with insertions, the frame's last bytes, or one next to the slot's end: byte by byte */
-__device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w, u32 ins, int vb) {
-#pragma unroll 1
-    for (int j = 0; j < 4 && vb > 0; j++, vb -= 4) {         /* word by word: the group rotates through w.x (no indexed registers) */
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (k < vb) {
-                if (ins & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                if (pos < cap) fout[pos] = (uint8_t)(w.x >> (24 - 8 * k));
-                pos++;
-                ins >>= 1;
-            }
-        }
-        w.x = w.y; w.y = w.z; w.z = w.w;
-    }
-}
-
-/* exclusive prefix sums of two words of packed 16-bit counters over the CTA (one barrier; alternate the buffers) */
-__device__ __forceinline__ void block_excl_scan_x2(u32 &lo, u32 &hi, uint2 *s_scan, u32 &tot_lo, u32 &tot_hi) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 il = lo, ih = hi;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const u32 a = __shfl_up_sync(FULL, il, d), b = __shfl_up_sync(FULL, ih, d);
-        if (lane >= d) { il += a; ih += b; }
-    }
-    if (lane == 31) s_scan[warp] = make_uint2(il, ih);
-    __syncthreads();
-    const uint2 ws = lane < NW ? s_scan[lane] : make_uint2(0u, 0u);
-    u32 wl = ws.x, wh = ws.y;
-#pragma unroll
-    for (int d = 1; d < NW; d <<= 1) {
-        const u32 a = __shfl_up_sync(FULL, wl, d), b = __shfl_up_sync(FULL, wh, d);
-        if (lane >= d) { wl += a; wh += b; }
-    }
-    const u32 el = __shfl_sync(FULL, wl - ws.x, warp), eh = __shfl_sync(FULL, wh - ws.y, warp);
-    tot_lo = __shfl_sync(FULL, wl, NW - 1);
-    tot_hi = __shfl_sync(FULL, wh, NW - 1);
-    lo = el + il - lo;
-    hi = eh + ih - hi;
-}
-
 /* exact insert mask of group q of the window (src/nal.c:24-50 in closed form) */
-__device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, int vb, u32 chunk_byte0, u32 zrun_in) {
+__device__ __noinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, int vb, u32 chunk_byte0, u32 zrun_in) {
     const u32 valid = (1u << vb) - 1u;
     u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
     u32 keep = valid;
@@ -303,173 +204,163 @@ __device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w,
     return epb_group_mask(z, m3 & keep, vb, rin);
 }
 
-constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without insertions: ins << 16 | valid bytes << 8 | count */
-
 /*
- * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from
- * chunk_byte0 on).  Returns the bytes inserted; leaves the closing zero run in sm.zrun[zpar ^ 1].
- * A pass covers EG 16-byte groups per thread:
- *   classify  a group that holds a zero byte (or starts with a byte <= 3 behind one), the frame's last
- *             partial group, everything next to the slot's end -> list; all other groups are clean
- *   masks     one lane per listed group: exact insert mask + count
- *   offsets   prefix sum of the counts (packed 16-bit fields, one scan for the EG rounds)
- *   store     clean groups leave as aligned or re-aligned 32/128-bit words; the listed groups that
- *             do insert (or are partial) go byte by byte, again one lane per group
- * Called by all threads after a barrier; the caller puts one behind it.
+ * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from chunk_byte0 on).
+ * Returns the bytes inserted; leaves the closing zero run in sm.zrun_out (read it behind a packer barrier).
+ * Called by all packer threads behind a packer barrier.  A pass covers EG 16-byte groups per thread (thread t owns
+ * groups t, t + NP, ... of the pass: neighbouring lanes hold neighbouring groups):
+ *   masks     the owner computes the exact insert mask of a group that holds a zero byte or starts with a byte <= 3
+ *             behind one; every other group inserts nothing
+ *   offsets   one prefix sum of the counts over the group (packed 16-bit fields, EG rounds at once)
+ *   store     a full group without insertions leaves as aligned or re-aligned 32/128-bit words (the word it shares
+ *             with a neighbour is a whole-word store when that neighbour - known by shuffle - is of the same kind);
+ *             groups that insert, the frame's last partial group and everything next to the slot's end go byte-wise,
+ *             one byte per lane, a warp per group
  */
-/* decoupled look-back over the chunks of one slice (slice rewrite): state word = flag << 30 | count; flag 1 = the
-   chunk's own insertions, 2 = inclusive sum over the slice so far.  Returns the insertions before chunk c. */
-__device__ __forceinline__ u32 chunk_lookback(volatile u32 *state, int c, u32 mine) {
-    if (c == 0) { state[0] = (2u << 30) | mine; return 0u; }
-    state[c] = (1u << 30) | mine;
-    __threadfence();
-    u32 sum = 0;
-    for (int p = c - 1;; ) {
-        const u32 v = state[p];
-        if ((v >> 30) == 0u) continue;                       /* not published yet: the chunk is running (tickets are taken in order) */
-        sum += v & 0x3FFFFFFFu;
-        if ((v >> 30) == 2u || p == 0) break;
-        p--;
-    }
-    state[c] = (2u << 30) | (sum + mine);
-    return sum;
-}
-
-__device__ __noinline__ u32 emit_window(ComposeSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar,
-                                        volatile u32 *lookback = nullptr, int lookback_c = 0) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const u32 zrun_in = sm.zrun[zpar];
-    const u32 cap = sm.cap;
-    uint8_t *fout = sm.fout;
+__device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int ptid, u32 chunk_byte0, int chunk_bytes,
+                                        u32 ins_total, u32 zrun_in, u32 cap, uint8_t *fout) {
+    const int lane = ptid & 31, pw = ptid >> 5;
     u32 *fout32 = (u32 *)fout;
     const u32 ins_in = ins_total;
     const int n_groups = (chunk_bytes + 15) >> 4;
-    for (int q0 = 0; q0 < n_groups; q0 += EPASS) {
+    u32 par = 0;
+    for (int q0 = 0; q0 < n_groups; q0 += EPASS, par ^= 1u) {
         /* even with an insertion after every second byte the pass stays clear of the slot's end */
-        /* (slice rewrite: the insertions before the chunk are not known yet - at most one per two bytes) */
-        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) +
-                           (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
-        /* ---- classify ---- */
-#pragma unroll 1                                             /* (code size matters more than the loop overhead) */
-        for (int r = 0; r < EG; r++) {
-            const int gl = tid + NT * r, q = q0 + gl;
-            const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
-            bool slow = false;
-            if (vb > 0) {
-                const uint4 w = ((const uint4 *)sm.win)[q];
-                const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                               ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-                slow = (hz & 0x80808080u) != 0u || vb < 16 || !roomy;
-                if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
-                /* the holder of the window's last byte hands the zero run to the next window */
-                if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
-            }
-            sm.gi[gl] = (u32)vb << 8;
-            const u32 m = __ballot_sync(FULL, slow);
-            if (m) {
-                u32 base = 0;
-                if (lane == 0) base = atomicAdd(&sm.n_list, (u32)__popc(m));
-                base = __shfl_sync(FULL, base, 0);
-                if (slow) sm.elist[base + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)gl;
-            }
-        }
-        __syncthreads();
-        const u32 nl = sm.n_list;
-        /* ---- masks ---- */
-        for (u32 i = (u32)tid; i < nl; i += NT) {
-            const int gl = sm.elist[i], q = q0 + gl;
-            const int vb = min(chunk_bytes - 16 * q, 16);
-            const u32 ins = group_insert_mask(sm.win, q, ((const uint4 *)sm.win)[q], vb, chunk_byte0, zrun_in);
-            sm.gi[gl] = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
-        }
-        __syncthreads();
-        if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
-        /* ---- offsets ---- */
-        u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
-        u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
-        u32 tlo, thi;
-        block_excl_scan_x2(lo, hi, sm.scan2, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
-        const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
-        if (lookback) {
-            /* slice rewrite: where this chunk's bytes go depends on the insertions of the chunks before it (single pass
-               per chunk: EPASS groups).  One thread looks back, everybody picks the result up from shared memory */
-            if (tid == 0) sm.scan2[NW].x = chunk_lookback(lookback, lookback_c, t0 + t1 + t2 + t3);
-            __syncthreads();
-            ins_total = sm.scan2[NW].x;
-        }
-        /* ---- store: clean groups ---- */
-        u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
+        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) + ins_total + 4u <= cap;
+        u64 insw = 0;                                        /* the groups' insert masks, 16 bits each */
+        u64 cntw = 0;                                        /* ... and their insert counts */
 #pragma unroll 1
         for (int r = 0; r < EG; r++) {
-            const int gl = tid + NT * r, q = q0 + gl;
-            const u32 g = sm.gi[gl];
-            const u32 before = round_base + (((r & 2) ? hi : lo) >> (16 * (r & 1)) & 0xFFFFu);
-            round_base += ((r & 2) ? thi : tlo) >> (16 * (r & 1)) & 0xFFFFu;
-            if ((g >> 8) == 0u) continue;                    /* past the chunk */
-            if (!(roomy && g == GI_CLEAN)) { sm.gpre[gl] = before; continue; }
-            const u32 D = chunk_byte0 + 16u * (u32)q + before;         /* output byte of the group's first byte */
-            const uint4 w = ((const uint4 *)sm.win)[q];
-            const u32 s = (4u - (D & 3u)) & 3u;              /* source bytes before the first aligned word */
-            u32 *dst = fout32 + ((D + s) >> 2);
-            if (s == 0u) {
-                const uint4 o = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
-                                           __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
-                if ((D & 15u) == 0u) *(uint4 *)dst = o;
-                else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
-            } else {
-                /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
-                const bool prev_clean = gl > 0 && sm.gi[gl - 1] == GI_CLEAN;
-                const bool next_clean = gl < EPASS - 1 && sm.gi[gl + 1] == GI_CLEAN;
-                const u32 wn = sm.win[4 * q + 4];
-                const u32 sel = realign_selector(s);
-                dst[0] = __byte_perm(w.x, w.y, sel);
-                dst[1] = __byte_perm(w.y, w.z, sel);
-                dst[2] = __byte_perm(w.z, w.w, sel);
-                const u32 o3 = __byte_perm(w.w, wn, sel);
-                if (next_clean) dst[3] = o3;
-                else {                                       /* (1..3 bytes, no loop) */
-                    uint8_t *t = fout + D + s + 12u;
-                    t[0] = (uint8_t)o3;
-                    if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
-                    if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
+            const int q = q0 + r * NP + ptid;
+            const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+            u32 ins = 0u;
+            if (vb > 0) {
+                const uint4 w = ((const uint4 *)win)[q];
+                const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                               ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+                bool sus = (hz & 0x80808080u) != 0u;
+                if (!sus && (w.x >> 26) == 0u) sus = q == 0 || (win[4 * q - 1] & 0xFFu) == 0u;
+                if (sus) ins = group_insert_mask(win, q, w, vb, chunk_byte0, zrun_in);
+                /* the holder of the window's last byte hands the zero run to the next window */
+                if (16 * (q + 1) >= chunk_bytes) sm.zrun_out = zeros_before_win(win, (u32)chunk_bytes, zrun_in);
+            }
+            insw |= (u64)ins << (16 * r);
+            cntw |= (u64)__popc(ins) << (16 * r);
+        }
+        u32 lo = (u32)cntw, hi = (u32)(cntw >> 32);
+        u32 tlo, thi;
+        group_excl_scan_x2<NWP, BAR_PACKER>(lo, hi, sm.escan[par], pw, tlo, thi);
+        u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
+        const u64 exw = (u64)lo | ((u64)hi << 32), totw = (u64)tlo | ((u64)thi << 32);
+#pragma unroll 1
+        for (int r = 0; r < EG; r++) {
+            const int q = q0 + r * NP + ptid;
+            const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+            const u32 before = round_base + ((u32)(exw >> (16 * r)) & 0xFFFFu);
+            round_base += (u32)(totw >> (16 * r)) & 0xFFFFu;
+            const u32 ins = (u32)(insw >> (16 * r)) & 0xFFFFu;
+            const u32 D = chunk_byte0 + 16u * (u32)q + before;             /* output byte of the group's first byte */
+            const bool clean = vb == 16 && ins == 0u && roomy;
+            const bool up = __shfl_up_sync(FULL, clean, 1), dn = __shfl_down_sync(FULL, clean, 1);
+            if (clean) {
+                const uint4 w = ((const uint4 *)win)[q];
+                const u32 s = (4u - (D & 3u)) & 3u;          /* source bytes before the first aligned word */
+                u32 *dst = fout32 + ((D + s) >> 2);
+                if (s == 0u) {
+                    const uint4 o = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
+                                               __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
+                    if ((D & 15u) == 0u) *(uint4 *)dst = o;
+                    else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
+                } else {
+                    /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
+                    const bool prev_clean = lane > 0 && up, next_clean = lane < 31 && dn;
+                    const u32 wn = win[4 * q + 4];
+                    const u32 sel = realign_selector(s);
+                    dst[0] = __byte_perm(w.x, w.y, sel);
+                    dst[1] = __byte_perm(w.y, w.z, sel);
+                    dst[2] = __byte_perm(w.z, w.w, sel);
+                    const u32 o3 = __byte_perm(w.w, wn, sel);
+                    if (next_clean) dst[3] = o3;
+                    else {                                   /* (1..3 bytes, no loop) */
+                        uint8_t *t = fout + D + s + 12u;
+                        t[0] = (uint8_t)o3;
+                        if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
+                        if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
+                    }
+                    if (!prev_clean) {
+                        uint8_t *h = fout + D;
+                        h[0] = (uint8_t)(w.x >> 24);
+                        if (s > 1u) h[1] = (uint8_t)(w.x >> 16);
+                        if (s > 2u) h[2] = (uint8_t)(w.x >> 8);
+                    }
                 }
-                if (!prev_clean) {
-                    uint8_t *h = fout + D;
-                    h[0] = (uint8_t)(w.x >> 24);
-                    if (s > 1u) h[1] = (uint8_t)(w.x >> 16);
-                    if (s > 2u) h[2] = (uint8_t)(w.x >> 8);
+            }
+            /* the others: the whole warp takes them one after the other, a byte per lane */
+            u32 m = __ballot_sync(FULL, vb > 0 && !clean);
+            while (m) {
+                const int l = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const u32 Dl = __shfl_sync(FULL, D, l), il = __shfl_sync(FULL, ins, l);
+                const int vl = __shfl_sync(FULL, vb, l), ql = __shfl_sync(FULL, q, l);
+                if (lane < vl) {
+                    const u32 byte = (win[4 * ql + (lane >> 2)] >> (24 - 8 * (lane & 3))) & 0xFFu;
+                    const u32 pos = Dl + (u32)lane + (u32)__popc(il & ((2u << lane) - 1u));
+                    if ((il >> lane) & 1u) { if (pos - 1u < cap) fout[pos - 1u] = 3; }
+                    if (pos < cap) fout[pos] = (uint8_t)byte;
                 }
             }
         }
-        __syncthreads();
-        /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
-        for (u32 i = (u32)tid; i < 4u * nl; i += NT) {        /* four lanes per group, a word each: the phase is as long as its longest lane */
-            const int gl = sm.elist[i >> 2], q = q0 + gl;
-            const u32 sub = i & 3u;
-            const u32 gg = sm.gi[gl];
-            if (roomy && gg == GI_CLEAN) continue;           /* turned out clean: stored above */
-            const u32 ins = gg >> 16;
-            const int vbs = (int)((gg >> 8) & 0xFFu) - 4 * (int)sub;           /* valid bytes from this word on */
-            if (vbs <= 0) continue;
-            const u32 wv = sm.win[4 * q + (int)sub];
-            u32 pos = chunk_byte0 + 16u * (u32)q + sm.gpre[gl] + 4u * sub + (u32)__popc(ins & ((1u << (4u * sub)) - 1u));
-            u32 is = ins >> (4u * sub);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k < vbs) {
-                    if (is & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                    if (pos < cap) fout[pos] = (uint8_t)(wv >> (24 - 8 * k));
-                    pos++;
-                    is >>= 1;
-                }
-            }
-        }
-        ins_total += t0 + t1 + t2 + t3;
-        if (q0 + EPASS < n_groups) __syncthreads();          /* list, counts and offsets are reused by the next pass (the caller
-                                                                 puts a barrier behind the last one) */
+        ins_total += (tlo & 0xFFFFu) + (tlo >> 16) + (thi & 0xFFFFu) + (thi >> 16);
     }
     return ins_total - ins_in;
 }
+
+/* splice: one lane per queue item */
+__device__ __forceinline__ void packer_splice(const uint4 *items, u32 n_items, int ptid, u32 *win, u32 wbase, int num_refs,
+                                           const u32 *pw, u32 n_words) {
+    for (u32 i = (u32)ptid; i < n_items; i += NP) {
+        const uint4 q = items[i];
+        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
+        consume_item(it, win, wbase, (u32)CH, num_refs, pw, n_words);
+    }
+}
+
+/* the packer group: takes windows off the ring until it is told to leave */
+__device__ __forceinline__ void packer_main(ComposeSmem &sm, int ptid) {
+    u32 ins_total = 0;                 /* emulation-prevention bytes inserted so far in the current frame */
+    u32 zrun = 0;                      /* zero bytes closing what the frame has emitted so far */
+    for (int s = 0;; s++) {
+        mbar_wait(&sm.full[s & 1], (u32)(s >> 1) & 1u);
+        const SlotMeta &m = sm.meta[s & 1];
+        const u32 flags = m.flags;
+        if (flags & SLOT_EXIT) break;
+        u32 *win = sm.win[m.buf];
+        const u32 wbase = m.wbase;
+        packer_splice(sm.items[s & 1], m.n_items, ptid, win, wbase, m.num_refs, m.pay_words, m.n_pay_words);
+        if (flags & SLOT_EMIT) {
+            group_sync<BAR_PACKER, NP>();                    /* every spliced bit is in */
+            if (m.carry && ptid < 4) {                       /* the frame goes on in the other window */
+                const u32 c = win[m.carry + (u32)ptid];
+                if (c) atomicOr(&sm.win[m.buf ^ 1u][ptid], c);
+            }
+            if (flags & SLOT_FIRST) { ins_total = 0; zrun = 0; }
+            const u32 chunk_bytes = m.chunk_bytes;
+            ins_total += packer_emit(sm, win, ptid, wbase << 2, (int)chunk_bytes, ins_total, zrun, m.cap, m.fout);
+            group_sync<BAR_PACKER, NP>();                    /* window fully read */
+            if (chunk_bytes > 0u) zrun = sm.zrun_out;
+            const u32 cw = (m.clear_words + 3u) & ~3u;
+#if COMPOSE_BULK_CLEAR
+            if (ptid == 0 && cw) smem_zero_bulk(win, 4u * cw);
+#else
+            for (u32 i = (u32)ptid; i < cw / 4u; i += NP) ((uint4 *)win)[i] = make_uint4(0u, 0u, 0u, 0u);
+#endif
+            if ((flags & SLOT_LAST) && ptid == 0) *m.size_ptr = m.total_bytes + ins_total;
+        }
+        mbar_arrive(&sm.empty[s & 1]);
+    }
+}
+
+/* ===================================================================== coder side */
 
 /*
  * The concatenation path of a thread whose macroblocks are all MBK_SHORT / MBK_NONE: bits [O, O + Ls)
@@ -502,19 +393,6 @@ __device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (
     if (!s) H = 0u;
 }
 
-/* the queue's consumer side: one lane per item.  Out of line: its loops get their own register allocation */
-__device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wbase, int num_refs) {
-    const u32 *pw = sm.pay_words, *ps = sm.pay_smem;
-    const u32 n_words = sm.n_pay_words, staged = sm.pay_staged;
-    for (u32 i = threadIdx.x; i < n_round; i += NT) {
-        const uint4 q = sm.items[i];
-        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
-        /* a spliced macroblock whose payload words (and the read-ahead word) are all staged reads shared memory */
-        const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
-        consume_item(it, sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
-    }
-}
-
 /*
  * The 8 macroblocks of a segment -> codes, lengths, kinds (4 bits each).  GEN = 0 is the reference mode
  * (skip OFF, reference predictor) with everything mode dependent folded away; GEN = 1 takes the flags.
@@ -522,9 +400,9 @@ __device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wba
  * zero-mvd code; the vote keeps the warp on that path as long as no lane needs the predictor
  * (spliced macroblocks do not: their length comes from the offset table).
  */
-template <int GEN, int DUMMY>
-__device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const uint2 (&abv)[MPT + 2], int nmb, bool first, bool row0,
-                                              int num_refs, const u32 *__restrict__ tab, u32 (&code)[MPT], u32 (&len)[MPT],
+template <int GEN>
+__device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const uint2 (&abv)[MPT + 2], int nmb, bool row0,
+                                              int num_refs, const u32 *tab, u32 (&code)[MPT], u32 (&len)[MPT],
                                               int skip_spec_in = 0, int pred_spec_in = 0) {
     const int skip_spec = GEN ? skip_spec_in : 0, pred_spec = GEN ? pred_spec_in : 0;
     u32 kinds = 0;
@@ -553,8 +431,8 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
         }
         if (present && dyn) {
             const u32 di = h.y >> 16;
-            const u32 b0 = __ldg(tab + di);
-            len[k] = __ldg(tab + di + 1) - b0 + (skip_spec ? 0u : 1u);
+            const u32 b0 = tab[di];                          /* (generic loads: the table is staged in shared memory when it fits) */
+            len[k] = tab[di + 1] - b0 + (skip_spec ? 0u : 1u);
             code[k] = b0;
             kd = MBK_DYN;
         }
@@ -585,32 +463,30 @@ __device__ __forceinline__ int next_own_frame(const H264GpuFrameDesc *__restrict
     return f;
 }
 
+/* the coders' view of the hand-over ring (every coder thread tracks it identically) */
+struct Ring {
+    int slot;             /* the slot being filled */
+    int confirmed;        /* every slot up to here is known to be consumed */
+};
+__device__ __forceinline__ void ring_wait(ComposeSmem &sm, Ring &r, int s) {
+    if (s > r.confirmed) { mbar_wait(&sm.empty[s & 1], (u32)(s >> 1) & 1u); r.confirmed = s; }
+}
+
 template <bool SPEC>
-__global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
-compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
-                      const H264GpuMbHint *__restrict__ hints,
-                      const H264GpuDynDesc *__restrict__ dyns,
-                      const u32 *__restrict__ dyn_tab,
-                      const uint8_t *__restrict__ payload,
-                      uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+__device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264GpuFrameDesc *__restrict__ descs, int n_frames,
+                                           const H264GpuMbHint *__restrict__ hints,
+                                           const H264GpuDynDesc *__restrict__ dyns,
+                                           const u32 *__restrict__ dyn_tab,
+                                           const uint8_t *__restrict__ payload,
+                                           uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
+    const int tid = threadIdx.x, lane = tid & 31, gw = tid >> 5;
+    u32 spar = 0;                      /* which sm.scan buffer the next group scan uses */
+    u32 ipar = 0;                      /* which sm.tile_items counter the current tile uses */
+    Ring ring; ring.slot = 0; ring.confirmed = -1;
+    u32 buf = 0;                       /* the window being filled */
+    u32 items_used = 0;                /* items queued in the slot being filled */
+    u32 tab_par = 0;                   /* phase of sm.tab_full the next staged table completes */
 
-    int f = next_own_frame<SPEC>(descs, blockIdx.x, n_frames, (int)gridDim.x);
-    if (f >= n_frames) return;
-
-    {   /* the window is zero wherever nothing was written: cleared once here, then every flush clears what it used */
-        uint4 *w4 = (uint4 *)sm.win;
-        for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) { sm.n_items[0] = 0; sm.n_items[1] = 0; sm.n_list = 0; }
-    }
-    u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
-    u32 ipar = 0;                      /* which sm.n_items counter the current tile uses */
-
-#if COMPOSE_TIMING
-    long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
-#endif
     FrameGeo geo = load_geo(descs, f, hints);
     stage_hints(sm.hbuf, geo, 0, min(geo.seg_max, geo.n_seg));
     cp_async_commit();
@@ -619,61 +495,79 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         /* ---- frame setup: the descriptor is read by every thread (one broadcast line) ------ */
         const uint4 *dq = (const uint4 *)(descs + f);
         const uint4 d2 = __ldg(dq + 2), d3 = __ldg(dq + 3);
-        const u64 out_off = (u64)d2.z | ((u64)d2.w << 32);
-        const u32 cap = d3.x, dyn_id = d3.y;
+        const u32 dyn_id = d3.y;
         const int W = geo.W;
         const u32 hdr_total = 40u + (d3.w & 0xFFu);
         const int num_refs = (int)((d3.w >> 8) & 0xFFu);
         const int skip_spec = SPEC ? ((d3.w >> 16) & H264GPU_SKIP_SPEC) != 0 : 0;
         const int pred_spec = SPEC ? ((d3.w >> 16) & H264GPU_PRED_SPEC) != 0 : 0;
         const u32 nal_header = d3.w >> 24;
-        const u32 *tab = nullptr;
-        {
-            const u32 *pay_words = nullptr;
-            u32 n_pay_words = 0;
-            if (dyn_id != H264GPU_NO_DYN) {
-                const uint4 *yq = (const uint4 *)(dyns + dyn_id);
-                const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
-                tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
-                pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
-                n_pay_words = (y1.y + 3u) >> 2;
+        const u32 *tab = nullptr;          /* the frame's payload bit-offset table as decide reads it */
+        bool tab_staged = false;
+        if (dyn_id != H264GPU_NO_DYN) {
+            const uint4 *yq = (const uint4 *)(dyns + dyn_id);
+            const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
+            tab = dyn_tab + ((u64)y0.z | ((u64)y0.w << 32));
+            /* the table (n_mbs + 1 words) goes to shared memory with one bulk copy of the 16-byte chunks that hold it;
+               every coder is past its last read of the previous frame's table (they all arrived at that frame's last
+               scan barrier, which this thread has left) */
+            const uintptr_t a0 = (uintptr_t)tab & ~(uintptr_t)15;
+            const u32 t_skip = (u32)(((uintptr_t)tab - a0) >> 2);
+            const u32 t_bytes = (4u * (t_skip + y1.x + 1u) + 15u) & ~15u;
+            tab_staged = y1.x < (u32)(TABCAP - 4);
+            if (tab_staged) {
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&sm.tab_full, t_bytes);
+                    bulk_g2s(sm.tab, (const void *)a0, t_bytes, &sm.tab_full);
+                }
+                tab = sm.tab + t_skip;
             }
-            /* the payload goes to shared memory (whole 16-byte chunks of it; what does not fit, and the odd bytes at its
-               end, stay in global memory and are only sent on their way to L2): the splice then reads it at shared-memory
-               latency.  Its cp.async group is committed behind the group of this frame's first hint tile, so the tile
-               loop waits for "all but the last group" until the queue stage needs the payload */
-            u32 staged = 0;
-            const u32 *pay_smem = nullptr;
-            if (pay_words != nullptr && PAYBUF16 > 0) {
-                const uintptr_t a0 = (uintptr_t)pay_words & ~(uintptr_t)15;
-                const u32 w_skip = (u32)(((uintptr_t)pay_words - a0) >> 2);
-                const u32 n16 = min((w_skip + n_pay_words) >> 2, (u32)PAYBUF16);
-                const u32 dst = smem_u32(sm.paybuf);
-                for (u32 c = (u32)tid; c < n16; c += NT) cp_async16(dst + 16u * c, (const void *)(a0 + 16u * (uintptr_t)c));
-                staged = 4u * n16 > w_skip ? 4u * n16 - w_skip : 0u;
-                pay_smem = (const u32 *)sm.paybuf + w_skip;
-                for (u32 o = 16u * n16 + 128u * (u32)tid; o < 4u * (w_skip + n_pay_words); o += 128u * NT) prefetch_l2((const uint8_t *)a0 + o);
-            }
-            cp_async_commit();
-            if (tid == 0) {                                    /* read again only after this frame's first barrier */
-                sm.zrun[0] = 0; sm.zrun[1] = 0;
-                sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
-                sm.pay_smem = pay_smem; sm.pay_staged = staged;
-                sm.cap = cap; sm.fout = out + out_off;
+            /* the payload is read by the packers straight from L2: send it on its way there now */
+            if (tid == 32 && y1.y) {
+                const uintptr_t pa = (uintptr_t)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
+                const uintptr_t p0 = pa & ~(uintptr_t)15;
+                const u64 p_bytes = ((pa - p0) + (u64)y1.y + 15ull) & ~15ull;
+                bulk_prefetch_l2((const void *)p0, (u32)(p_bytes < (1ull << 20) ? p_bytes : (1ull << 20)));
             }
         }
         const int kc = (W - 1) & 7;                            /* position of a row's last MB inside its segment */
 
-        /* frame state every thread tracks identically (all of it follows from block-wide totals) */
+        /* frame state every thread tracks identically (all of it follows from group-wide totals) */
         u32 bitpos = hdr_total;        /* slice bits composed so far (incl. the 40-bit Annex-B prefix) */
         int last_coded = -1;           /* raster index of the last non-skipped MB */
-        u32 ins_total = 0;             /* emulation-prevention bytes inserted so far */
-        u32 zpar = 0;                  /* which sm.zrun slot holds the current state */
-        u32 wbase = 0;                 /* frame word held by window word 0; words below it have left for global memory */
+        u32 wbase = 0;                 /* frame word held by window word 0; words below it have left for the packers */
+        bool first_emit = true;
 
         const int f_next = next_own_frame<SPEC>(descs, f + (int)gridDim.x, n_frames, (int)gridDim.x);
         FrameGeo geo_next = geo;
         if (f_next < n_frames) geo_next = load_geo(descs, f_next, hints);
+
+        /* a window (+ its queue) goes to the packers; thread 0 reads the frame's constants again (they are not worth
+           registers in every thread).  Slots alternate between the windows except behind a splice-only hand-over, whose
+           completion the coders wait for: whoever fills slot s may touch its window and its queue once slot s - 2 is done */
+        auto hand_over = [&](u32 flags, u32 chunk_bytes, u32 clear_words, u32 total_bytes, u32 carry = 0u) {
+            if (tid == 0) {
+                SlotMeta &m = sm.meta[ring.slot & 1];
+                const uint4 e2 = __ldg(dq + 2), e3 = __ldg(dq + 3);
+                m.fout = out + ((u64)e2.z | ((u64)e2.w << 32)); m.cap = e3.x;
+                m.pay_words = nullptr; m.n_pay_words = 0;
+                if (e3.y != H264GPU_NO_DYN) {
+                    const uint4 *yq = (const uint4 *)(dyns + e3.y);
+                    const uint4 y0 = __ldg(yq), y1 = __ldg(yq + 1);
+                    m.pay_words = (const u32 *)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
+                    m.n_pay_words = (y1.y + 3u) >> 2;
+                }
+                m.size_ptr = sizes + f;
+                m.buf = buf; m.n_items = items_used; m.flags = flags;
+                m.wbase = wbase; m.chunk_bytes = chunk_bytes; m.clear_words = clear_words; m.total_bytes = total_bytes;
+                m.carry = carry; m.num_refs = num_refs;
+            }
+            mbar_arrive(&sm.full[ring.slot & 1]);
+            ring.slot++;
+            items_used = 0;
+        };
+        /* the window to fill and the queue of the slot to fill are free again */
+        auto acquire = [&]() { ring_wait(sm, ring, ring.slot - 2); };
 
         for (int s0 = 0; s0 < geo.n_seg;) {
             const int n = min(geo.seg_max, geo.n_seg - s0);
@@ -682,10 +576,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const uint4 *hb = sm.hbuf;
 
             /* ---- stage: this tile's hints have landed ---------- */
-            STAGE_MARK(7);                                      /* frame setup / loop glue */
-            if (tile0) cp_async_wait_but_last(); else cp_async_wait_all();   /* (the payload's group may still be in flight) */
-            __syncthreads();
-            STAGE_MARK(0);                                      /* wait for the hint tile (and for the slowest warp of the tile before) */
+            cp_async_wait_all();
+            group_sync<BAR_CODER, NC>();
+            if (tile0 && tab_staged) mbar_wait(&sm.tab_full, tab_par);
 
             /* ---- load: own segment, the one above, the hints beside them ------------------------ */
             const int s = s0 + tid;
@@ -727,10 +620,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             /* ---- decide + code ------------------------------------------------ */
             u32 code[MPT], len[MPT];
             u32 kinds;
-            if (!SPEC) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
-            else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
+            if (!SPEC) kinds = decide_segment<0>(own, abv, nmb, row == 0, num_refs, tab, code, len);
+            else kinds = decide_segment<1>(own, abv, nmb, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
 
-            STAGE_MARK(1);                                      /* load + decide */
             /* ---- mb_skip_run prefixes (SPEC skip; with skip OFF the constant bit is already in) ---- */
             int last_coded_total = last_coded;
             int prev0 = 0;
@@ -740,7 +632,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 for (int k = 0; k < MPT; k++)
                     if ((kinds >> (4 * k)) & 0xFu) lc = g0 + k;
                 int blk_max;
-                prev0 = max(block_excl_scan_max(lc, (int *)sm.scan[spar], blk_max), last_coded);
+                prev0 = max(group_excl_scan_max<NWC, BAR_CODER>(lc, (int *)sm.scan[spar], gw, blk_max), last_coded);
                 spar ^= 1u;
                 last_coded_total = max(blk_max, last_coded);
                 attach_runs(code, len, kinds, g0, prev0);
@@ -769,15 +661,14 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             }
             if (owns_trailer) n_it++;
             u32 ibase = 0;
-            if (n_it) ibase = atomicAdd(&sm.n_items[ipar], n_it);
+            if (n_it) ibase = atomicAdd(&sm.tile_items[ipar], n_it);
             const u32 L = Ls + (owns_trailer ? tr_len : 0u);
 
             /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
             u32 total;
-            const u32 O = bitpos + block_excl_scan(L, sm.scan[spar], total);
+            const u32 O = bitpos + group_excl_scan<NWC, BAR_CODER>(L, sm.scan[spar], gw, total);
             spar ^= 1u;
-            const u32 total_items = sm.n_items[ipar];
-            STAGE_MARK(2);                                      /* prefixes, bit counts, scan (incl. its barrier) */
+            const u32 total_items = sm.tile_items[ipar];
             /* ---- stage: everybody is past its loads from the hint tile: start the copy of the next one ---- */
             if (!last || f_next < n_frames) {
                 const FrameGeo &gn = last ? geo_next : geo;
@@ -785,7 +676,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
             }
             cp_async_commit();
-            if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
+            if (tid == 0) sm.tile_items[ipar ^ 1u] = 0;            /* the next tile's counter; nobody adds to it before the next barrier */
             const u32 E = O + L;
             const u32 end = bitpos + total;
             const u32 total_bytes = (end + 7u) >> 3;                       /* meaningful when last */
@@ -794,26 +685,30 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const u32 w_last = last ? (w_stop ? w_stop - 1u : 0u) : w_end; /* last word this tile writes to */
             const u32 warp_end = __shfl_sync(FULL, E, 31);
 
-            /* ---- the tile does not fit behind what the window already holds: send that off first ---- */
-            {
+            /* ---- the tile does not fit behind what the window (or its queue) already holds: send that off first ---- */
+            if (!tile0 && (w_last - wbase >= (u32)CH || items_used + total_items > (u32)LCAP)) {
                 const u32 wf_al = (bitpos >> 5) & ~3u;             /* 16-byte group of the tile's first word */
-                if (!tile0 && w_last - wbase >= (u32)CH && wf_al > wbase) {
-                    __syncthreads();
+                if (wf_al > wbase) {
+                    /* the window's whole groups leave; its last (up to four) words go on in the other window, which must be
+                       free by now.  The packers move them once the queued items are spliced (the last macroblocks of the tile
+                       before may be among them) - OR-ed in, as the tile's own writes to those words are */
                     const u32 src = wf_al - wbase;
-                    if (tid == 0) sm.pay_staged = 0;                       /* the emit stage reuses the payload buffer */
-                    ins_total += emit_window(sm, wbase << 2, (int)(src << 2), ins_total, zpar);
-                    zpar ^= 1u;
-                    __syncthreads();                                       /* window consumed */
-                    if (tid < 4) { const u32 c = sm.win[src + tid]; sm.win[src + tid] = 0u; sm.win[tid] = c; }
-                    uint4 *w4 = (uint4 *)sm.win;
-                    for (u32 i = 1u + (u32)tid; i < src / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+                    const u32 nb = buf ^ 1u;
+                    ring_wait(sm, ring, ring.slot - 1);
+                    hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u), src << 2, src + 4u, 0u, src);
+                    first_emit = false;
+                    buf = nb;
                     wbase = wf_al;
-                    __syncthreads();
-                    STAGE_MARK(5);
+                } else if (items_used) {
+                    /* nothing whole to emit yet, but the queue must be drained: splice only, and wait for it */
+                    hand_over(0u, 0u, 0u, 0u);
+                    ring_wait(sm, ring, ring.slot - 1);
                 }
             }
 
             for (;;) {
+                acquire();
+                u32 *win = sm.win[buf];
                 /* ---- header: start code, NAL header byte, slice header bits ---------- */
                 if (tile0 && tid < 10 && 32u * (u32)tid < hdr_total) {
                     const uint4 h0 = __ldg(dq), h1 = __ldg(dq + 1);
@@ -822,7 +717,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     u32 v = header_bits32(hdr, nal_header, 32u * (u32)tid);
                     const u32 left = hdr_total - 32u * (u32)tid;
                     if (left < 32u) v &= ~(FULL >> left);
-                    if ((u32)tid - wbase < (u32)CH && v) atomicOr(&sm.win[(u32)tid - wbase], v);
+                    if ((u32)tid - wbase < (u32)CH && v) atomicOr(&win[(u32)tid - wbase], v);
                 }
 
                 /* ---- write: concatenation path + merge of the partial words between threads ---------- */
@@ -832,9 +727,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     u32 H = 0u, T = 0u;
                     bool has_t = false;
                     const u32 lmax = __reduce_max_sync(FULL, Lc);
-                    if (lmax <= 64u) { if (Lc) simple_words<2>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
-                    else if (lmax <= 128u) { if (Lc) simple_words<4>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
-                    else { if (Lc) simple_words<8>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
+                    if (lmax <= 64u) { if (Lc) simple_words<2>(code, len, O, Lc, win, wbase, H, T, has_t); }
+                    else if (lmax <= 128u) { if (Lc) simple_words<4>(code, len, O, Lc, win, wbase, H, T, has_t); }
+                    else { if (Lc) simple_words<8>(code, len, O, Lc, win, wbase, H, T, has_t); }
                     const u32 key = O >> 5;
                     u32 tj = (Ec - 1u) >> 5;
                     if (!Lc) {
@@ -848,10 +743,10 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                         u32 v = T | __shfl_down_sync(FULL, H, 1);
                         if (lane == 31) v = T;
                         if (tj - wbase < (u32)CH) {
-                            if (lane == 31) atomicOr(&sm.win[tj - wbase], v);   /* the next warp's (or tile's) first head lands here */
-                            else sm.win[tj - wbase] = v;
+                            if (lane == 31) atomicOr(&win[tj - wbase], v);   /* the next warp's (or tile's) first head lands here */
+                            else win[tj - wbase] = v;
                         }
-                        if (lane == 0 && H != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], H);
+                        if (lane == 0 && H != 0u && key - wbase < (u32)CH) atomicOr(&win[key - wbase], H);
                     } else {
                         /* general case: segmented suffix OR of the heads that share a word */
                         u32 X = H;
@@ -866,19 +761,20 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                         if (has_t && tj - wbase < (u32)CH) {
                             u32 v = T;
                             if (lane < 31 && kn == tj) v |= Xn;
-                            if ((warp_end >> 5) == tj) atomicOr(&sm.win[tj - wbase], v);   /* later warps (or the next tile) add to this word */
-                            else sm.win[tj - wbase] = v;
+                            if ((warp_end >> 5) == tj) atomicOr(&win[tj - wbase], v);   /* later warps (or the next tile) add to this word */
+                            else win[tj - wbase] = v;
                         }
-                        if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&sm.win[key - wbase], X);
+                        if (lane == 0 && X != 0u && key - wbase < (u32)CH) atomicOr(&win[key - wbase], X);
                     }
                 }
 
-                STAGE_MARK(3);                                  /* stage next tile, header, concatenation path + merge */
-                /* ---- queue: items of this tile in rounds of LCAP, one lane per item ----------- */
-                for (u32 r0 = 0; r0 < total_items; r0 += (u32)LCAP) {
-                    if (r0) __syncthreads();                               /* the previous round is consumed */
-                    if (n_it && ibase < r0 + (u32)LCAP && ibase + n_it > r0) {
-                        u32 slot = ibase - r0, bit = O;
+                /* ---- push: this tile's items into the slot's queue; a tile with more items than the queue has room for
+                        goes in rounds, each sent ahead as a splice-only hand-over ----------- */
+                for (u32 r_lo = 0;;) {
+                    const u32 r_hi = min(total_items, r_lo + ((u32)LCAP - items_used));
+                    if (n_it && ibase < r_hi && ibase + n_it > r_lo) {
+                        uint4 *queue = sm.items[ring.slot & 1] + items_used;
+                        u32 idx = ibase, bit = O;
                         int prev = prev0;
                         if (cplx) {
 #pragma unroll
@@ -887,233 +783,101 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                                 if (len[k]) {
                                     const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
                                     prev = g0 + k;
-                                    if (slot < (u32)LCAP) {
+                                    if (idx - r_lo < r_hi - r_lo) {
                                         uint2 h = make_uint2(0u, 0u);
                                         if (kd == MBK_LONG) h = __ldg(geo.fh + g0 + k);   /* the staged tile is being replaced */
                                         const Item it = make_item(kd, code[k], len[k], bit, pre, h.x, h.y);
-                                        sm.items[slot] = make_uint4(it.x, it.y, it.z, it.w);
+                                        queue[idx - r_lo] = make_uint4(it.x, it.y, it.z, it.w);
                                     }
-                                    slot++;
+                                    idx++;
                                     bit += len[k];
                                 }
                             }
                         } else bit += Ls;
-                        if (owns_trailer && slot < (u32)LCAP)
-                            sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
+                        if (owns_trailer && idx - r_lo < r_hi - r_lo)
+                            queue[idx - r_lo] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
                     }
-                    cp_async_wait_but_last();                              /* the staged payload has landed (the next hint tile may still be on its way) */
-                    __syncthreads();
-                    STAGE_MARK(6);                              /* queue: push + wait for the slowest writer */
-                    consume_round(sm, min((u32)LCAP, total_items - r0), wbase, num_refs);
+                    items_used += r_hi - r_lo;
+                    if (r_hi >= total_items) break;
+                    hand_over(0u, 0u, 0u, 0u);                             /* (the same window goes on) */
+                    ring_wait(sm, ring, ring.slot - 1);
+                    r_lo = r_hi;
                 }
 
-                STAGE_MARK(4);                                  /* queue */
                 const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
                 if (!(last || !fits)) break;                               /* keep filling the window with the next tile */
 
-                /* ---- emit: emulation prevention + store of frame words [wbase, e_hi) --------- */
-                __syncthreads();
+                /* ---- the window is full or the frame ends: frame words [wbase, e_hi) go to the packers --------- */
                 const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
-                const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
-                if (tid == 0) sm.pay_staged = 0;                               /* the emit stage reuses the payload buffer */
-                ins_total += emit_window(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
-                if (chunk_bytes > 0) zpar ^= 1u;
-                __syncthreads();                                               /* window fully consumed */
-                {   /* clear the words this window used */
-                    const u32 used = min((u32)CH, w_last - wbase + 1u);
-                    uint4 *w4 = (uint4 *)sm.win;
-                    for (u32 i = (u32)tid; i < (used + 3u) / 4u; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                STAGE_MARK(5);                                  /* emit + window clear */
-                if (fits) break;                                               /* (frame done) */
-                wbase += CH;                                                   /* a full window has left; the tile goes on in the next one */
-                __syncthreads();
+                const u32 chunk_bytes = e_hi > wbase ? ((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0u;
+                hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u) | (fits ? SLOT_LAST : 0u), chunk_bytes,
+                          min((u32)CH, w_last - wbase + 1u), total_bytes);
+                first_emit = false;
+                buf ^= 1u;
+                if (fits) break;                                           /* (frame done) */
+                wbase += CH;                                               /* a full window has left; the tile goes on in the next one */
             }
 
             bitpos = end;
             last_coded = last_coded_total;
-            if (last && tid == 0) sizes[f] = total_bytes + ins_total;
             ipar ^= 1u;
             s0 += n;
         }
+        if (tab_staged) tab_par ^= 1u;
         f = f_next;
         geo = geo_next;
     }
     cp_async_wait_all();
-#if COMPOSE_TIMING
-    if (tid == 0)
-        for (int i = 0; i < 8; i++) atomicAdd(&g_stage_cycles[i], (unsigned long long)stage_acc[i]);
-#endif
+    /* tell the packers to leave */
+    ring_wait(sm, ring, ring.slot - 2);
+    if (tid == 0) sm.meta[ring.slot & 1].flags = SLOT_EXIT;
+    mbar_arrive(&sm.full[ring.slot & 1]);
 }
 
-#if COMPOSE_TIMING
-cudaError_t read_stage_cycles(unsigned long long *h8) {
-    cudaError_t e = cudaMemcpyFromSymbol(h8, g_stage_cycles, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof z);
-    return e;
-}
-#endif
+#include "coder_lean.cuh"
 
-/* ------------------------------------------------------- slice rewrite
- *
- * h264_rewrite_idr_frame / h264_rewrite_as_non_idr_i_frame (src/h264_writer.c:242-350) on the device: the NAL unit
- *     00 00 00 01 | nal_header | EBSP( new slice header bits | source RBSP bits [start, start + n) | zero padding )
- * i.e. copy_bits (src/h264_writer.c:228-240) over megabytes plus nal_write_unit (src/nal.c:52-84).  The byte string in
- * front of emulation prevention is cut into chunks of one window (32 KB); a CTA builds its chunk with funnel shifts
- * and runs the composer's emit stage on it.  Where a chunk's bytes go depends on the insertions in all chunks before
- * it, so the work is three launches: count per chunk, exclusive scan per slice, emit.
- */
-constexpr int RW_CHUNK_BYTES = CH * 4;
-
-__device__ __forceinline__ u32 rewrite_word(const H264GpuRewriteDesc &d, const u64 (&hdr)[4], const u32 *__restrict__ src,
-                                            u32 n_src_words, u64 a /* string bit of the word's first bit */) {
-    const u64 p0 = 40u + d.hdr_nbits, e = p0 + d.n_bits;
-    u32 v = 0u;
-    if (a < p0) {
-        v = header_bits32(hdr, d.nal_header, (u32)a);
-        if (a + 32u > p0) v &= ~(FULL >> (u32)(p0 - a));
-    }
-    if (a + 32u > p0 && a < e) {
-        u32 pv;
-        if (a >= p0) pv = pay_ld32(src, n_src_words, (u32)(d.src_start_bit + (a - p0)));
-        else pv = pay_ld32(src, n_src_words, (u32)d.src_start_bit) >> (u32)(p0 - a);
-        if (a + 32u > e) pv &= ~(FULL >> (u32)(e - a));
-        v |= pv;
-    }
-    return v;
-}
-
-static_assert(RW_CHUNK_BYTES / 16 <= EPASS, "a chunk must be one emit pass (the look-back sits inside the pass)");
-
+template <bool SPEC>
 __global__ void __launch_bounds__(NT, COMPOSE_MIN_CTAS)
-rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices, int max_chunks,
-                      const uint8_t *__restrict__ src_base, uint8_t *__restrict__ out, u32 *__restrict__ sizes,
-                      u32 *__restrict__ state /* [1 + n_slices * max_chunks], zeroed: ticket counter, then the look-back words */) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
+                      const H264GpuMbHint *__restrict__ hints,
+                      const H264GpuDynDesc *__restrict__ dyns,
+                      const u32 *__restrict__ dyn_tab,
+                      const uint8_t *__restrict__ payload,
+                      uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    /* chunks are handed out in launch order: whoever holds ticket k knows that every chunk below k is running or done */
-    if (tid == 0) sm.n_list = atomicAdd(state, 1u);
-    __syncthreads();
-    const int ticket = (int)sm.n_list;
-    __syncthreads();
-    /* tickets walk chunk-major over the slices (chunk c of every slice before chunk c + 1 of any): the CTAs in flight then
-       work on a few chunk indices of many slices, so a chunk's predecessors are long done - an inclusive look-back word
-       one or two steps back - instead of all being in flight with it */
-    const int c = ticket / n_slices, sl = ticket - c * n_slices;
-    if (c >= max_chunks) return;
-    const H264GpuRewriteDesc d = descs[sl];
-    const u64 total_bits = 40u + d.hdr_nbits + d.n_bits;
-    const u64 total_bytes = (total_bits + 7u) >> 3;
-    const u64 byte0 = (u64)c * RW_CHUNK_BYTES;
-    if (byte0 >= total_bytes) return;                        /* whole CTA */
-    const int chunk_bytes = (int)min((u64)RW_CHUNK_BYTES, total_bytes - byte0);
-    const u64 hdr[4] = {d.hdr_bits[0], d.hdr_bits[1], d.hdr_bits[2], d.hdr_bits[3]};
-    const u32 *src = (const u32 *)(src_base + d.src_off);
-    const u32 n_src_words = (u32)((d.src_bytes + 3u) >> 2);
-    /* ---- the chunk (plus the read-ahead pad of the emit stage) as MSB-first words ----
-       The source words the chunk needs are copied to shared memory first (16-byte cp.async, everything in flight at
-       once: the hint tile buffer is free in this kernel); a word that lies wholly in the copied macroblock data is then
-       one funnel shift of two staged words with the same shift for the whole chunk.  Words that touch the header or
-       the end of the data go the general way. */
-    const int n_words = (chunk_bytes + 3) >> 2;
-    const u64 p0 = 40u + d.hdr_nbits, e_bit = p0 + d.n_bits, a0 = 8u * byte0;
-    const u64 a_lo = a0 > p0 ? a0 : p0;                      /* first string bit of the chunk that is macroblock data */
-    u32 *stage = (u32 *)sm.hbuf;
-    constexpr int STAGE_WORDS = HBS * 16;
-    static_assert(STAGE_WORDS >= CH + 16, "the hint tile buffer must hold a chunk of source words");
-    const u64 sbit_lo = d.src_start_bit + (a_lo - p0);       /* source bit of string bit a_lo */
-    const u64 src_w_lo = sbit_lo >> 5;                       /* first source word needed */
-    const uintptr_t g_addr = ((uintptr_t)(src + src_w_lo)) & ~(uintptr_t)15;          /* 16-byte aligned start of the copy */
-    const u32 w_skip = (u32)(((uintptr_t)(src + src_w_lo) - g_addr) >> 2);             /* staged words in front of src_w_lo */
-    const bool any_data = a_lo < e_bit && a_lo < a0 + 32u * (u64)n_words;
-    if (any_data) {
-        const uintptr_t g_end = (uintptr_t)src + (((uintptr_t)d.src_bytes + 3u) & ~(uintptr_t)3) + 16u;   /* readable bytes end here */
-        const u32 s_base = smem_u32(stage);
-        for (int c16 = tid; c16 < (CH + 16) / 4; c16 += NT) {
-            const uintptr_t g = g_addr + 16u * (uintptr_t)c16;
-            if (g + 16u <= g_end) cp_async16(s_base + 16u * (u32)c16, (const void *)g);
-            else ((uint4 *)stage)[c16] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-    cp_async_commit();
-    /* ---- zero bytes right in front of the chunk (the state rbsp_to_ebsp would be in, src/nal.c:29-47): one warp looks them
-       up while the staging copies are in flight ---- */
-    if (tid < 32) {
-        u32 run = 0;
-        if (c > 0) {
-            u64 wi = byte0 / 4u;                             /* words before the chunk, newest first, 32 at a time */
-            bool open = true;
-            while (open && wi > 0) {
-                const u64 mine = wi > (u64)tid ? wi - 1u - (u64)tid : ~0ull;
-                u32 v = 0xFFFFFFFFu;
-                if (mine != ~0ull) {
-                    v = rewrite_word(d, hdr, src, n_src_words, 32u * mine);
-                    if (mine == 1u) v |= 0xFF000000u;        /* byte 4 (the NAL header) and the start code never take part */
-                    if (mine == 0u) v = 0xFFFFFFFFu;
-                }
-                const u32 nz = __ballot_sync(FULL, v != 0u);
-                if (nz) {
-                    const int l = __ffs((int)nz) - 1;        /* nearest word that holds a non-zero byte */
-                    const u32 vv = __shfl_sync(FULL, v, l);
-                    run += 4u * (u32)l + ((vv & 0xFFu) ? 0u : (vv & 0xFF00u) ? 1u : (vv & 0xFF0000u) ? 2u : 3u);
-                    open = false;
-                } else { run += 128u; wi = wi > 32u ? wi - 32u : 0u; }
-            }
-        }
+
+    const int f = next_own_frame<SPEC>(descs, blockIdx.x, n_frames, (int)gridDim.x);
+    if (f >= n_frames) return;                                 /* (the whole CTA) */
+
+    {   /* the windows are zero wherever nothing was written: cleared once here, then the packers clear what was used */
+        uint4 *w4 = (uint4 *)sm.win;
+        for (int i = tid; i < 2 * (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
         if (tid == 0) {
-            sm.zrun[0] = run; sm.zrun[1] = 0; sm.n_list = 0;
-            sm.cap = d.out_cap; sm.fout = out + d.out_off;
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    {
-        /* string bit a (>= p0) is source bit src_start_bit + a - p0: the word index moves with w, the shift does not.
-           Words [w_first, w_last) of the chunk lie wholly inside the copied data */
-        const int w_first = a0 >= p0 ? 0 : (int)((p0 - a0 + 31u) >> 5);
-        const int w_last = e_bit <= a0 ? 0 : (int)min((u64)n_words, (e_bit - a0) >> 5);
-        const u64 sb_first = d.src_start_bit + (a0 + 32u * (u64)w_first - p0);       /* (only meaningful when w_first < w_last) */
-        const int sh = (int)(sb_first & 31u);
-        const int k_off = (int)((sb_first >> 5) - src_w_lo) + (int)w_skip - w_first;  /* staged word of chunk word w: w + k_off */
-        /* four window words per thread and step: five staged words, each byte-swapped once, four funnel shifts, one
-           16-byte store; a group that touches the header or the end of the data goes word by word */
-        static_assert((CH + 8) % 4 == 0, "the window is built in groups of four words");
-        for (int w = 4 * tid; w < CH + 8; w += 4 * NT) {
-            if (w >= w_first && w + 4 <= w_last) {
-                /* the five staged words sit in two aligned 16-byte chunks (conflict-free loads); which five is the same
-                   for every thread: (w + k_off) & 3 does not depend on w */
-                const int b = w + k_off;
-                const uint4 A = ((const uint4 *)stage)[b >> 2], B = ((const uint4 *)stage)[(b >> 2) + 1];
-                u32 s0, s1, s2, s3, s4;
-                switch (b & 3) {
-                    case 0:  s0 = A.x; s1 = A.y; s2 = A.z; s3 = A.w; s4 = B.x; break;
-                    case 1:  s0 = A.y; s1 = A.z; s2 = A.w; s3 = B.x; s4 = B.y; break;
-                    case 2:  s0 = A.z; s1 = A.w; s2 = B.x; s3 = B.y; s4 = B.z; break;
-                    default: s0 = A.w; s1 = B.x; s2 = B.y; s3 = B.z; s4 = B.w; break;
-                }
-                s0 = __byte_perm(s0, 0u, 0x0123u); s1 = __byte_perm(s1, 0u, 0x0123u); s2 = __byte_perm(s2, 0u, 0x0123u);
-                s3 = __byte_perm(s3, 0u, 0x0123u); s4 = __byte_perm(s4, 0u, 0x0123u);
-                *(uint4 *)(sm.win + w) = make_uint4(fshl(s0, s1, sh), fshl(s1, s2, sh), fshl(s2, s3, sh), fshl(s3, s4, sh));
-            } else {
-#pragma unroll 1
-                for (int j = w; j < w + 4; j++) {
-                    u32 v = 0u;
-                    if (j >= w_first && j < w_last)
-                        v = fshl(__byte_perm(stage[j + k_off], 0u, 0x0123u), __byte_perm(stage[j + k_off + 1], 0u, 0x0123u), sh);
-                    else if (j < n_words) v = rewrite_word(d, hdr, src, n_src_words, a0 + 32u * (u64)j);
-                    sm.win[j] = v;
-                }
-            }
+            mbar_init(&sm.full[0], NC); mbar_init(&sm.full[1], NC);
+            mbar_init(&sm.empty[0], NP); mbar_init(&sm.empty[1], NP);
+            mbar_init(&sm.tab_full, 1);
+            sm.tile_items[0] = 0; sm.tile_items[1] = 0;
+            mbar_init_fence();
         }
     }
     __syncthreads();
-    volatile u32 *st = state + 1 + (size_t)sl * max_chunks;
-    /* (with a look-back the emit stage returns the insertions up to and including this chunk) */
-    const u32 ins_incl = emit_window(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
-    if (tid == 0 && byte0 + (u64)chunk_bytes >= total_bytes) sizes[sl] = (u32)total_bytes + ins_incl;   /* the slice's last chunk */
+    /* the register file is re-divided between the groups (whole warpgroups of 128 threads each): the packers give up
+       what the coders need (NP * PACKER_REGS + NC * CODER_REGS = NT * the launch allocation) */
+    if (tid >= NC) {
+#if COMPOSE_PACKER_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(COMPOSE_PACKER_REGS));
+#endif
+        packer_main(sm, tid - NC);
+    } else {
+#if COMPOSE_PACKER_REGS
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(COMPOSE_CODER_REGS));
+#endif
+        if (SPEC) coder_main<true>(sm, f, descs, n_frames, hints, dyns, dyn_tab, payload, out, sizes);
+        else coder_lean(sm, f, descs, n_frames, hints, dyns, dyn_tab, payload, out, sizes);
+    }
 }
 
 /* ------------------------------------------------------------ rasteriser */
@@ -1292,6 +1056,7 @@ pack_copy_kernel(const H264GpuFrameDesc *__restrict__ descs, const u32 *__restri
     }
 }
 
+
 /* ---------------------------------------------------------------- launch */
 
 cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
@@ -1299,16 +1064,14 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
                            const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    static int ctas_per_sm = 0;           /* resident CTAs per SM for this build (registers / shared memory) */
     const int smem = (int)sizeof(ComposeSmem);
-    if (ctas_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(compose_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(compose_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, compose_frames_kernel<false>, NT, smem) != cudaSuccess || n < 1) n = 1;
-        ctas_per_sm = n;
-    }
+    /* (per call: function attributes and occupancy belong to the calling thread's current device) */
+    cudaError_t e = cudaFuncSetAttribute(compose_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(compose_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = 0;                  /* resident CTAs per SM for this build (registers / shared memory) */
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, compose_frames_kernel<false>, NT, smem) != cudaSuccess || ctas_per_sm < 1)
+        ctas_per_sm = 1;
     const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
     int grid = n_frames < resident ? n_frames : resident;
     /* reference-mode frames, then the frames with SPEC flags (that launch returns at once when there are none) */
@@ -1316,25 +1079,6 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
     compose_frames_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
     return cudaGetLastError();
 }
-
-cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks, const uint8_t *d_src,
-                           uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream) {
-    if (n_slices <= 0 || max_chunks <= 0) return cudaSuccess;
-    static bool ready = false;
-    const int smem = (int)sizeof(ComposeSmem);
-    if (!ready) {
-        cudaError_t e = cudaFuncSetAttribute(rewrite_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        ready = true;
-    }
-    const unsigned grid = (unsigned)n_slices * (unsigned)max_chunks;
-    cudaError_t e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);   /* ticket + look-back words */
-    if (e != cudaSuccess) return e;
-    rewrite_slices_kernel<<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_state);
-    return cudaGetLastError();
-}
-
-int rewrite_chunk_bytes() { return RW_CHUNK_BYTES; }
 
 cudaError_t launch_canonicalize(H264GpuMbHint *d_hints, size_t n_hints, cudaStream_t stream) {
     if (n_hints == 0) return cudaSuccess;

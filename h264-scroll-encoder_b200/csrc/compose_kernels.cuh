@@ -7,21 +7,42 @@
 #include "composer_gpu.h"
 
 #ifndef COMPOSE_THREADS
-#define COMPOSE_THREADS      512     /* threads per CTA: a tile is 4096 macroblocks.  Few large CTAs beat many small ones here:
-                                        fewer code regions in flight per SM (the kernel is sensitive to instruction fetch) */
+#define COMPOSE_THREADS      512     /* threads per CTA: coder warps + packer warps */
+#endif
+#ifndef COMPOSE_CODER_THREADS
+#define COMPOSE_CODER_THREADS 384    /* coder threads: a tile is 3072 macroblocks (multiple of 64); the rest are packers */
 #endif
 #ifndef COMPOSE_MIN_CTAS
 #define COMPOSE_MIN_CTAS     2       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
-#define COMPOSE_WINDOW_WORDS 8192    /* slice words staged in shared memory per pass (multiple of 4) */
+#define COMPOSE_WINDOW_WORDS 6144    /* slice words per window buffer (two per CTA; multiple of 4) */
 #endif
 #ifndef COMPOSE_ITEM_SLOTS
-#define COMPOSE_ITEM_SLOTS   1024    /* work-queue items per round */
+#define COMPOSE_ITEM_SLOTS   768     /* work-queue items per window hand-over */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
-#define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
-                                                         up to 264 MBs wide, at least 2 segments per tile at the widest */
+#define COMPOSE_HINT_SLOTS   (COMPOSE_CODER_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
+                                                               up to 264 MBs wide, at least 2 segments per tile at the widest */
+#endif
+#ifndef COMPOSE_TAB_WORDS
+#define COMPOSE_TAB_WORDS    1024    /* entries of a frame's payload bit-offset table staged in shared memory (larger tables are read from global memory) */
+#endif
+#ifndef COMPOSE_PACKER_REGS
+#define COMPOSE_PACKER_REGS  40      /* setmaxnreg: registers per packer thread (0: leave the launch allocation alone) ... */
+#define COMPOSE_CODER_REGS   72      /* ... and per coder thread: 128 * 40 + 384 * 72 = 512 * 64 */
+#endif
+#ifndef COMPOSE_BULK_CLEAR
+#define COMPOSE_BULK_CLEAR   1       /* the packers clear a window with one st.bulk instead of a store loop */
+#endif
+#ifndef REWRITE_THREADS
+#define REWRITE_THREADS      512
+#endif
+#ifndef REWRITE_MIN_CTAS
+#define REWRITE_MIN_CTAS     2
+#endif
+#ifndef REWRITE_WINDOW_WORDS
+#define REWRITE_WINDOW_WORDS 8192    /* string words per rewrite chunk (32 KB) */
 #endif
 #define COMPOSE_MAX_MB_W  H264GPU_MAX_MB_W
 
