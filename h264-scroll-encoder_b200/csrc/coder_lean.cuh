@@ -111,7 +111,9 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
     const int tid = threadIdx.x, lane = tid & 31, gw = tid >> 5;
     u32 spar = 0;                      /* which sm.scan buffer the next group scan uses */
     u32 ipar = 0;                      /* which sm.tile_items counter the current tile uses */
-    Ring ring; ring.slot = 0; ring.confirmed = -1;
+    Ring ring; ring.slot = 0; ring.confirmed = -1;   /* (warp-specialised build only) */
+    PackState pst;                     /* (fused build only: this thread is a packer too) */
+    pack_state_init(pst);
     u32 buf = 0;                       /* the window being filled */
     u32 items_used = 0;                /* items queued in the slot being filled */
     u32 tab_par = 0;                   /* phase of sm.tab_full the next staged table completes */
@@ -148,14 +150,18 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                 }
                 tab = sm.tab + t_skip;
             }
-            /* the payload is read by the packers straight from L2: send it on its way there now */
-            if (tid == 32 && y1.y) {
-                const uintptr_t pa = (uintptr_t)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
-                const uintptr_t p0 = pa & ~(uintptr_t)15;
-                const u64 p_bytes = ((pa - p0) + (u64)y1.y + 15ull) & ~15ull;
+            const uint8_t *pa = payload + ((u64)y0.x | ((u64)y0.y << 32));
+            if (FUSED) {
+                /* the payload goes to shared memory now; it lands while the frame's first tile is composed (nobody reads the
+                   previous frame's payload any more: that frame ended with an emit) */
+                stage_payload(sm, pst, sizes + f, (const u32 *)pa, (y1.y + 3u) >> 2, tid == 0);
+            } else if (tid == 32 && y1.y) {
+                /* the packers fetch the payload when they meet the frame: send it on its way to L2 now */
+                const uintptr_t p0 = (uintptr_t)pa & ~(uintptr_t)15;
+                const u64 p_bytes = (((uintptr_t)pa - p0) + (u64)y1.y + 15ull) & ~15ull;
                 bulk_prefetch_l2((const void *)p0, (u32)(p_bytes < (1ull << 20) ? p_bytes : (1ull << 20)));
             }
-        }
+        } else if (FUSED) stage_payload(sm, pst, sizes + f, nullptr, 0u, false);
         const int kc = (W - 1) & 7;                            /* position of a row's last MB inside its segment */
 
         /* frame state every thread tracks identically (all of it follows from group-wide totals) */
@@ -164,11 +170,18 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
         bool first_emit = true;
 
         const int f_next = next_own_frame<false>(descs, f + (int)gridDim.x, n_frames, (int)gridDim.x);
+        /* the next frame's dense hint map is sent to L2 a whole frame ahead: the tile copies then find it there */
+        if (tid == 64 && f_next < n_frames) {
+            const uint4 *nq = (const uint4 *)(descs + f_next);
+            const uint4 n2 = __ldg(nq + 2), n3 = __ldg(nq + 3);
+            const u64 n_bytes = (8ull * (n3.z & 0xFFFFu) * (n3.z >> 16)) & ~15ull;
+            if (n_bytes) bulk_prefetch_l2((const uint2 *)hints + ((u64)n2.x | ((u64)n2.y << 32)), (u32)(n_bytes < (1ull << 20) ? n_bytes : (1ull << 20)));
+        }
 
         /* a window (+ its queue) goes to the packers (see coder_main) */
         auto hand_over = [&](u32 flags, u32 chunk_bytes, u32 clear_words, u32 total_bytes, u32 carry = 0u) {
             if (tid == 0) {
-                SlotMeta &m = sm.meta[ring.slot & 1];
+                SlotMeta &m = sm.meta[FUSED ? 0 : ring.slot & 1];
                 const uint4 e2 = __ldg(dq + 2), e3 = __ldg(dq + 3);
                 m.fout = out + ((u64)e2.z | ((u64)e2.w << 32)); m.cap = e3.x;
                 m.pay_words = nullptr; m.n_pay_words = 0;
@@ -183,8 +196,14 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                 m.wbase = wbase; m.chunk_bytes = chunk_bytes; m.clear_words = clear_words; m.total_bytes = total_bytes;
                 m.carry = carry; m.num_refs = num_refs;
             }
-            mbar_arrive(&sm.full[ring.slot & 1]);
-            ring.slot++;
+            if (FUSED) {                                            /* every thread turns packer for this window */
+                __syncthreads();
+                process_slot(sm, sm.meta[0], sm.items[0], tid, pst);
+                __syncthreads();
+            } else {
+                mbar_arrive(&sm.full[ring.slot & 1]);
+                ring.slot++;
+            }
             items_used = 0;
         };
 
@@ -208,37 +227,27 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
             const u32 c_own = 4u * (u32)(tid + geo.tpr + 1), c_abv = 4u * (u32)(tid + 1);   /* first chunks of the own segment / the one above */
             const bool owns_trailer = last && tid == n - 1;
 
-            /* ---- decide + code: one macroblock per iteration ------------------------------------------------ */
+            /* ---- decide + code: two macroblocks (one 16-byte chunk of the staged tile) per iteration ---------------- */
             u32 acc[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = 0u;
             u32 Ls = 0;                /* bits in the accumulator */
             u32 Ldyn = 0;              /* bits of the spliced macroblocks (with their mb_skip_run bit) */
             u32 Lpre = 0;              /* accumulator bits in front of the spliced run */
-            u32 run = 0;               /* k_first | n_run << 8 | irregular << 16 | items of the irregular path << 20 */
+            u32 run = 0;               /* k_first | n_run << 8 | irregular << 16 */
             u32 di_first = 0;
             {
-                const uint2 un = make_uint2(0u, HINT_Y_UNAVAIL);
-                uint2 a = un, d = un, b = un;
-                if (active) {
-                    if (!first) { a = ld_hint(hb, c_own - 1u, 1u); d = ld_hint(hb, c_abv - 1u, 1u); }
-                    b = ld_hint(hb, c_abv, 0u);
-                }
-#pragma unroll 1
-                for (int k = 0; k < MPT; k++) {
-                    uint2 h = un, c = un;
-                    if (active) {
-                        h = ld_hint(hb, c_own + ((u32)k >> 1), (u32)k & 1u);
-                        c = ld_hint(hb, c_abv + ((u32)(k + 1) >> 1), (u32)(k + 1) & 1u);
-                        if (lastseg && k == kc) c = d;                 /* C of the row's last MB is D (src/h264_writer.c:391-399) */
-                    }
+                const bool row0 = row == 0;
+                /* one macroblock against A, B, C (D where the row ends, src/h264_writer.c:391-399): its code and length */
+                auto one_mb = [&](int k, const uint2 h, const uint2 a, const uint2 b, uint2 c, const uint2 d, u32 &code, u32 &len) {
+                    if (lastseg && k == kc) c = d;
                     const bool present = k < nmb;
                     const bool dyn = (h.y & 0xFF00u) != 0u;
                     /* top row: A alone decides (src/h264_writer.c:407-417); else B == C == own hint: two refs match and
                        min(max(a, h), h) is h whatever A is */
-                    const bool uni = row == 0 ? ((h.x ^ a.x) | (h.y ^ a.y)) == 0u
-                                              : ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
-                    u32 code = 0u, len = 0u;
+                    const bool uni = row0 ? ((h.x ^ a.x) | (h.y ^ a.y)) == 0u
+                                          : ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
+                    code = 0u; len = 0u;
                     if (__all_sync(FULL, uni || dyn || !present)) {
                         if (present && !dyn) decide_mb_uniform(h.y, num_refs, 0, code, len);
                     } else if (present && !dyn) {
@@ -247,21 +256,45 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                             Ldyn += len; code = 0u; len = 0u;          /* (its bits are counted, not accumulated) */
                         }
                     }
-                    if (present && dyn) {
-                        const u32 di = h.y >> 16;
-                        const u32 n_run = (run >> 8) & 0xFFu;
-                        Ldyn += tab[di + 1] - tab[di] + 1u;            /* (generic loads: the table is staged in shared memory when it fits) */
-                        if (n_run == 0u) { run |= (u32)k | (1u << 8); di_first = di; Lpre = Ls; }
-                        else if ((u32)k == (run & 0xFFu) + n_run && di == di_first + n_run) run += 1u << 8;
-                        else run |= 1u << 16;                          /* a second run, or scattered payload indices */
+                    if (__any_sync(FULL, present && dyn)) {
+                        if (present && dyn) {
+                            const u32 di = h.y >> 16;
+                            const u32 n_run = (run >> 8) & 0xFFu;
+                            Ldyn += tab[di + 1] - tab[di] + 1u;        /* (generic loads: the table is staged in shared memory when it fits) */
+                            if (n_run == 0u) { run |= (u32)k | (1u << 8); di_first = di; Lpre = Ls + len; }
+                            else if ((u32)k == (run & 0xFFu) + n_run && di == di_first + n_run) run += 1u << 8;
+                            else run |= 1u << 16;                      /* a second run, or scattered payload indices */
+                        }
                     }
-                    if (present) run += 1u << 20;
-                    const u32 lmax = __reduce_max_sync(FULL, Ls + len);
-                    if (lmax <= 64u) acc_append<2>(acc, code, len);
-                    else if (lmax <= 128u) acc_append<4>(acc, code, len);
-                    else acc_append<8>(acc, code, len);
-                    Ls += len;
-                    a = h; d = b; b = c;
+                };
+                const uint2 un = make_uint2(0u, HINT_Y_UNAVAIL);
+                uint2 a = un, d = un;
+                uint4 pa = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);      /* chunk j of the segment above */
+                if (active) {
+                    if (!first) { a = ld_hint(hb, c_own - 1u, 1u); d = ld_hint(hb, c_abv - 1u, 1u); }
+                    pa = hb[hint_swizzle(c_abv)];
+                }
+#pragma unroll 1
+                for (int j = 0; j < MPT / 2; j++) {
+                    uint4 o = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL), na = o;
+                    if (active) {
+                        o = hb[hint_swizzle(c_own + (u32)j)];
+                        na = hb[hint_swizzle(c_abv + (u32)j + 1u)];
+                    }
+                    const uint2 h0 = make_uint2(o.x, o.y), h1 = make_uint2(o.z, o.w);
+                    const uint2 b0 = make_uint2(pa.x, pa.y), b1 = make_uint2(pa.z, pa.w);
+                    u32 code0, len0, code1, len1;
+                    one_mb(2 * j, h0, a, b0, b1, d, code0, len0);
+                    const u32 Ls0 = Ls;
+                    Ls += len0;                                        /* (Lpre of a run that starts at the second macroblock) */
+                    one_mb(2 * j + 1, h1, h0, b1, make_uint2(na.x, na.y), b0, code1, len1);
+                    Ls = Ls0;
+                    const u32 lmax = __reduce_max_sync(FULL, Ls + len0 + len1);
+                    if (lmax <= 64u) { acc_append<2>(acc, code0, len0); acc_append<2>(acc, code1, len1); }
+                    else if (lmax <= 128u) { acc_append<4>(acc, code0, len0); acc_append<4>(acc, code1, len1); }
+                    else { acc_append<8>(acc, code0, len0); acc_append<8>(acc, code1, len1); }
+                    Ls += len0 + len1;
+                    a = h1; d = b1; pa = na;
                 }
             }
             bool irregular = (run >> 16) & 1u;
@@ -282,7 +315,7 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
             }
 
             /* ---- bit count of the thread, queue slots ---------------------------- */
-            const u32 n_it = (irregular ? (run >> 20) : n_run) + (tr_len ? 1u : 0u);
+            const u32 n_it = (irregular ? (u32)nmb : n_run) + (tr_len ? 1u : 0u);
             u32 ibase = 0;
             if (n_it) ibase = atomicAdd(&sm.tile_items[ipar], n_it);
             const u32 L = Ls + Ldyn + tr_len;
@@ -314,19 +347,19 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                 const u32 wf_al = (bitpos >> 5) & ~3u;             /* 16-byte group of the tile's first word */
                 if (wf_al > wbase) {
                     const u32 src = wf_al - wbase;
-                    ring_wait(sm, ring, ring.slot - 1);            /* the other window must be free: the packers move the last words over */
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);   /* the other window must be free: the packers move the last words over */
                     hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u), src << 2, src + 4u, 0u, src);
                     first_emit = false;
-                    buf ^= 1u;
+                    if (!FUSED) buf ^= 1u;
                     wbase = wf_al;
                 } else if (items_used) {
                     hand_over(0u, 0u, 0u, 0u);                     /* nothing whole to emit yet: splice only, and wait for it */
-                    ring_wait(sm, ring, ring.slot - 1);
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);
                 }
             }
 
             for (;;) {
-                ring_wait(sm, ring, ring.slot - 2);                /* the window and the slot's queue are ours */
+                if (!FUSED) ring_wait(sm, ring, ring.slot - 2);    /* the window and the slot's queue are ours */
                 u32 *win = sm.win[buf];
                 /* ---- header: start code, NAL header byte, slice header bits ---------- */
                 if (tile0 && tid < 10 && 32u * (u32)tid < hdr_total) {
@@ -399,11 +432,11 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                 for (u32 r_lo = 0;;) {
                     const u32 r_hi = min(total_items, r_lo + ((u32)LCAP - items_used));
                     if (n_it && ibase < r_hi && ibase + n_it > r_lo) {
-                        uint4 *queue = sm.items[ring.slot & 1] + items_used;
+                        uint4 *queue = sm.items[FUSED ? 0 : ring.slot & 1] + items_used;
                         u32 idx = ibase, bit = O;
                         if (irregular) {
                             irregular_items(geo.fh, W, row, MPT * col, nmb, num_refs, tab, O, ibase, r_lo, r_hi, queue);
-                            idx += run >> 20;
+                            idx += (u32)nmb;
                             bit += Ls + Ldyn;
                         } else {
                             /* the run's items from the offset table: '1' (mb_skip_run = 0) + the macroblock's payload bits */
@@ -426,7 +459,7 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                     items_used += r_hi - r_lo;
                     if (r_hi >= total_items) break;
                     hand_over(0u, 0u, 0u, 0u);                             /* (the same window goes on) */
-                    ring_wait(sm, ring, ring.slot - 1);
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);
                     r_lo = r_hi;
                 }
 
@@ -440,7 +473,7 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
                 hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u) | (fits ? SLOT_LAST : 0u), chunk_bytes,
                           min((u32)CH, w_last - wbase + 1u), total_bytes);
                 first_emit = false;
-                buf ^= 1u;
+                if (!FUSED) buf ^= 1u;
                 if (fits) break;                                           /* (frame done) */
                 wbase += CH;                                               /* a full window has left; the tile goes on in the next one */
             }
@@ -454,10 +487,11 @@ __device__ __forceinline__ void coder_lean(ComposeSmem &sm, int f, const H264Gpu
         f = f_next;
     }
     cp_async_wait_all();
-    /* tell the packers to leave */
-    ring_wait(sm, ring, ring.slot - 2);
-    if (tid == 0) sm.meta[ring.slot & 1].flags = SLOT_EXIT;
-    mbar_arrive(&sm.full[ring.slot & 1]);
+    if (!FUSED) {                                                          /* tell the packers to leave */
+        ring_wait(sm, ring, ring.slot - 2);
+        if (tid == 0) sm.meta[ring.slot & 1].flags = SLOT_EXIT;
+        mbar_arrive(&sm.full[ring.slot & 1]);
+    }
 }
 
 #endif

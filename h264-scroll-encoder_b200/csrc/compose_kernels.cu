@@ -43,19 +43,22 @@
 namespace h264scroll {
 
 constexpr int NT = COMPOSE_THREADS;          /* threads per CTA */
-constexpr int NC = COMPOSE_CODER_THREADS;    /* coder threads (warps 0 .. NC/32-1) */
-constexpr int NP = NT - NC;                  /* packer threads */
+constexpr bool FUSED = COMPOSE_FUSED != 0;   /* every thread is coder and packer in turn (no warp specialisation) */
+constexpr int NC = FUSED ? NT : COMPOSE_CODER_THREADS;       /* coder threads (warps 0 .. NC/32-1) */
+constexpr int NP = FUSED ? NT : NT - COMPOSE_CODER_THREADS;  /* packer threads */
+constexpr int NWIN = FUSED ? 1 : 2;          /* window buffers (and queues) per CTA */
 constexpr int MPT = 8;                       /* macroblocks per segment / coder thread */
 constexpr int NWC = NC / 32, NWP = NP / 32;
 constexpr int CH = COMPOSE_WINDOW_WORDS;     /* window: slice words staged per buffer */
 constexpr int LCAP = COMPOSE_ITEM_SLOTS;     /* queue items per window hand-over */
 constexpr int HBS = COMPOSE_HINT_SLOTS;      /* 64-byte segment slots per staged hint tile */
 constexpr int TABCAP = COMPOSE_TAB_WORDS;    /* staged entries of the frame's payload bit-offset table */
+constexpr int PAYBUF16 = COMPOSE_PAYBUF16;   /* 16-byte chunks of the frame's payload the packers stage in shared memory */
 constexpr u32 FULL = 0xFFFFFFFFu;
 constexpr int EG = 4;                        /* emit: 16-byte groups per packer thread per pass */
 constexpr int EPASS = EG * NP;               /* emit: groups per pass */
-constexpr int BAR_CODER = 1, BAR_PACKER = 2; /* named barriers of the two groups */
-static_assert(NC % 64 == 0 && NP % 32 == 0 && NP >= 32, "group sizes");
+constexpr int BAR_CODER = FUSED ? 0 : 1, BAR_PACKER = FUSED ? 0 : 2;   /* named barriers of the two groups (0 = the whole CTA) */
+static_assert(NC % 64 == 0 && NP % 32 == 0 && NP >= 32 && (FUSED || NC + NP == NT), "group sizes");
 static_assert(NWC <= 32 && NWP <= 32, "a warp scans the group's warp totals");
 static_assert(CH % 4 == 0 && TABCAP % 4 == 0, "16-byte granules");
 
@@ -83,15 +86,17 @@ struct SlotMeta {
 };
 
 struct __align__(128) ComposeSmem {
-    u32 win[2][CH + 8];                  /* slice words [wbase, wbase + CH) of a frame, MSB first (+ read-ahead pad); zero where unwritten */
+    u32 win[NWIN][CH + 8];               /* slice words [wbase, wbase + CH) of a frame, MSB first (+ read-ahead pad); zero where unwritten */
     uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks) */
-    uint4 items[2][LCAP];                /* work queues, one per hand-over slot */
+    uint4 items[NWIN][LCAP];             /* work queues, one per hand-over slot */
     u32 tab[TABCAP];                     /* the frame's payload bit-offset table (bulk copy) */
+    uint4 paybuf[PAYBUF16];              /* packers: the frame's pre-encoded payload (bulk copy; what does not fit is read from global memory) */
     SlotMeta meta[2];
     u64 full[2], empty[2];               /* hand-over ring: coders -> packers, packers -> coders */
     u64 tab_full;
+    u64 pay_full;
     u32 scan[2][NWC + 1];                /* coders: double buffered, one barrier per group scan */
-    uint2 escan[2][NWP + 1];             /* packers: the emit stage's scan */
+    u32 escan[2][NWP + 1];               /* packers: the warps' insert totals of an emit pass (double buffered) */
     u32 tile_items[2];                   /* coders: items of the current / next tile */
     u32 zrun_out;                        /* packers: zero bytes closing the bytes emitted so far (rbsp_to_ebsp state) */
 };
@@ -207,15 +212,17 @@ __device__ __noinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, in
 /*
  * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from chunk_byte0 on).
  * Returns the bytes inserted; leaves the closing zero run in sm.zrun_out (read it behind a packer barrier).
- * Called by all packer threads behind a packer barrier.  A pass covers EG 16-byte groups per thread (thread t owns
- * groups t, t + NP, ... of the pass: neighbouring lanes hold neighbouring groups):
+ * Called by all packer threads behind a packer barrier.  A pass covers EG 16-byte groups per thread; a warp owns
+ * EG * 32 consecutive groups of the pass (round r of warp w = groups (w * EG + r) * 32 + lane: neighbouring lanes hold
+ * neighbouring groups, and a round's last group is followed by the next round's first one in the same warp):
  *   masks     the owner computes the exact insert mask of a group that holds a zero byte or starts with a byte <= 3
  *             behind one; every other group inserts nothing
- *   offsets   one prefix sum of the counts over the group (packed 16-bit fields, EG rounds at once)
+ *   offsets   prefix sums of the counts inside the warp (packed 16-bit fields, EG rounds at once), one exchange of the
+ *             warps' totals through shared memory (one barrier per pass)
  *   store     a full group without insertions leaves as aligned or re-aligned 32/128-bit words (the word it shares
- *             with a neighbour is a whole-word store when that neighbour - known by shuffle - is of the same kind);
- *             groups that insert, the frame's last partial group and everything next to the slot's end go byte-wise,
- *             one byte per lane, a warp per group
+ *             with a neighbour is a whole-word store when that neighbour - a bit of the round's ballot - is of the
+ *             same kind); groups that insert, the frame's last partial group and everything next to the slot's end
+ *             go byte-wise, one byte per lane, two groups per warp and step
  */
 __device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int ptid, u32 chunk_byte0, int chunk_bytes,
                                         u32 ins_total, u32 zrun_in, u32 cap, uint8_t *fout) {
@@ -227,11 +234,13 @@ __device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int pti
     for (int q0 = 0; q0 < n_groups; q0 += EPASS, par ^= 1u) {
         /* even with an insertion after every second byte the pass stays clear of the slot's end */
         const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) + ins_total + 4u <= cap;
+        const int qw = q0 + pw * (EG * 32) + lane;           /* the thread's group of round 0 */
         u64 insw = 0;                                        /* the groups' insert masks, 16 bits each */
-        u64 cntw = 0;                                        /* ... and their insert counts */
+        u32 lo = 0, hi = 0;                                  /* ... and their insert counts (rounds 0, 1 | 2, 3) */
+        u32 edge = 0;                                        /* bit 2r: the round's first group is clean, bit 2r + 1: its last one */
 #pragma unroll 1
         for (int r = 0; r < EG; r++) {
-            const int q = q0 + r * NP + ptid;
+            const int q = qw + 32 * r;
             const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
             u32 ins = 0u;
             if (vb > 0) {
@@ -244,24 +253,42 @@ __device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int pti
                 /* the holder of the window's last byte hands the zero run to the next window */
                 if (16 * (q + 1) >= chunk_bytes) sm.zrun_out = zeros_before_win(win, (u32)chunk_bytes, zrun_in);
             }
+            const u32 cm = __ballot_sync(FULL, vb == 16 && ins == 0u && roomy);
+            edge |= ((cm & 1u) | ((cm >> 30) & 2u)) << (2 * r);
             insw |= (u64)ins << (16 * r);
-            cntw |= (u64)__popc(ins) << (16 * r);
+            const u32 c = (u32)__popc(ins) << (16 * (r & 1));
+            if (r & 2) hi |= c; else lo |= c;
         }
-        u32 lo = (u32)cntw, hi = (u32)(cntw >> 32);
-        u32 tlo, thi;
-        group_excl_scan_x2<NWP, BAR_PACKER>(lo, hi, sm.escan[par], pw, tlo, thi);
-        u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
-        const u64 exw = (u64)lo | ((u64)hi << 32), totw = (u64)tlo | ((u64)thi << 32);
+        /* inclusive prefix sums over the lanes, the warp's totals per round, the warps' totals through shared memory */
+        u32 il = lo, ih = hi;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const u32 x = __shfl_up_sync(FULL, il, dd), y = __shfl_up_sync(FULL, ih, dd);
+            if (lane >= dd) { il += x; ih += y; }
+        }
+        const u32 tl = __shfl_sync(FULL, il, 31), th = __shfl_sync(FULL, ih, 31);
+        const u32 wsum = (tl & 0xFFFFu) + (tl >> 16) + (th & 0xFFFFu) + (th >> 16);
+        if (lane == 0) sm.escan[par][pw] = wsum;
+        group_sync<BAR_PACKER, NP>();
+        u32 wbase_ins = 0, pass_total = 0;
+#pragma unroll
+        for (int w = 0; w < NWP; w++) {
+            const u32 v = sm.escan[par][w];
+            pass_total += v;
+            if (w < pw) wbase_ins += v;
+        }
+        const u64 exw = (u64)(il - lo) | ((u64)(ih - hi) << 32), totw = (u64)tl | ((u64)th << 32);
+        u32 round_base = ins_total + wbase_ins;              /* bytes inserted before the round's first group */
 #pragma unroll 1
         for (int r = 0; r < EG; r++) {
-            const int q = q0 + r * NP + ptid;
+            const int q = qw + 32 * r;
             const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
             const u32 before = round_base + ((u32)(exw >> (16 * r)) & 0xFFFFu);
             round_base += (u32)(totw >> (16 * r)) & 0xFFFFu;
             const u32 ins = (u32)(insw >> (16 * r)) & 0xFFFFu;
             const u32 D = chunk_byte0 + 16u * (u32)q + before;             /* output byte of the group's first byte */
             const bool clean = vb == 16 && ins == 0u && roomy;
-            const bool up = __shfl_up_sync(FULL, clean, 1), dn = __shfl_down_sync(FULL, clean, 1);
+            const u32 cm = __ballot_sync(FULL, clean);
             if (clean) {
                 const uint4 w = ((const uint4 *)win)[q];
                 const u32 s = (4u - (D & 3u)) & 3u;          /* source bytes before the first aligned word */
@@ -272,8 +299,11 @@ __device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int pti
                     if ((D & 15u) == 0u) *(uint4 *)dst = o;
                     else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
                 } else {
-                    /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
-                    const bool prev_clean = lane > 0 && up, next_clean = lane < 31 && dn;
+                    /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is
+                       clean too: the lanes beside this one, the previous round's last / the next round's first group at the
+                       warp's ends (nobody beyond the warp's span: those few bytes go one by one) */
+                    const bool prev_clean = lane > 0 ? (cm >> (lane - 1)) & 1u : (r > 0 && ((edge >> (2 * r - 1)) & 1u));
+                    const bool next_clean = lane < 31 ? (cm >> (lane + 1)) & 1u : (r < EG - 1 && ((edge >> (2 * r + 2)) & 1u));
                     const u32 wn = win[4 * q + 4];
                     const u32 sel = realign_selector(s);
                     dst[0] = __byte_perm(w.x, w.y, sel);
@@ -295,67 +325,128 @@ __device__ __noinline__ u32 packer_emit(ComposeSmem &sm, const u32 *win, int pti
                     }
                 }
             }
-            /* the others: the whole warp takes them one after the other, a byte per lane */
+            /* the others: the warp takes them two at a time, a byte per lane */
             u32 m = __ballot_sync(FULL, vb > 0 && !clean);
             while (m) {
-                const int l = __ffs((int)m) - 1;
+                const int l0 = __ffs((int)m) - 1;
                 m &= m - 1u;
-                const u32 Dl = __shfl_sync(FULL, D, l), il = __shfl_sync(FULL, ins, l);
+                int l1 = -1;
+                if (m) { l1 = __ffs((int)m) - 1; m &= m - 1u; }
+                const int l = (lane < 16 || l1 < 0) ? l0 : l1;
+                const u32 Dl = __shfl_sync(FULL, D, l), il2 = __shfl_sync(FULL, ins, l);
                 const int vl = __shfl_sync(FULL, vb, l), ql = __shfl_sync(FULL, q, l);
-                if (lane < vl) {
-                    const u32 byte = (win[4 * ql + (lane >> 2)] >> (24 - 8 * (lane & 3))) & 0xFFu;
-                    const u32 pos = Dl + (u32)lane + (u32)__popc(il & ((2u << lane) - 1u));
-                    if ((il >> lane) & 1u) { if (pos - 1u < cap) fout[pos - 1u] = 3; }
+                const int j = lane & 15;
+                if (j < vl && (lane < 16 || l1 >= 0)) {
+                    const u32 byte = (win[4 * ql + (j >> 2)] >> (24 - 8 * (j & 3))) & 0xFFu;
+                    const u32 pos = Dl + (u32)j + (u32)__popc(il2 & ((2u << j) - 1u));
+                    if ((il2 >> j) & 1u) { if (pos - 1u < cap) fout[pos - 1u] = 3; }
                     if (pos < cap) fout[pos] = (uint8_t)byte;
                 }
             }
         }
-        ins_total += (tlo & 0xFFFFu) + (tlo >> 16) + (thi & 0xFFFFu) + (thi >> 16);
+        ins_total += pass_total;
     }
     return ins_total - ins_in;
 }
 
-/* splice: one lane per queue item */
+/* splice: one lane per queue item; a spliced macroblock whose payload words (and the read-ahead word) are all staged
+   reads shared memory */
 __device__ __forceinline__ void packer_splice(const uint4 *items, u32 n_items, int ptid, u32 *win, u32 wbase, int num_refs,
-                                           const u32 *pw, u32 n_words) {
+                                           const u32 *pw, u32 n_words, const u32 *ps, u32 staged) {
     for (u32 i = (u32)ptid; i < n_items; i += NP) {
         const uint4 q = items[i];
         Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
-        consume_item(it, win, wbase, (u32)CH, num_refs, pw, n_words);
+        const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
+        consume_item(it, win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
+    }
+}
+
+/* what the packing side carries from window to window */
+struct PackState {
+    u32 ins_total;                     /* emulation-prevention bytes inserted so far in the current frame */
+    u32 zrun;                          /* zero bytes closing what the frame has emitted so far */
+    const u32 *frame_id;               /* the frame whose payload is staged (its sizes[] entry names it) */
+    const u32 *pay_smem;               /* payload word i of that frame = pay_smem[i] for i < pay_staged */
+    u32 pay_staged, pay_par;
+};
+__device__ __forceinline__ void pack_state_init(PackState &st) {
+    st.ins_total = 0; st.zrun = 0; st.frame_id = nullptr; st.pay_smem = nullptr; st.pay_staged = 0; st.pay_par = 0;
+}
+
+/*
+ * A frame's payload comes to shared memory with one bulk copy of the whole 16-byte chunks that hold it (what does not
+ * fit, and the odd bytes at its ends, are read from global memory).  `issuer` issues the copy; everybody learns what is
+ * staged.  Nobody may still read the previous frame's payload (a frame's last hand-over is an emit, with barriers
+ * behind its splice).
+ */
+__device__ __forceinline__ void stage_payload(ComposeSmem &sm, PackState &st, const u32 *frame_id, const u32 *pay_words, u32 n_pay_words, bool issuer) {
+    st.frame_id = frame_id;
+    st.pay_staged = 0;
+    st.pay_par &= 1u;                                        /* (bit 1: this frame's copy has been waited for) */
+    if (PAYBUF16 > 0 && pay_words != nullptr) {
+        const uintptr_t a0 = (uintptr_t)pay_words & ~(uintptr_t)15;
+        const u32 w_skip = (u32)(((uintptr_t)pay_words - a0) >> 2);
+        const u32 n16 = min((w_skip + n_pay_words) >> 2, (u32)PAYBUF16);
+        if (4u * n16 > w_skip) {
+            if (issuer) {
+                mbar_arrive_expect_tx(&sm.pay_full, 16u * n16);
+                bulk_g2s(sm.paybuf, (const void *)a0, 16u * n16, &sm.pay_full);
+            }
+            st.pay_staged = 4u * n16 - w_skip;
+            st.pay_smem = (const u32 *)sm.paybuf + w_skip;
+        }
+    }
+}
+/* wait for the staged payload (once per frame: pay_par flips) */
+__device__ __forceinline__ void await_payload(ComposeSmem &sm, PackState &st) {
+    if (st.pay_staged && !(st.pay_par & 2u)) { mbar_wait(&sm.pay_full, st.pay_par & 1u); st.pay_par = (st.pay_par ^ 1u) | 2u; }
+}
+
+/* one hand-over: splice the queue into the window, then (SLOT_EMIT) emit and clear it.  Called by all NP packing
+   threads; the barriers are the packing group's */
+__device__ __noinline__ void process_slot(ComposeSmem &sm, const SlotMeta &m, const uint4 *items, int ptid, PackState &st) {
+    const u32 flags = m.flags;
+    u32 *win = sm.win[m.buf];
+    const u32 wbase = m.wbase;
+    if (!FUSED && m.size_ptr != st.frame_id)                 /* (the fused coder stages at frame start) */
+        stage_payload(sm, st, m.size_ptr, m.pay_words, m.n_pay_words, ptid == 0);
+    await_payload(sm, st);
+    packer_splice(items, m.n_items, ptid, win, wbase, m.num_refs, m.pay_words, m.n_pay_words, st.pay_smem, st.pay_staged);
+    if (flags & SLOT_EMIT) {
+        group_sync<BAR_PACKER, NP>();                        /* every spliced bit is in */
+        u32 cval = 0;                                        /* the frame goes on behind this window: its last words move on */
+        if (m.carry && ptid < 4) {
+            cval = win[m.carry + (u32)ptid];
+            if (!FUSED && cval) atomicOr(&sm.win[(m.buf ^ 1u) & (NWIN - 1)][ptid], cval);
+        }
+        if (flags & SLOT_FIRST) { st.ins_total = 0; st.zrun = 0; }
+        const u32 chunk_bytes = m.chunk_bytes;
+        st.ins_total += packer_emit(sm, win, ptid, wbase << 2, (int)chunk_bytes, st.ins_total, st.zrun, m.cap, m.fout);
+        group_sync<BAR_PACKER, NP>();                        /* window fully read */
+        if (chunk_bytes > 0u) st.zrun = sm.zrun_out;
+        const u32 cw = (m.clear_words + 3u) & ~3u;
+#if COMPOSE_BULK_CLEAR
+        if (ptid == 0 && cw) smem_zero_bulk(win, 4u * cw);
+#else
+        for (u32 i = (u32)ptid; i < cw / 4u; i += NP) ((uint4 *)win)[i] = make_uint4(0u, 0u, 0u, 0u);
+#endif
+        if ((flags & SLOT_LAST) && ptid == 0) *m.size_ptr = m.total_bytes + st.ins_total;
+        if (FUSED && m.carry) {                              /* (one window: the words come back in at its start) */
+            group_sync<BAR_PACKER, NP>();
+            if (ptid < 4 && cval) atomicOr(&win[ptid], cval);
+        }
     }
 }
 
 /* the packer group: takes windows off the ring until it is told to leave */
 __device__ __forceinline__ void packer_main(ComposeSmem &sm, int ptid) {
-    u32 ins_total = 0;                 /* emulation-prevention bytes inserted so far in the current frame */
-    u32 zrun = 0;                      /* zero bytes closing what the frame has emitted so far */
+    PackState st;
+    pack_state_init(st);
     for (int s = 0;; s++) {
         mbar_wait(&sm.full[s & 1], (u32)(s >> 1) & 1u);
         const SlotMeta &m = sm.meta[s & 1];
-        const u32 flags = m.flags;
-        if (flags & SLOT_EXIT) break;
-        u32 *win = sm.win[m.buf];
-        const u32 wbase = m.wbase;
-        packer_splice(sm.items[s & 1], m.n_items, ptid, win, wbase, m.num_refs, m.pay_words, m.n_pay_words);
-        if (flags & SLOT_EMIT) {
-            group_sync<BAR_PACKER, NP>();                    /* every spliced bit is in */
-            if (m.carry && ptid < 4) {                       /* the frame goes on in the other window */
-                const u32 c = win[m.carry + (u32)ptid];
-                if (c) atomicOr(&sm.win[m.buf ^ 1u][ptid], c);
-            }
-            if (flags & SLOT_FIRST) { ins_total = 0; zrun = 0; }
-            const u32 chunk_bytes = m.chunk_bytes;
-            ins_total += packer_emit(sm, win, ptid, wbase << 2, (int)chunk_bytes, ins_total, zrun, m.cap, m.fout);
-            group_sync<BAR_PACKER, NP>();                    /* window fully read */
-            if (chunk_bytes > 0u) zrun = sm.zrun_out;
-            const u32 cw = (m.clear_words + 3u) & ~3u;
-#if COMPOSE_BULK_CLEAR
-            if (ptid == 0 && cw) smem_zero_bulk(win, 4u * cw);
-#else
-            for (u32 i = (u32)ptid; i < cw / 4u; i += NP) ((uint4 *)win)[i] = make_uint4(0u, 0u, 0u, 0u);
-#endif
-            if ((flags & SLOT_LAST) && ptid == 0) *m.size_ptr = m.total_bytes + ins_total;
-        }
+        if (m.flags & SLOT_EXIT) break;
+        process_slot(sm, m, sm.items[s & (NWIN - 1)], ptid, st);
         mbar_arrive(&sm.empty[s & 1]);
     }
 }
@@ -482,7 +573,9 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
     const int tid = threadIdx.x, lane = tid & 31, gw = tid >> 5;
     u32 spar = 0;                      /* which sm.scan buffer the next group scan uses */
     u32 ipar = 0;                      /* which sm.tile_items counter the current tile uses */
-    Ring ring; ring.slot = 0; ring.confirmed = -1;
+    Ring ring; ring.slot = 0; ring.confirmed = -1;   /* (warp-specialised build only) */
+    PackState pst;                     /* (fused build only: this thread is a packer too) */
+    pack_state_init(pst);
     u32 buf = 0;                       /* the window being filled */
     u32 items_used = 0;                /* items queued in the slot being filled */
     u32 tab_par = 0;                   /* phase of sm.tab_full the next staged table completes */
@@ -523,13 +616,14 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                 tab = sm.tab + t_skip;
             }
             /* the payload is read by the packers straight from L2: send it on its way there now */
-            if (tid == 32 && y1.y) {
-                const uintptr_t pa = (uintptr_t)(payload + ((u64)y0.x | ((u64)y0.y << 32)));
-                const uintptr_t p0 = pa & ~(uintptr_t)15;
-                const u64 p_bytes = ((pa - p0) + (u64)y1.y + 15ull) & ~15ull;
+            const uint8_t *pa = payload + ((u64)y0.x | ((u64)y0.y << 32));
+            if (FUSED) stage_payload(sm, pst, sizes + f, (const u32 *)pa, (y1.y + 3u) >> 2, tid == 0);
+            else if (tid == 32 && y1.y) {
+                const uintptr_t p0 = (uintptr_t)pa & ~(uintptr_t)15;
+                const u64 p_bytes = (((uintptr_t)pa - p0) + (u64)y1.y + 15ull) & ~15ull;
                 bulk_prefetch_l2((const void *)p0, (u32)(p_bytes < (1ull << 20) ? p_bytes : (1ull << 20)));
             }
-        }
+        } else if (FUSED) stage_payload(sm, pst, sizes + f, nullptr, 0u, false);
         const int kc = (W - 1) & 7;                            /* position of a row's last MB inside its segment */
 
         /* frame state every thread tracks identically (all of it follows from group-wide totals) */
@@ -547,7 +641,7 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
            completion the coders wait for: whoever fills slot s may touch its window and its queue once slot s - 2 is done */
         auto hand_over = [&](u32 flags, u32 chunk_bytes, u32 clear_words, u32 total_bytes, u32 carry = 0u) {
             if (tid == 0) {
-                SlotMeta &m = sm.meta[ring.slot & 1];
+                SlotMeta &m = sm.meta[FUSED ? 0 : ring.slot & 1];
                 const uint4 e2 = __ldg(dq + 2), e3 = __ldg(dq + 3);
                 m.fout = out + ((u64)e2.z | ((u64)e2.w << 32)); m.cap = e3.x;
                 m.pay_words = nullptr; m.n_pay_words = 0;
@@ -562,12 +656,18 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                 m.wbase = wbase; m.chunk_bytes = chunk_bytes; m.clear_words = clear_words; m.total_bytes = total_bytes;
                 m.carry = carry; m.num_refs = num_refs;
             }
-            mbar_arrive(&sm.full[ring.slot & 1]);
-            ring.slot++;
+            if (FUSED) {                                            /* every thread turns packer for this window */
+                __syncthreads();
+                process_slot(sm, sm.meta[0], sm.items[0], tid, pst);
+                __syncthreads();
+            } else {
+                mbar_arrive(&sm.full[ring.slot & 1]);
+                ring.slot++;
+            }
             items_used = 0;
         };
         /* the window to fill and the queue of the slot to fill are free again */
-        auto acquire = [&]() { ring_wait(sm, ring, ring.slot - 2); };
+        auto acquire = [&]() { if (!FUSED) ring_wait(sm, ring, ring.slot - 2); };
 
         for (int s0 = 0; s0 < geo.n_seg;) {
             const int n = min(geo.seg_max, geo.n_seg - s0);
@@ -694,15 +794,15 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                        before may be among them) - OR-ed in, as the tile's own writes to those words are */
                     const u32 src = wf_al - wbase;
                     const u32 nb = buf ^ 1u;
-                    ring_wait(sm, ring, ring.slot - 1);
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);
                     hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u), src << 2, src + 4u, 0u, src);
                     first_emit = false;
-                    buf = nb;
+                    if (!FUSED) buf = nb;
                     wbase = wf_al;
                 } else if (items_used) {
                     /* nothing whole to emit yet, but the queue must be drained: splice only, and wait for it */
                     hand_over(0u, 0u, 0u, 0u);
-                    ring_wait(sm, ring, ring.slot - 1);
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);
                 }
             }
 
@@ -773,7 +873,7 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                 for (u32 r_lo = 0;;) {
                     const u32 r_hi = min(total_items, r_lo + ((u32)LCAP - items_used));
                     if (n_it && ibase < r_hi && ibase + n_it > r_lo) {
-                        uint4 *queue = sm.items[ring.slot & 1] + items_used;
+                        uint4 *queue = sm.items[FUSED ? 0 : ring.slot & 1] + items_used;
                         u32 idx = ibase, bit = O;
                         int prev = prev0;
                         if (cplx) {
@@ -800,7 +900,7 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                     items_used += r_hi - r_lo;
                     if (r_hi >= total_items) break;
                     hand_over(0u, 0u, 0u, 0u);                             /* (the same window goes on) */
-                    ring_wait(sm, ring, ring.slot - 1);
+                    if (!FUSED) ring_wait(sm, ring, ring.slot - 1);
                     r_lo = r_hi;
                 }
 
@@ -814,7 +914,7 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
                 hand_over(SLOT_EMIT | (first_emit ? SLOT_FIRST : 0u) | (fits ? SLOT_LAST : 0u), chunk_bytes,
                           min((u32)CH, w_last - wbase + 1u), total_bytes);
                 first_emit = false;
-                buf ^= 1u;
+                if (!FUSED) buf ^= 1u;
                 if (fits) break;                                           /* (frame done) */
                 wbase += CH;                                               /* a full window has left; the tile goes on in the next one */
             }
@@ -829,10 +929,11 @@ __device__ __forceinline__ void coder_main(ComposeSmem &sm, int f, const H264Gpu
         geo = geo_next;
     }
     cp_async_wait_all();
-    /* tell the packers to leave */
-    ring_wait(sm, ring, ring.slot - 2);
-    if (tid == 0) sm.meta[ring.slot & 1].flags = SLOT_EXIT;
-    mbar_arrive(&sm.full[ring.slot & 1]);
+    if (!FUSED) {                                                          /* tell the packers to leave */
+        ring_wait(sm, ring, ring.slot - 2);
+        if (tid == 0) sm.meta[ring.slot & 1].flags = SLOT_EXIT;
+        mbar_arrive(&sm.full[ring.slot & 1]);
+    }
 }
 
 #include "coder_lean.cuh"
@@ -854,25 +955,31 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
     {   /* the windows are zero wherever nothing was written: cleared once here, then the packers clear what was used */
         uint4 *w4 = (uint4 *)sm.win;
-        for (int i = tid; i < 2 * (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < NWIN * (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
         if (tid == 0) {
             mbar_init(&sm.full[0], NC); mbar_init(&sm.full[1], NC);
             mbar_init(&sm.empty[0], NP); mbar_init(&sm.empty[1], NP);
             mbar_init(&sm.tab_full, 1);
+            mbar_init(&sm.pay_full, 1);
             sm.tile_items[0] = 0; sm.tile_items[1] = 0;
             mbar_init_fence();
         }
     }
     __syncthreads();
+    if (FUSED) {
+        if (SPEC || !COMPOSE_LEAN) coder_main<SPEC>(sm, f, descs, n_frames, hints, dyns, dyn_tab, payload, out, sizes);
+        else coder_lean(sm, f, descs, n_frames, hints, dyns, dyn_tab, payload, out, sizes);
+        return;
+    }
     /* the register file is re-divided between the groups (whole warpgroups of 128 threads each): the packers give up
        what the coders need (NP * PACKER_REGS + NC * CODER_REGS = NT * the launch allocation) */
     if (tid >= NC) {
-#if COMPOSE_PACKER_REGS
+#if COMPOSE_PACKER_REGS && !COMPOSE_FUSED
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(COMPOSE_PACKER_REGS));
 #endif
         packer_main(sm, tid - NC);
     } else {
-#if COMPOSE_PACKER_REGS
+#if COMPOSE_PACKER_REGS && !COMPOSE_FUSED
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(COMPOSE_CODER_REGS));
 #endif
         if (SPEC) coder_main<true>(sm, f, descs, n_frames, hints, dyns, dyn_tab, payload, out, sizes);

@@ -6,6 +6,13 @@
 #include <stdint.h>
 #include "composer_gpu.h"
 
+#ifndef COMPOSE_FUSED
+#define COMPOSE_FUSED        1       /* 1: every thread codes a tile, then packs the window (phase-synchronous CTA); 0: warp-specialised coder /
+                                        packer groups over two windows */
+#endif
+#ifndef COMPOSE_LEAN
+#define COMPOSE_LEAN         1       /* reference-mode frames through the rolled coder (coder_lean.cuh); 0: through the general one */
+#endif
 #ifndef COMPOSE_THREADS
 #define COMPOSE_THREADS      512     /* threads per CTA: coder warps + packer warps */
 #endif
@@ -16,17 +23,20 @@
 #define COMPOSE_MIN_CTAS     2       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
-#define COMPOSE_WINDOW_WORDS 6144    /* slice words per window buffer (two per CTA; multiple of 4) */
+#define COMPOSE_WINDOW_WORDS (COMPOSE_FUSED ? 8192 : 4096)   /* slice words per window buffer (multiple of 4) */
 #endif
 #ifndef COMPOSE_ITEM_SLOTS
-#define COMPOSE_ITEM_SLOTS   768     /* work-queue items per window hand-over */
+#define COMPOSE_ITEM_SLOTS   (COMPOSE_FUSED ? 1024 : 512)  /* work-queue items per window hand-over */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
-#define COMPOSE_HINT_SLOTS   (COMPOSE_CODER_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
+#define COMPOSE_HINT_SLOTS   ((COMPOSE_FUSED ? COMPOSE_THREADS : COMPOSE_CODER_THREADS) + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
                                                                up to 264 MBs wide, at least 2 segments per tile at the widest */
 #endif
 #ifndef COMPOSE_TAB_WORDS
 #define COMPOSE_TAB_WORDS    1024    /* entries of a frame's payload bit-offset table staged in shared memory (larger tables are read from global memory) */
+#endif
+#ifndef COMPOSE_PAYBUF16
+#define COMPOSE_PAYBUF16     1408    /* 16-byte chunks of a frame's payload staged in shared memory (24 KB: a 25x25-MB region at ~300 bits per MB) */
 #endif
 #ifndef COMPOSE_PACKER_REGS
 #define COMPOSE_PACKER_REGS  40      /* setmaxnreg: registers per packer thread (0: leave the launch allocation alone) ... */

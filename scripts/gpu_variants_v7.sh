@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 cp h264-scroll-encoder_b200/libh264scroll_b200.so /tmp/orig.so
 for tag in "$@"; do
   cp variants/$tag.so h264-scroll-encoder_b200/libh264scroll_b200.so
-  timeout 150 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1
+  timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1
   rc=$?
   tail -2 gpurun_out/smoke_$tag.log | cut -c1-300
   if [ $rc -eq 124 ]; then echo "$tag: smoke HUNG - stopping"; break; fi
