@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG, "libh264scroll_b200.so")
 # every symbol include/*.h declares; tests check the built library exports all of them
 GPU_SYMBOLS = [
     "h264gpu_init", "h264gpu_shutdown", "h264gpu_device_count", "h264gpu_last_error", "h264gpu_sm_count",
+    "h264gpu_ctx_create", "h264gpu_ctx_destroy", "h264gpu_ctx_make_current", "h264gpu_ctx_device",
     "h264gpu_malloc", "h264gpu_free", "h264gpu_host_alloc", "h264gpu_host_free", "h264gpu_memcpy_h2d",
     "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
@@ -63,6 +64,10 @@ def load_library(path=None):
     L = C.CDLL(path)
     vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
     L.h264gpu_last_error.restype = C.c_char_p
+    L.h264gpu_ctx_create.restype = vp; L.h264gpu_ctx_create.argtypes = [ci]
+    L.h264gpu_ctx_destroy.argtypes = [vp]; L.h264gpu_ctx_destroy.restype = None
+    L.h264gpu_ctx_make_current.argtypes = [vp]
+    L.h264gpu_ctx_device.argtypes = [vp]
     L.h264gpu_malloc.restype = vp; L.h264gpu_malloc.argtypes = [sz]
     L.h264gpu_free.argtypes = [vp]; L.h264gpu_free.restype = None
     L.h264gpu_host_alloc.restype = vp; L.h264gpu_host_alloc.argtypes = [sz]
@@ -126,12 +131,30 @@ class DeviceBuffer:
 class GpuComposer:
     """Thin object over the C ABI (include/composer_gpu.h)."""
 
-    def __init__(self, device=0, lib=None):
+    def __init__(self, device=0, lib=None, own_context=False):
+        """own_context=False: the library's default context (h264gpu_init).  own_context=True: a context of its own
+        (h264gpu_ctx_create), made current for the calling thread - every thread that uses the object calls
+        make_current() first."""
         self.lib = lib or load_library()
-        rc = self.lib.h264gpu_init(device)
-        if rc != 0:
-            raise GpuError("h264gpu_init(%d) failed (%d): %s" % (device, rc, self.err()))
+        self.ctx = None
+        if own_context:
+            self.ctx = self.lib.h264gpu_ctx_create(device)
+            if not self.ctx:
+                raise GpuError("h264gpu_ctx_create(%d) failed: %s" % (device, self.err()))
+            self.make_current()
+        else:
+            rc = self.lib.h264gpu_init(device)
+            if rc != 0:
+                raise GpuError("h264gpu_init(%d) failed (%d): %s" % (device, rc, self.err()))
         self.device = device
+
+    def make_current(self):
+        self.check(self.lib.h264gpu_ctx_make_current(self.ctx))
+
+    def close(self):
+        if self.ctx:
+            self.lib.h264gpu_ctx_destroy(self.ctx)
+            self.ctx = None
 
     def err(self):
         return (self.lib.h264gpu_last_error() or b"").decode()

@@ -22,9 +22,47 @@ namespace h264scroll { cudaError_t read_stage_cycles(unsigned long long *h8); }
 
 namespace {
 
-std::mutex g_mu;
-int g_device = -1;
-int g_sm_count = 0;
+constexpr int PIPE_STREAMS = 3;            /* upload, kernels, download */
+constexpr int PIPE_LAG = 2;                /* chunks enqueued before the first packed chunk is fetched */
+constexpr int PIPE_MAX_CHUNKS = 64;
+
+/* scratch cached by h264gpu_compose_host */
+struct Scratch {
+    void *d = nullptr;
+    size_t cap = 0;
+};
+
+/* streams, events and buffers of the pipelined host-batch call */
+struct Pipe {
+    cudaStream_t st[PIPE_STREAMS] = {};
+    cudaEvent_t ready[PIPE_MAX_CHUNKS] = {};      /* chunk c: packed, its frame offsets are on the host */
+    cudaEvent_t uploaded[PIPE_MAX_CHUNKS] = {};   /* chunk c: inputs are on the device */
+    bool made = false;
+    char *dev = nullptr;  size_t dev_cap = 0;
+    char *pin = nullptr;  size_t pin_cap = 0;
+};
+
+}  // namespace
+
+/*
+ * One context per (device, user): the device index, what the launches need to know about it, and the scratch the
+ * host-buffer calls cache (device and pinned memory, streams, events).  Nothing is shared between contexts: two host
+ * threads with a context each - on two GPUs or on one - never wait for each other.  The host-buffer calls of ONE context
+ * serialise on its mutex (they share its scratch).
+ */
+struct H264GpuCtx {
+    int device = -1;
+    int sm_count = 0;
+    std::mutex mu;
+    Scratch scratch;
+    Pipe pipe;
+};
+
+namespace {
+
+std::mutex g_mu;                           /* guards g_default */
+H264GpuCtx *g_default = nullptr;           /* the context h264gpu_init makes */
+thread_local H264GpuCtx *t_current = nullptr;   /* h264gpu_ctx_make_current: this thread's context (else the default one) */
 std::atomic<uint64_t> g_launches{0};
 thread_local char g_err[256] = "";
 
@@ -34,17 +72,81 @@ int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
     return code;
 }
 
-/* scratch cached by h264gpu_compose_host */
-struct Scratch {
-    void *d = nullptr;
-    size_t cap = 0;
-    void *pin = nullptr;
-    size_t pin_cap = 0;
-} g_scratch;
-
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-void pipe_release();
+void pipe_release(Pipe &p) {
+    for (int i = 0; i < PIPE_STREAMS; i++) if (p.st[i]) cudaStreamDestroy(p.st[i]);
+    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (p.ready[i]) cudaEventDestroy(p.ready[i]);
+    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (p.uploaded[i]) cudaEventDestroy(p.uploaded[i]);
+    if (p.dev) cudaFree(p.dev);
+    if (p.pin) cudaFreeHost(p.pin);
+    p = Pipe();
+}
+
+/* the calling thread's context, its device made current for the thread (the current device is per host thread) */
+H264GpuCtx *current() {
+    H264GpuCtx *c = t_current ? t_current : g_default;
+    if (!c) { fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init / h264gpu_ctx_create was not called (or failed)"); return nullptr; }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) { fail(H264GPU_ERR_CUDA, "cudaSetDevice", e); return nullptr; }
+    return c;
+}
+
+H264GpuCtx *ctx_new(int device, int *rc) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); *rc = fail(H264GPU_ERR_NO_DEVICE, "no CUDA device visible", e); return nullptr; }
+    if (device < 0 || device >= n) { *rc = fail(H264GPU_ERR_ARG, "device index out of range"); return nullptr; }
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) { *rc = fail(H264GPU_ERR_CUDA, "cudaGetDeviceProperties", e); return nullptr; }
+    if (p.major != 10) {
+        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library only carries sm_100a code", device, p.major, p.minor);
+        *rc = H264GPU_ERR_NO_DEVICE;
+        return nullptr;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { *rc = fail(H264GPU_ERR_CUDA, "cudaSetDevice", e); return nullptr; }
+    H264GpuCtx *c = new (std::nothrow) H264GpuCtx();
+    if (!c) { *rc = fail(H264GPU_ERR_NOMEM, "context"); return nullptr; }
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    *rc = H264GPU_OK;
+    return c;
+}
+
+void ctx_free(H264GpuCtx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->scratch.d) cudaFree(c->scratch.d);
+    pipe_release(c->pipe);
+    delete c;
+}
+
+}  // namespace
+
+namespace {
+
+/* what both host-buffer calls check about a batch's frame and dyn descriptors: ranges, alignment, missing arrays */
+int validate_frames(const H264GpuFrameDesc *desc, int n, size_t n_hints, size_t out_bytes,
+                    const H264GpuDynDesc *dyn, int n_dyn, const uint32_t *tab, size_t n_tab,
+                    const uint8_t *payload, size_t payload_bytes) {
+    for (int f = 0; f < n; f++) {
+        const H264GpuFrameDesc &d = desc[f];
+        if (d.mb_w == 0 || d.mb_h == 0 || d.mb_w > H264GPU_MAX_MB_W) return fail(H264GPU_ERR_ARG, "frame width out of range");
+        if ((d.hint_off & 1) || (d.out_off & 15) || (d.out_cap & 15)) return fail(H264GPU_ERR_ARG, "misaligned frame descriptor");
+        if (d.hint_off + (size_t)d.mb_w * d.mb_h > n_hints) return fail(H264GPU_ERR_ARG, "hints out of range");
+        if (d.out_off + d.out_cap > out_bytes) return fail(H264GPU_ERR_ARG, "output slot out of range");
+        if (d.dyn_id != H264GPU_NO_DYN) {
+            if (!dyn || (int)d.dyn_id >= n_dyn) return fail(H264GPU_ERR_ARG, "dyn id out of range");
+            const H264GpuDynDesc &y = dyn[d.dyn_id];
+            if (!tab || (y.payload_bytes && !payload)) return fail(H264GPU_ERR_ARG, "dyn table / payload missing");
+            if (y.table_off + y.n_mbs + 1 > n_tab || y.payload_off + y.payload_bytes > payload_bytes || (y.payload_off & 3))
+                return fail(H264GPU_ERR_ARG, "dyn table / payload out of range");
+        }
+    }
+    return H264GPU_OK;
+}
 
 }  // namespace
 
@@ -58,40 +160,44 @@ int h264gpu_device_count(void) {
 
 int h264gpu_init(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device == device) return H264GPU_OK;
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(H264GPU_ERR_NO_DEVICE, "no CUDA device visible", e); }
-    if (device < 0 || device >= n) return fail(H264GPU_ERR_ARG, "device index out of range");
-    cudaDeviceProp p;
-    e = cudaGetDeviceProperties(&p, device);
-    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "cudaGetDeviceProperties", e);
-    if (p.major != 10) {
-        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library only carries sm_100a code", device, p.major, p.minor);
-        return H264GPU_ERR_NO_DEVICE;
-    }
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "cudaSetDevice", e);
-    g_device = device;
-    g_sm_count = p.multiProcessorCount;
+    if (g_default && g_default->device == device) return H264GPU_OK;
+    int rc = H264GPU_OK;
+    H264GpuCtx *c = ctx_new(device, &rc);
+    if (!c) return rc;
+    ctx_free(g_default);                              /* (a different device: the old default context and its scratch go) */
+    g_default = c;
     return H264GPU_OK;
 }
 
 void h264gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device < 0) return;
-    if (g_scratch.d) cudaFree(g_scratch.d);
-    if (g_scratch.pin) cudaFreeHost(g_scratch.pin);
-    g_scratch = Scratch();
-    pipe_release();
-    g_device = -1;
+    ctx_free(g_default);
+    g_default = nullptr;
 }
 
+H264GpuCtx *h264gpu_ctx_create(int device) {
+    int rc = H264GPU_OK;
+    return ctx_new(device, &rc);
+}
+
+void h264gpu_ctx_destroy(H264GpuCtx *ctx) {
+    if (t_current == ctx) t_current = nullptr;
+    ctx_free(ctx);
+}
+
+int h264gpu_ctx_make_current(H264GpuCtx *ctx) {
+    t_current = ctx;
+    return current() ? H264GPU_OK : H264GPU_ERR_NO_DEVICE;
+}
+
+int h264gpu_ctx_device(const H264GpuCtx *ctx) { return ctx ? ctx->device : -1; }
+
 const char *h264gpu_last_error(void) { return g_err; }
-int h264gpu_sm_count(void) { return g_sm_count; }
+int h264gpu_sm_count(void) { H264GpuCtx *c = t_current ? t_current : g_default; return c ? c->sm_count : 0; }
 uint64_t h264gpu_launch_count(void) { return g_launches.load(); }
 
 void *h264gpu_malloc(size_t bytes) {
+    if (!current()) return nullptr;
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
     if (e != cudaSuccess) { fail(H264GPU_ERR_NOMEM, "cudaMalloc", e); return nullptr; }
@@ -100,6 +206,7 @@ void *h264gpu_malloc(size_t bytes) {
 void h264gpu_free(void *d) { if (d) cudaFree(d); }
 
 void *h264gpu_host_alloc(size_t bytes) {
+    if (!current()) return nullptr;
     void *p = nullptr;
     cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
     if (e != cudaSuccess) { fail(H264GPU_ERR_NOMEM, "cudaMallocHost", e); return nullptr; }
@@ -121,6 +228,7 @@ int h264gpu_memset(void *dst, int value, size_t bytes, void *stream) {
 }
 
 void *h264gpu_stream_create(void) {
+    if (!current()) return nullptr;
     cudaStream_t s = nullptr;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     return (void *)s;
@@ -131,6 +239,7 @@ int h264gpu_stream_sync(void *s) {
     return e == cudaSuccess ? H264GPU_OK : fail(H264GPU_ERR_CUDA, "stream sync", e);
 }
 void *h264gpu_event_create(void) {
+    if (!current()) return nullptr;
     cudaEvent_t ev = nullptr;
     if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
     return (void *)ev;
@@ -151,10 +260,11 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
                           const H264GpuMbHint *d_hints, const H264GpuDynDesc *d_dyn,
                           const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                           uint8_t *d_out, uint32_t *d_sizes, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_desc || !d_hints || !d_out || !d_sizes) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload,
-                                               d_out, d_sizes, g_sm_count, (cudaStream_t)stream);
+                                               d_out, d_sizes, ctx->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
     if (n_frames > 0) g_launches.fetch_add(2);        /* reference-mode kernel + SPEC-mode kernel */
     return H264GPU_OK;
@@ -163,7 +273,8 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
 int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs_per_frame,
                            const H264GpuRegion *d_regions, const H264GpuMbHint *d_dyn_info,
                            H264GpuMbHint *d_hints, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_rdesc || !d_regions || !d_hints) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_raster(d_rdesc, n_frames, max_mbs_per_frame, d_regions, d_dyn_info,
                                               d_hints, (cudaStream_t)stream);
@@ -173,7 +284,8 @@ int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int m
 }
 
 int h264gpu_canonicalize_hints(H264GpuMbHint *d_hints, size_t n_hints, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (!d_hints && n_hints) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_canonicalize(d_hints, n_hints, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "canonicalize launch", e);
@@ -185,8 +297,10 @@ size_t h264gpu_parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals) { r
 
 int h264gpu_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
                          uint32_t *d_scratch, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (!d_data || !d_units || !d_scratch) return fail(H264GPU_ERR_ARG, "null argument");
+    if (n_bytes > 0xFFFFFFF0ull) return fail(H264GPU_ERR_ARG, "stream too large for 32-bit offsets");
     cudaError_t e = h264scroll::launch_parse_annexb(d_data, n_bytes, d_units, max_nals, d_scratch, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "annexb scan launch", e);
     if (n_bytes && max_nals) g_launches.fetch_add(2);
@@ -197,7 +311,8 @@ int h264gpu_unescape_chunk_bytes(void) { return h264scroll::unescape_chunk_bytes
 
 int h264gpu_unescape_nals(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks,
                           const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_scratch, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_nals < 0 || max_chunks < 0 || !d_desc || !d_src || !d_out || !d_sizes || !d_scratch) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_unescape(d_desc, n_nals, max_chunks, d_src, d_out, d_sizes, d_scratch, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "unescape launch", e);
@@ -209,7 +324,8 @@ int h264gpu_rewrite_chunk_bytes(void) { return h264scroll::rewrite_chunk_bytes()
 
 int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int max_chunks,
                            const uint8_t *d_src, uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_counts, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_slices < 0 || max_chunks < 0 || !d_desc || !d_src || !d_out || !d_sizes || !d_counts) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_rewrite(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_counts, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "rewrite launch", e);
@@ -219,7 +335,8 @@ int h264gpu_rewrite_slices(const H264GpuRewriteDesc *d_desc, int n_slices, int m
 
 int h264gpu_pack_frames(const H264GpuFrameDesc *d_desc, const uint32_t *d_sizes, int n_frames,
                         const uint8_t *d_slots, uint8_t *d_packed, uint64_t *d_offsets, void *stream) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_desc || !d_sizes || !d_slots || !d_packed || !d_offsets) return fail(H264GPU_ERR_ARG, "null argument");
     cudaError_t e = h264scroll::launch_pack(d_desc, d_sizes, n_frames, d_slots, d_packed,
                                             (unsigned long long *)d_offsets, (cudaStream_t)stream);
@@ -234,18 +351,24 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
                          const uint32_t *h_dyn_tab, size_t n_tab,
                          const uint8_t *h_payload, size_t payload_bytes,
                          uint8_t *h_out, size_t out_bytes, uint32_t *h_sizes) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames <= 0) return H264GPU_OK;
     if (!h_desc || !h_hints || !h_out || !h_sizes) return fail(H264GPU_ERR_ARG, "null argument");
-    for (int f = 0; f < n_frames; f++) {
-        const H264GpuFrameDesc &d = h_desc[f];
-        if (d.mb_w == 0 || d.mb_h == 0 || d.mb_w > H264GPU_MAX_MB_W) return fail(H264GPU_ERR_ARG, "frame width out of range");
-        if ((d.hint_off & 1) || (d.out_off & 15) || (d.out_cap & 15)) return fail(H264GPU_ERR_ARG, "misaligned frame descriptor");
-        if (d.hint_off + (size_t)d.mb_w * d.mb_h > n_hints) return fail(H264GPU_ERR_ARG, "hints out of range");
-        if (d.out_off + d.out_cap > out_bytes) return fail(H264GPU_ERR_ARG, "output slot out of range");
-        if (d.dyn_id != H264GPU_NO_DYN && (int)d.dyn_id >= n_dyn) return fail(H264GPU_ERR_ARG, "dyn id out of range");
+    {
+        const int rc = validate_frames(h_desc, n_frames, n_hints, out_bytes, h_dyn, n_dyn, h_dyn_tab, n_tab, h_payload, payload_bytes);
+        if (rc) return rc;
+        /* a hint's dyn_idx must lie inside its frame's table: checked where the hints are (they are host memory here) */
+        for (int f = 0; f < n_frames; f++) {
+            const H264GpuFrameDesc &d = h_desc[f];
+            const uint32_t n_dyn_mbs = d.dyn_id != H264GPU_NO_DYN ? h_dyn[d.dyn_id].n_mbs : 0;
+            const H264GpuMbHint *h = h_hints + d.hint_off;
+            for (size_t i = 0, m = (size_t)d.mb_w * d.mb_h; i < m; i++)
+                if (h[i].kind != H264GPU_MB_INTER && h[i].dyn_idx >= n_dyn_mbs) return fail(H264GPU_ERR_ARG, "a hint's dyn_idx lies outside the frame's table");
+        }
     }
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Scratch &g_scratch = ctx->scratch;
     /* device layout: desc | hints | dyn | tab | payload(+8) | sizes | out */
     size_t o_desc = 0;
     size_t o_hint = align_up(o_desc + sizeof(H264GpuFrameDesc) * n_frames, 256);
@@ -281,7 +404,7 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
                                    (const H264GpuMbHint *)(base + o_hint),
                                    (const H264GpuDynDesc *)(base + o_dyn),
                                    (const uint32_t *)(base + o_tab), (const uint8_t *)(base + o_pay),
-                                   (uint8_t *)(base + o_out), (uint32_t *)(base + o_sz), g_sm_count, st);
+                                   (uint8_t *)(base + o_out), (uint32_t *)(base + o_sz), ctx->sm_count, st);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
     g_launches.fetch_add(2);
     e = cudaMemcpyAsync(h_sizes, base + o_sz, sizeof(uint32_t) * n_frames, cudaMemcpyDeviceToHost, st);
@@ -299,26 +422,13 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
 
 namespace {
 
-constexpr int PIPE_STREAMS = 3;            /* upload, kernels, download */
-constexpr int PIPE_LAG = 2;            /* chunks enqueued before the first packed chunk is fetched */
-constexpr int PIPE_MAX_CHUNKS = 64;
-
-struct Pipe {
-    cudaStream_t st[PIPE_STREAMS] = {};
-    cudaEvent_t ready[PIPE_MAX_CHUNKS] = {};      /* chunk c: packed, its frame offsets are on the host */
-    cudaEvent_t uploaded[PIPE_MAX_CHUNKS] = {};   /* chunk c: inputs are on the device */
-    bool made = false;
-    char *dev = nullptr;  size_t dev_cap = 0;
-    char *pin = nullptr;  size_t pin_cap = 0;
-} g_pipe;
-
-cudaError_t pipe_setup(size_t dev_bytes, size_t pin_bytes) {
+cudaError_t pipe_setup(Pipe &g_pipe, size_t dev_bytes, size_t pin_bytes) {
     cudaError_t e = cudaSuccess;
     if (!g_pipe.made) {
         for (int i = 0; i < PIPE_STREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&g_pipe.st[i], cudaStreamNonBlocking);
         for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.ready[i], cudaEventDisableTiming);
         for (int i = 0; i < PIPE_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&g_pipe.uploaded[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) { pipe_release(); return e; }      /* (nothing half-made is kept) */
+        if (e != cudaSuccess) { pipe_release(g_pipe); return e; }      /* (nothing half-made is kept) */
         g_pipe.made = true;
     }
     if (dev_bytes > g_pipe.dev_cap) {
@@ -338,22 +448,14 @@ cudaError_t pipe_setup(size_t dev_bytes, size_t pin_bytes) {
     return cudaSuccess;
 }
 
-void pipe_release() {
-    for (int i = 0; i < PIPE_STREAMS; i++) if (g_pipe.st[i]) cudaStreamDestroy(g_pipe.st[i]);
-    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.ready[i]) cudaEventDestroy(g_pipe.ready[i]);
-    for (int i = 0; i < PIPE_MAX_CHUNKS; i++) if (g_pipe.uploaded[i]) cudaEventDestroy(g_pipe.uploaded[i]);
-    if (g_pipe.dev) cudaFree(g_pipe.dev);
-    if (g_pipe.pin) cudaFreeHost(g_pipe.pin);
-    g_pipe = Pipe();
-}
-
 }  // namespace
 
 extern "C" {
 
 int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, size_t stream_cap,
                                  uint64_t *h_offsets, uint32_t *h_sizes, int n_chunks) {
-    if (g_device < 0) return fail(H264GPU_ERR_NO_DEVICE, "h264gpu_init was not called (or failed)");
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (!b || !h_stream || !h_offsets) return fail(H264GPU_ERR_ARG, "null argument");
     const int n = b->n_frames;
     h_offsets[0] = 0;
@@ -364,24 +466,25 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
     if (n_chunks > PIPE_MAX_CHUNKS) n_chunks = PIPE_MAX_CHUNKS;
 
     /* ---- validation: ranges and alignment ---- */
+    {
+        const int rc = validate_frames(b->desc, n, b->n_hints, b->slots_bytes, b->dyn, b->n_dyn, b->dyn_tab, b->n_tab, b->payload, b->payload_bytes);
+        if (rc) return rc;
+    }
     for (int f = 0; f < n; f++) {
         const H264GpuFrameDesc &d = b->desc[f];
         const H264GpuRasterDesc &r = b->rdesc[f];
-        if (d.mb_w == 0 || d.mb_h == 0 || d.mb_w > H264GPU_MAX_MB_W) return fail(H264GPU_ERR_ARG, "frame width out of range");
-        if ((d.hint_off & 1) || (d.out_off & 15) || (d.out_cap & 15)) return fail(H264GPU_ERR_ARG, "misaligned frame descriptor");
-        if (d.hint_off + (size_t)d.mb_w * d.mb_h > b->n_hints) return fail(H264GPU_ERR_ARG, "hints out of range");
-        if (d.out_off + d.out_cap > b->slots_bytes) return fail(H264GPU_ERR_ARG, "output slot out of range");
         if (r.hint_off != d.hint_off || r.mb_w != d.mb_w || r.mb_h != d.mb_h) return fail(H264GPU_ERR_ARG, "raster and frame descriptor disagree");
         if (r.region_count > H264GPU_MAX_REGIONS || (uint64_t)r.region_first + r.region_count > b->n_regions) return fail(H264GPU_ERR_ARG, "regions out of range");
-        if (r.dyn_info_off > b->n_dyn_info) return fail(H264GPU_ERR_ARG, "dyn_info out of range");
-        if (d.dyn_id != H264GPU_NO_DYN) {
-            if (!b->dyn || (int)d.dyn_id >= b->n_dyn) return fail(H264GPU_ERR_ARG, "dyn id out of range");
-            const H264GpuDynDesc &y = b->dyn[d.dyn_id];
-            if (y.table_off + y.n_mbs + 1 > b->n_tab || y.payload_off + y.payload_bytes > b->payload_bytes) return fail(H264GPU_ERR_ARG, "dyn table / payload out of range");
+        for (uint32_t i = 0; i < r.region_count; i++) {
+            const H264GpuRegion &g = b->regions[r.region_first + i];
+            if (g.kind != H264GPU_REGION_DYN || g.mb_x1 <= g.mb_x0 || g.mb_y1 <= g.mb_y0) continue;
+            const size_t z = (size_t)r.dyn_info_off + g.dyn_base + (size_t)(g.mb_x1 - g.mb_x0) * (size_t)(g.mb_y1 - g.mb_y0);
+            if (!b->dyn_info || z > b->n_dyn_info) return fail(H264GPU_ERR_ARG, "a spliced region's dyn_info lies outside the array");
         }
     }
 
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Pipe &g_pipe = ctx->pipe;
     int bounds[PIPE_MAX_CHUNKS + 1];
     int chunk_frames = 0;
     for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n * c / n_chunks);
@@ -410,7 +513,7 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
     const size_t o_packed = align_up(o_slots + b->slots_bytes, 256);
     const size_t dev_total = o_packed + chunk_cap * n_chunks;
     const size_t p_offs = 0, p_sz = align_up(8 * (size_t)(chunk_frames + 1) * n_chunks, 256);
-    cudaError_t e = pipe_setup(dev_total, p_sz + sizeof(uint32_t) * n);
+    cudaError_t e = pipe_setup(g_pipe, dev_total, p_sz + sizeof(uint32_t) * n);
     if (e != cudaSuccess) return fail(H264GPU_ERR_NOMEM, "pipeline scratch", e);
     char *D = g_pipe.dev;
     uint64_t *pin_offs = (uint64_t *)(g_pipe.pin + p_offs);
@@ -429,7 +532,7 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
                 const H264GpuRegion &g = b->regions[r.region_first + i];
                 if (g.kind != H264GPU_REGION_DYN || g.mb_x1 <= g.mb_x0 || g.mb_y1 <= g.mb_y0) continue;
                 size_t z = (size_t)r.dyn_info_off + g.dyn_base + (size_t)(g.mb_x1 - g.mb_x0) * (size_t)(g.mb_y1 - g.mb_y0);
-                R.info.add(r.dyn_info_off, z < b->n_dyn_info ? z : b->n_dyn_info);
+                R.info.add(r.dyn_info_off, z);
             }
             const uint32_t id = b->desc[f].dyn_id;
             if (id != H264GPU_NO_DYN) {
@@ -491,7 +594,7 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
             if (e == cudaSuccess) e = h264scroll::launch_compose((const H264GpuFrameDesc *)(D + o_desc) + f0, f1 - f0, (const H264GpuMbHint *)(D + o_hint),
                                                                  (const H264GpuDynDesc *)(D + o_dyn), (const uint32_t *)(D + o_tab),
                                                                  (const uint8_t *)(D + o_pay), (uint8_t *)(D + o_slots), (uint32_t *)(D + o_sz) + f0,
-                                                                 g_sm_count, s_k);
+                                                                 ctx->sm_count, s_k);
             if (e == cudaSuccess) e = h264scroll::launch_pack((const H264GpuFrameDesc *)(D + o_desc) + f0, (const uint32_t *)(D + o_sz) + f0, f1 - f0,
                                                               (const uint8_t *)(D + o_slots), (uint8_t *)(D + o_packed) + chunk_cap * c,
                                                               (unsigned long long *)(pin_offs + (size_t)(chunk_frames + 1) * c), s_k);

@@ -6,44 +6,29 @@
 #include <stdint.h>
 #include "composer_gpu.h"
 
-#ifndef COMPOSE_FUSED
-#define COMPOSE_FUSED        1       /* 1: every thread codes a tile, then packs the window (phase-synchronous CTA); 0: warp-specialised coder /
-                                        packer groups over two windows */
-#endif
-#ifndef COMPOSE_LEAN
-#define COMPOSE_LEAN         1       /* reference-mode frames through the rolled coder (coder_lean.cuh); 0: through the general one */
-#endif
 #ifndef COMPOSE_THREADS
-#define COMPOSE_THREADS      512     /* threads per CTA: coder warps + packer warps */
-#endif
-#ifndef COMPOSE_CODER_THREADS
-#define COMPOSE_CODER_THREADS 384    /* coder threads: a tile is 3072 macroblocks (multiple of 64); the rest are packers */
+#define COMPOSE_THREADS      512     /* threads per CTA: a tile is 4096 macroblocks.  Few large CTAs beat many small ones here:
+                                        fewer code regions in flight per SM (the kernel is sensitive to instruction fetch) */
 #endif
 #ifndef COMPOSE_MIN_CTAS
 #define COMPOSE_MIN_CTAS     2       /* resident CTAs per SM the register budget is sized for */
 #endif
 #ifndef COMPOSE_WINDOW_WORDS
-#define COMPOSE_WINDOW_WORDS (COMPOSE_FUSED ? 8192 : 4096)   /* slice words per window buffer (multiple of 4) */
+#define COMPOSE_WINDOW_WORDS 8192    /* slice words staged in shared memory per pass (multiple of 4) */
 #endif
 #ifndef COMPOSE_ITEM_SLOTS
-#define COMPOSE_ITEM_SLOTS   (COMPOSE_FUSED ? 1024 : 512)  /* work-queue items per window hand-over */
+#define COMPOSE_ITEM_SLOTS   1024    /* work-queue items per round */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
-#define COMPOSE_HINT_SLOTS   ((COMPOSE_FUSED ? COMPOSE_THREADS : COMPOSE_CODER_THREADS) + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
-                                                               up to 264 MBs wide, at least 2 segments per tile at the widest */
-#endif
-#ifndef COMPOSE_TAB_WORDS
-#define COMPOSE_TAB_WORDS    1024    /* entries of a frame's payload bit-offset table staged in shared memory (larger tables are read from global memory) */
+#define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
+                                                         up to 264 MBs wide, at least 2 segments per tile at the widest */
 #endif
 #ifndef COMPOSE_PAYBUF16
-#define COMPOSE_PAYBUF16     1408    /* 16-byte chunks of a frame's payload staged in shared memory (24 KB: a 25x25-MB region at ~300 bits per MB) */
+#define COMPOSE_PAYBUF16     1664    /* 16-byte chunks of a frame's payload staged in shared memory (26 KB: a 25x25-MB region at ~300 bits per MB) */
 #endif
-#ifndef COMPOSE_PACKER_REGS
-#define COMPOSE_PACKER_REGS  40      /* setmaxnreg: registers per packer thread (0: leave the launch allocation alone) ... */
-#define COMPOSE_CODER_REGS   72      /* ... and per coder thread: 128 * 40 + 384 * 72 = 512 * 64 */
-#endif
-#ifndef COMPOSE_BULK_CLEAR
-#define COMPOSE_BULK_CLEAR   1       /* the packers clear a window with one st.bulk instead of a store loop */
+#ifndef COMPOSE_BULK_OPS
+#define COMPOSE_BULK_OPS     1       /* sm_100 bulk operations: payload staged by one cp.async.bulk (TMA unit) on an mbarrier, next frame's hints
+                                        sent to L2 by cp.async.bulk.prefetch, window cleared by st.bulk; 0: cp.async / store loops */
 #endif
 #ifndef REWRITE_THREADS
 #define REWRITE_THREADS      512

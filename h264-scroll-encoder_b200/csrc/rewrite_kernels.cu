@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "mb_codec.cuh"
 #include "kernel_util.cuh"
+#include "emit_stage.cuh"
 #include "compose_kernels.cuh"
 
 namespace h264scroll {
@@ -22,8 +23,7 @@ constexpr int NT = REWRITE_THREADS;      /* threads per CTA */
 constexpr int NW = NT / 32;
 constexpr int CH = REWRITE_WINDOW_WORDS; /* window: string words per chunk */
 constexpr u32 FULL = 0xFFFFFFFFu;
-constexpr int EG = 4;                    /* emit: 16-byte groups per thread per pass */
-constexpr int EPASS = EG * NT;           /* emit: groups per pass */
+constexpr int EPASS = EMIT_EG * NT;      /* emit: groups per pass */
 constexpr int STAGE_WORDS = CH + 32;     /* staged source words of a chunk */
 
 struct __align__(16) RewriteSmem {
@@ -38,209 +38,6 @@ struct __align__(16) RewriteSmem {
     u32 cap;                             /* output slot capacity */
     uint8_t *fout;                       /* output slot */
 };
-
-/* out of line: the backward scan is rare */
-__device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in) { return zeros_before(win, b, zrun_in); }
-
-/* a group with insertions, the frame's last bytes, or one next to the slot's end: byte by byte */
-__device__ __noinline__ void emit_bytes(uint8_t *fout, u32 cap, u32 pos, uint4 w, u32 ins, int vb) {
-#pragma unroll 1
-    for (int j = 0; j < 4 && vb > 0; j++, vb -= 4) {         /* word by word: the group rotates through w.x (no indexed registers) */
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (k < vb) {
-                if (ins & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                if (pos < cap) fout[pos] = (uint8_t)(w.x >> (24 - 8 * k));
-                pos++;
-                ins >>= 1;
-            }
-        }
-        w.x = w.y; w.y = w.z; w.z = w.w;
-    }
-}
-
-/* exact insert mask of group q of the window (src/nal.c:24-50 in closed form) */
-__device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, int vb, u32 chunk_byte0, u32 zrun_in) {
-    const u32 valid = (1u << vb) - 1u;
-    u32 z = (zero_nib(w.x) | (zero_nib(w.y) << 4) | (zero_nib(w.z) << 8) | (zero_nib(w.w) << 12)) & valid;
-    u32 keep = valid;
-    if (chunk_byte0 == 0u && q == 0) { z &= ~0x1Fu; keep &= ~0x1Fu; }   /* start code + NAL header */
-    const bool need = ((w.x >> 26) == 0u) && (keep & 1u);                /* a first byte <= 3 may close a zero run of the bytes before */
-    if (!(need || (z & (z << 1)))) return 0u;
-    u32 rin = 0;
-    if (need && (q == 0 || (win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(win, 16u * (u32)q, zrun_in);
-    const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
-                   (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
-    return epb_group_mask(z, m3 & keep, vb, rin);
-}
-
-constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without insertions: ins << 16 | valid bytes << 8 | count */
-
-/*
- * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from
- * chunk_byte0 on).  Returns the bytes inserted; leaves the closing zero run in sm.zrun[zpar ^ 1].
- * A pass covers EG 16-byte groups per thread:
- *   classify  a group that holds a zero byte (or starts with a byte <= 3 behind one), the frame's last
- *             partial group, everything next to the slot's end -> list; all other groups are clean
- *   masks     one lane per listed group: exact insert mask + count
- *   offsets   prefix sum of the counts (packed 16-bit fields, one scan for the EG rounds)
- *   store     clean groups leave as aligned or re-aligned 32/128-bit words; the listed groups that
- *             do insert (or are partial) go byte by byte, again one lane per group
- * Called by all threads after a barrier; the caller puts one behind it.
- */
-/* decoupled look-back over the chunks of one slice (slice rewrite): state word = flag << 30 | count; flag 1 = the
-   chunk's own insertions, 2 = inclusive sum over the slice so far.  Returns the insertions before chunk c. */
-__device__ __forceinline__ u32 chunk_lookback(volatile u32 *state, int c, u32 mine) {
-    if (c == 0) { state[0] = (2u << 30) | mine; return 0u; }
-    state[c] = (1u << 30) | mine;
-    __threadfence();
-    u32 sum = 0;
-    for (int p = c - 1;; ) {
-        const u32 v = state[p];
-        if ((v >> 30) == 0u) continue;                       /* not published yet: the chunk is running (tickets are taken in order) */
-        sum += v & 0x3FFFFFFFu;
-        if ((v >> 30) == 2u || p == 0) break;
-        p--;
-    }
-    state[c] = (2u << 30) | (sum + mine);
-    return sum;
-}
-
-__device__ __noinline__ u32 emit_window(RewriteSmem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar,
-                                        volatile u32 *lookback = nullptr, int lookback_c = 0) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const u32 zrun_in = sm.zrun[zpar];
-    const u32 cap = sm.cap;
-    uint8_t *fout = sm.fout;
-    u32 *fout32 = (u32 *)fout;
-    const u32 ins_in = ins_total;
-    const int n_groups = (chunk_bytes + 15) >> 4;
-    for (int q0 = 0; q0 < n_groups; q0 += EPASS) {
-        /* even with an insertion after every second byte the pass stays clear of the slot's end */
-        /* (slice rewrite: the insertions before the chunk are not known yet - at most one per two bytes) */
-        const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) +
-                           (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
-        /* ---- classify ---- */
-#pragma unroll 1                                             /* (code size matters more than the loop overhead) */
-        for (int r = 0; r < EG; r++) {
-            const int gl = tid + NT * r, q = q0 + gl;
-            const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
-            bool slow = false;
-            if (vb > 0) {
-                const uint4 w = ((const uint4 *)sm.win)[q];
-                const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                               ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-                slow = (hz & 0x80808080u) != 0u || vb < 16 || !roomy;
-                if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
-                /* the holder of the window's last byte hands the zero run to the next window */
-                if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
-            }
-            sm.gi[gl] = (u32)vb << 8;
-            const u32 m = __ballot_sync(FULL, slow);
-            if (m) {
-                u32 base = 0;
-                if (lane == 0) base = atomicAdd(&sm.n_list, (u32)__popc(m));
-                base = __shfl_sync(FULL, base, 0);
-                if (slow) sm.elist[base + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)gl;
-            }
-        }
-        __syncthreads();
-        const u32 nl = sm.n_list;
-        /* ---- masks ---- */
-        for (u32 i = (u32)tid; i < nl; i += NT) {
-            const int gl = sm.elist[i], q = q0 + gl;
-            const int vb = min(chunk_bytes - 16 * q, 16);
-            const u32 ins = group_insert_mask(sm.win, q, ((const uint4 *)sm.win)[q], vb, chunk_byte0, zrun_in);
-            sm.gi[gl] = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
-        }
-        __syncthreads();
-        if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
-        /* ---- offsets ---- */
-        u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
-        u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
-        u32 tlo, thi;
-        group_excl_scan_x2<NW, 0>(lo, hi, sm.scan2, threadIdx.x >> 5, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
-        const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
-        if (lookback) {
-            /* slice rewrite: where this chunk's bytes go depends on the insertions of the chunks before it (single pass
-               per chunk: EPASS groups).  One thread looks back, everybody picks the result up from shared memory */
-            if (tid == 0) sm.scan2[NW].x = chunk_lookback(lookback, lookback_c, t0 + t1 + t2 + t3);
-            __syncthreads();
-            ins_total = sm.scan2[NW].x;
-        }
-        /* ---- store: clean groups ---- */
-        u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
-#pragma unroll 1
-        for (int r = 0; r < EG; r++) {
-            const int gl = tid + NT * r, q = q0 + gl;
-            const u32 g = sm.gi[gl];
-            const u32 before = round_base + (((r & 2) ? hi : lo) >> (16 * (r & 1)) & 0xFFFFu);
-            round_base += ((r & 2) ? thi : tlo) >> (16 * (r & 1)) & 0xFFFFu;
-            if ((g >> 8) == 0u) continue;                    /* past the chunk */
-            if (!(roomy && g == GI_CLEAN)) { sm.gpre[gl] = before; continue; }
-            const u32 D = chunk_byte0 + 16u * (u32)q + before;         /* output byte of the group's first byte */
-            const uint4 w = ((const uint4 *)sm.win)[q];
-            const u32 s = (4u - (D & 3u)) & 3u;              /* source bytes before the first aligned word */
-            u32 *dst = fout32 + ((D + s) >> 2);
-            if (s == 0u) {
-                const uint4 o = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
-                                           __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
-                if ((D & 15u) == 0u) *(uint4 *)dst = o;
-                else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
-            } else {
-                /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
-                const bool prev_clean = gl > 0 && sm.gi[gl - 1] == GI_CLEAN;
-                const bool next_clean = gl < EPASS - 1 && sm.gi[gl + 1] == GI_CLEAN;
-                const u32 wn = sm.win[4 * q + 4];
-                const u32 sel = realign_selector(s);
-                dst[0] = __byte_perm(w.x, w.y, sel);
-                dst[1] = __byte_perm(w.y, w.z, sel);
-                dst[2] = __byte_perm(w.z, w.w, sel);
-                const u32 o3 = __byte_perm(w.w, wn, sel);
-                if (next_clean) dst[3] = o3;
-                else {                                       /* (1..3 bytes, no loop) */
-                    uint8_t *t = fout + D + s + 12u;
-                    t[0] = (uint8_t)o3;
-                    if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
-                    if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
-                }
-                if (!prev_clean) {
-                    uint8_t *h = fout + D;
-                    h[0] = (uint8_t)(w.x >> 24);
-                    if (s > 1u) h[1] = (uint8_t)(w.x >> 16);
-                    if (s > 2u) h[2] = (uint8_t)(w.x >> 8);
-                }
-            }
-        }
-        __syncthreads();
-        /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
-        for (u32 i = (u32)tid; i < 4u * nl; i += NT) {        /* four lanes per group, a word each: the phase is as long as its longest lane */
-            const int gl = sm.elist[i >> 2], q = q0 + gl;
-            const u32 sub = i & 3u;
-            const u32 gg = sm.gi[gl];
-            if (roomy && gg == GI_CLEAN) continue;           /* turned out clean: stored above */
-            const u32 ins = gg >> 16;
-            const int vbs = (int)((gg >> 8) & 0xFFu) - 4 * (int)sub;           /* valid bytes from this word on */
-            if (vbs <= 0) continue;
-            const u32 wv = sm.win[4 * q + (int)sub];
-            u32 pos = chunk_byte0 + 16u * (u32)q + sm.gpre[gl] + 4u * sub + (u32)__popc(ins & ((1u << (4u * sub)) - 1u));
-            u32 is = ins >> (4u * sub);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k < vbs) {
-                    if (is & 1u) { if (pos < cap) fout[pos] = 3; pos++; }
-                    if (pos < cap) fout[pos] = (uint8_t)(wv >> (24 - 8 * k));
-                    pos++;
-                    is >>= 1;
-                }
-            }
-        }
-        ins_total += t0 + t1 + t2 + t3;
-        if (q0 + EPASS < n_groups) __syncthreads();          /* list, counts and offsets are reused by the next pass (the caller
-                                                                 puts a barrier behind the last one) */
-    }
-    return ins_total - ins_in;
-}
 
 constexpr int RW_CHUNK_BYTES = CH * 4;
 
@@ -388,7 +185,7 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
     __syncthreads();
     volatile u32 *st = state + 1 + (size_t)sl * max_chunks;
     /* (with a look-back the emit stage returns the insertions up to and including this chunk) */
-    const u32 ins_incl = emit_window(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
+    const u32 ins_incl = emit_window<RewriteSmem, NT>(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
     if (tid == 0 && byte0 + (u64)chunk_bytes >= total_bytes) sizes[sl] = (u32)total_bytes + ins_incl;   /* the slice's last chunk */
 }
 
@@ -403,6 +200,7 @@ cudaError_t launch_rewrite(const H264GpuRewriteDesc *d_desc, int n_slices, int m
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)n_slices * (unsigned)max_chunks;
     e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);   /* ticket + look-back words */
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_sizes, 0, sizeof(uint32_t) * (size_t)n_slices, stream);   /* a slice with more chunks than max_chunks reports 0 */
     if (e != cudaSuccess) return e;
     rewrite_slices_kernel<<<grid, NT, smem, stream>>>(d_desc, n_slices, max_chunks, d_src, d_out, d_sizes, d_state);
     return cudaGetLastError();

@@ -300,7 +300,10 @@ annexb_starts_kernel(const uint8_t *__restrict__ data, unsigned long long n_byte
         while (m) {
             const int i = __ffs((int)m) - 1;
             m &= m - 1u;
+            /* max_nals + 1 positions are kept: record max_nals - 1 ends at the start code behind it (slot max_nals holds the
+               count, so the extra position lives one word further) */
             if (k < max_nals) starts[k] = (u32)(t0 + 16u * (u64)r + (u64)i + 3u);
+            else if (k == max_nals) starts[max_nals + 1u] = (u32)(t0 + 16u * (u64)r + (u64)i + 3u);
             k++;
         }
     }
@@ -310,10 +313,11 @@ annexb_starts_kernel(const uint8_t *__restrict__ data, unsigned long long n_byte
 __global__ void __launch_bounds__(256)
 annexb_units_kernel(const uint8_t *__restrict__ data, unsigned long long n_bytes, const u32 *__restrict__ starts, u32 max_nals,
                     H264GpuNalUnit *__restrict__ units) {
-    const u32 n = min(starts[max_nals], max_nals);
+    const u32 n_all = starts[max_nals], n = min(n_all, max_nals);
     for (u32 k = blockIdx.x * 256u + threadIdx.x; k < n; k += gridDim.x * 256u) {
         const u64 b = starts[k];
-        u64 e = k + 1u < n ? (u64)starts[k + 1u] - 3u : n_bytes;
+        /* the unit ends in front of the next start code - also when that one opens a unit beyond max_nals */
+        u64 e = k + 1u < n_all ? (u64)starts[k + 1u < max_nals ? k + 1u : max_nals + 1u] - 3u : n_bytes;
         while (e > b && data[e - 1u] == 0) e--;              /* "remove trailing zeros before next start code" */
         H264GpuNalUnit u;
         u.offset = (u32)b + 1u;                              /* payload behind the header byte, as NALUnit.data */
@@ -329,15 +333,13 @@ annexb_units_kernel(const uint8_t *__restrict__ data, unsigned long long n_bytes
 cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int max_chunks, const uint8_t *d_src,
                             uint8_t *d_out, uint32_t *d_sizes, uint32_t *d_state, cudaStream_t stream) {
     if (n_nals <= 0 || max_chunks <= 0) return cudaSuccess;
-    static bool ready = false;
     const int smem = (int)sizeof(UnescapeSmem);
-    if (!ready) {
-        cudaError_t e = cudaFuncSetAttribute(unescape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        ready = true;
-    }
+    /* (per call: function attributes belong to the calling thread's current device) */
+    cudaError_t e = cudaFuncSetAttribute(unescape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)n_nals * (unsigned)max_chunks;
-    cudaError_t e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);
+    e = cudaMemsetAsync(d_state, 0, sizeof(uint32_t) * (1 + (size_t)grid), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_sizes, 0, sizeof(uint32_t) * (size_t)n_nals, stream);   /* an empty payload (or one with more chunks than max_chunks) reports 0 */
     if (e != cudaSuccess) return e;
     unescape_kernel<<<grid, UT, smem, stream>>>(d_desc, n_nals, max_chunks, d_src, d_out, d_sizes, d_state);
     return cudaGetLastError();
@@ -346,11 +348,11 @@ cudaError_t launch_unescape(const H264GpuUnescapeDesc *d_desc, int n_nals, int m
 int unescape_chunk_bytes() { return UCHUNK; }
 
 cudaError_t launch_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
-                                uint32_t *d_scratch /* 2 + max_nals + chunks */, cudaStream_t stream) {
+                                uint32_t *d_scratch /* 3 + max_nals + chunks */, cudaStream_t stream) {
     if (n_bytes == 0 || max_nals == 0) return cudaSuccess;
     const unsigned chunks = (unsigned)((n_bytes + PCHUNK - 1) / PCHUNK);
-    uint32_t *starts = d_scratch, *state = d_scratch + max_nals + 1;
-    cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t) * ((size_t)max_nals + 2 + chunks), stream);
+    uint32_t *starts = d_scratch, *state = d_scratch + max_nals + 2;    /* starts[0 .. max_nals), the count, one more start */
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t) * ((size_t)max_nals + 3 + chunks), stream);
     if (e != cudaSuccess) return e;
     annexb_starts_kernel<<<chunks, PT, 0, stream>>>(d_data, (unsigned long long)n_bytes, starts, max_nals, state);
     unsigned g2 = (max_nals + 255u) / 256u;
@@ -359,6 +361,6 @@ cudaError_t launch_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNa
     return cudaGetLastError();
 }
 
-size_t parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals) { return (size_t)max_nals + 2 + (n_bytes + PCHUNK - 1) / PCHUNK; }
+size_t parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals) { return (size_t)max_nals + 3 + (n_bytes + PCHUNK - 1) / PCHUNK; }
 
 }  /* namespace h264scroll */

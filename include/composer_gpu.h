@@ -115,9 +115,22 @@ typedef struct {
 #define H264GPU_MAX_REGIONS 512
 #define H264GPU_MAX_MB_W    1023   /* widest frame the composer stages (16368 px) */
 
-/* ---- device lifecycle -------------------------------------------------- */
-int         h264gpu_init(int device);          /* idempotent per device    */
-void        h264gpu_shutdown(void);
+/* ---- device lifecycle --------------------------------------------------
+ *
+ * A context = one device + the scratch the host-buffer calls cache on it (device and pinned memory, streams, events).
+ * h264gpu_init(device) makes the DEFAULT context, which every call uses unless the calling host thread has picked
+ * another one with h264gpu_ctx_make_current.  The reference is single-threaded with no globals (distinct Composer
+ * objects are independent); here distinct contexts are: one host thread + one context per GPU run side by side without
+ * sharing a lock, a stream or a byte of scratch.  Calls on ONE context from several threads are safe, the
+ * host-buffer calls among them serialise.  Every call (re)selects its context's device for the calling thread.
+ */
+typedef struct H264GpuCtx H264GpuCtx;
+int         h264gpu_init(int device);          /* makes / replaces the default context; idempotent per device */
+void        h264gpu_shutdown(void);            /* destroys the default context */
+H264GpuCtx *h264gpu_ctx_create(int device);    /* NULL on failure (h264gpu_last_error) */
+void        h264gpu_ctx_destroy(H264GpuCtx *ctx);
+int         h264gpu_ctx_make_current(H264GpuCtx *ctx);   /* for the calling host thread; NULL = back to the default context */
+int         h264gpu_ctx_device(const H264GpuCtx *ctx);
 int         h264gpu_device_count(void);
 const char *h264gpu_last_error(void);
 int         h264gpu_sm_count(void);
@@ -163,7 +176,9 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
 
 /*
  * Expand region lists into dense hint maps on the device
- * (replaces the per-MB region test of src/h264_writer.c:598-620).
+ * (replaces the per-MB region test of src/h264_writer.c:598-620).  The descriptors live in device memory, so nothing
+ * about them can be refused here: region_count > H264GPU_MAX_REGIONS is invalid, the kernel then paints the first
+ * H264GPU_MAX_REGIONS regions only (h264gpu_compose_regions_host, which sees the descriptors, rejects it).
  */
 int h264gpu_raster_regions(const H264GpuRasterDesc *d_rdesc, int n_frames, int max_mbs_per_frame,
                            const H264GpuRegion *d_regions,
@@ -291,8 +306,11 @@ typedef struct {
 /* words of scratch h264gpu_parse_annexb needs for a stream of n_bytes and up to max_nals units */
 size_t h264gpu_parse_annexb_scratch_words(size_t n_bytes, uint32_t max_nals);
 
-/* d_data must be readable 20 bytes past n_bytes and 16-byte aligned.  The unit count lands in d_scratch[max_nals]
- * (it may exceed max_nals: then only the first max_nals records were written).  Asynchronous on `stream`. */
+/* d_data must be readable 20 bytes past n_bytes and 16-byte aligned; n_bytes < 4 GiB.  The unit count lands in
+ * d_scratch[max_nals]; it may exceed max_nals: then the first max_nals records were written, each of them complete (the
+ * last one ends at the start code behind it).  Unlike nal_parser_next, which stops at an empty unit (two start codes
+ * back to back, or one at the very end), the scan reports such a unit as a record of size 0 and type 0 and goes on.
+ * Asynchronous on `stream`. */
 int h264gpu_parse_annexb(const uint8_t *d_data, size_t n_bytes, H264GpuNalUnit *d_units, uint32_t max_nals,
                          uint32_t *d_scratch, void *stream);
 

@@ -60,5 +60,10 @@ def test_parse_composed_stream(gpu, po):
     frames, _ = gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload)
     stream = np.concatenate(frames)
     _check(gpu, stream)
-    units, count = gpu.parse_annexb(stream, 10)              # fewer records than units: the count still tells
-    assert count == b.n_frames and len(units) == 10
+    # fewer records than units: the count still tells, and every written record - the last one too - is complete
+    for max_nals in (1, 10, b.n_frames - 1):
+        units, count = gpu.parse_annexb(stream, max_nals)
+        assert count == b.n_frames and len(units) == max_nals
+        want = _cpu_units(gpu.lib, stream)[:max_nals]
+        got = [(int(u["offset"]), int(u["size"]), int(u["nal_ref_idc"]), int(u["nal_unit_type"])) for u in units]
+        assert got == want
