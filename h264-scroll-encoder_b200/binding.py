@@ -25,7 +25,7 @@ REFERENCE_API_SYMBOLS = [
     # include/composer.h
     "composer_init", "composer_get_width", "composer_get_height", "composer_write_header",
     "composer_write_scroll_frame", "composer_get_output_size", "composer_get_output",
-    "composer_write_to_file", "composer_finish", "composer_write_scroll_frames",
+    "composer_write_to_file", "composer_finish", "composer_write_scroll_frames", "composer_write_hinted_frames",
     # include/h264_writer.h
     "composer_config_init", "composer_config_set_sps_params", "composer_config_set_pps_params",
     "h264_generate_sps", "h264_generate_pps", "h264_rewrite_idr_frame", "h264_rewrite_as_non_idr_i_frame",
@@ -349,3 +349,21 @@ class Composer(C.Structure):
                 ("orig_pps", C.c_void_p), ("orig_pps_size", C.c_size_t),
                 ("nw", NALWriter), ("output_buffer", C.c_void_p), ("output_capacity", C.c_size_t),
                 ("rbsp_temp", C.c_void_p), ("rbsp_capacity", C.c_size_t), ("frames_written", C.c_int)]
+
+
+class ComposerMotionRegion(C.Structure):
+    _fields_ = [("mb_x0", C.c_int16), ("mb_y0", C.c_int16), ("mb_x1", C.c_int16), ("mb_y1", C.c_int16),
+                ("mv_x_px", C.c_int16), ("mv_y_px", C.c_int16), ("ref_idx", C.c_uint8)]
+
+
+class ComposerMbInfo(C.Structure):
+    _fields_ = [("mv_x_qpel", C.c_int16), ("mv_y_qpel", C.c_int16), ("ref_idx", C.c_uint8), ("intra", C.c_uint8)]
+
+
+class ComposerDynRegion(C.Structure):
+    _fields_ = [("mb_x0", C.c_int16), ("mb_y0", C.c_int16), ("mb_x1", C.c_int16), ("mb_y1", C.c_int16),
+                ("payload", C.c_void_p), ("payload_bytes", C.c_size_t), ("mb_bit_off", C.c_void_p), ("mb_info", C.c_void_p)]
+
+
+class ComposerFrameHints(C.Structure):
+    _fields_ = [("offset_px", C.c_int), ("regions", C.c_void_p), ("n_regions", C.c_int), ("dyn", C.c_void_p)]

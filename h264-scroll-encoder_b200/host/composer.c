@@ -153,6 +153,14 @@ int composer_write_scroll_frames(Composer *c, const int *offsets, int n) {
     return 0;
 }
 
+int composer_write_hinted_frames(Composer *c, const ComposerFrameHints *frames, int n) {
+    int made = 0;
+    if (n <= 0) return 0;
+    if (!frames || h264_write_hinted_sequence(&c->nw, &c->cfg, frames, n, &made) < 0) return -1;
+    c->frames_written += n;
+    return 0;
+}
+
 size_t composer_get_output_size(Composer *c) { return nal_writer_get_size(&c->nw); }
 uint8_t *composer_get_output(Composer *c) { return nal_writer_get_output(&c->nw); }
 

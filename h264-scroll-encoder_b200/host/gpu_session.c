@@ -106,6 +106,9 @@ static int compose_chunk(const LegacyFrame *fr, int n, int mb_w, int mb_h,
         rd[f].mb_w = (uint16_t)mb_w;
         rd[f].mb_h = (uint16_t)mb_h;
         rd[f].dyn_info_off = 0;
+        /* quarter-pel MVs travel as int16: offsets beyond +-8191 px cannot be coded here (the reference's int arithmetic
+           would go on; its hardware-decoder limit is +-512 px, include/h264_writer.h:23-24) */
+        if (L->mv_top_qpel < -32768 || L->mv_top_qpel > 32767 || L->mv_bot_qpel < -32768 || L->mv_bot_qpel > 32767) return H264GPU_ERR_ARG;
         int split = L->split_row < 0 ? 0 : (L->split_row > mb_h ? mb_h : L->split_row);
         H264GpuRegion *r = &reg[2 * f];
         memset(r, 0, 2 * sizeof *r);
@@ -168,5 +171,128 @@ int gpu_session_compose_legacy(const LegacyFrame *frames, int n, int mb_w, int m
     if (rc && rc != H264GPU_ERR_NO_DEVICE)
         fprintf(stderr, "Error: GPU compose failed (%d: %s)\n", rc, h264gpu_last_error());
     *total = done_bytes;
+    return rc;
+}
+
+/* ------------------------------------------------------------ hinted frames */
+
+#include "composer.h"
+
+/* a frame with hints: worst-case inline code 104 bits per macroblock, payload once, 3/2 for emulation prevention */
+static uint32_t hinted_slot_cap(size_t n_mbs, size_t payload_bytes) {
+    return (uint32_t)up(256 + n_mbs * 20 + payload_bytes * 3 / 2, 16);
+}
+
+int gpu_session_compose_hinted(const LegacyFrame *fr, const HintOverlay *ov, int n, int mb_w, int mb_h,
+                               uint8_t *dst, size_t cap, uint32_t *sizes, size_t *total) {
+    *total = 0;
+    if (n <= 0) return 0;
+    if (mb_w <= 0 || mb_h <= 0 || mb_w > H264GPU_MAX_MB_W) return H264GPU_ERR_ARG;
+    const size_t n_mbs = (size_t)mb_w * mb_h, hint_stride = up(n_mbs, 2);
+
+    /* sizes of the batch's arrays */
+    size_t n_reg = 0, n_info = 0, n_tab = 0, n_pay = 0;
+    int n_dyn = 0;
+    for (int f = 0; f < n; f++) {
+        n_reg += 2;
+        if (!ov || (!ov[f].regions && !ov[f].dyn)) continue;
+        if (ov[f].n_regions < 0 || ov[f].n_regions + 3 > H264GPU_MAX_REGIONS) return H264GPU_ERR_ARG;
+        n_reg += (size_t)ov[f].n_regions;
+        const ComposerDynRegion *d = ov[f].dyn;
+        if (d) {
+            if (d->mb_x0 < 0 || d->mb_y0 < 0 || d->mb_x1 > mb_w || d->mb_y1 > mb_h || d->mb_x1 <= d->mb_x0 || d->mb_y1 <= d->mb_y0)
+                return H264GPU_ERR_ARG;                          /* the rectangle must lie inside the frame */
+            const size_t m = (size_t)(d->mb_x1 - d->mb_x0) * (size_t)(d->mb_y1 - d->mb_y0);
+            if (m > 65535 || !d->mb_bit_off || !d->mb_info || (d->payload_bytes && !d->payload)) return H264GPU_ERR_ARG;
+            if ((size_t)d->mb_bit_off[m] > 8 * d->payload_bytes) return H264GPU_ERR_ARG;
+            n_reg += 1; n_info += m; n_tab += m + 1; n_pay += up(d->payload_bytes, 4); n_dyn++;
+        }
+    }
+    H264GpuFrameDesc *desc = calloc((size_t)n, sizeof *desc);
+    H264GpuRasterDesc *rd = calloc((size_t)n, sizeof *rd);
+    H264GpuRegion *reg = calloc(n_reg, sizeof *reg);
+    H264GpuMbHint *info = calloc(n_info ? n_info : 1, sizeof *info);
+    H264GpuDynDesc *dyn = calloc((size_t)(n_dyn ? n_dyn : 1), sizeof *dyn);
+    uint32_t *tab = calloc(n_tab ? n_tab : 1, sizeof *tab);
+    uint8_t *pay = calloc(n_pay + 4, 1);
+    uint64_t *offs = calloc((size_t)n + 1, sizeof *offs);
+    int rc = (desc && rd && reg && info && dyn && tab && pay && offs) ? 0 : H264GPU_ERR_NOMEM;
+
+    size_t r = 0, i0 = 0, t0 = 0, p0 = 0, slots = 0;
+    int y = 0;
+    for (int f = 0; f < n && !rc; f++) {
+        const LegacyFrame *L = &fr[f];
+        const ComposerDynRegion *d = ov ? ov[f].dyn : NULL;
+        const uint32_t slot = hinted_slot_cap(n_mbs, d ? d->payload_bytes : 0);
+        memcpy(desc[f].hdr_bits, L->hdr, sizeof L->hdr);
+        desc[f].hint_off = hint_stride * (size_t)f;
+        desc[f].out_off = slots;
+        desc[f].out_cap = slot;
+        slots += slot;
+        desc[f].dyn_id = H264GPU_NO_DYN;
+        desc[f].mb_w = (uint16_t)mb_w; desc[f].mb_h = (uint16_t)mb_h;
+        desc[f].hdr_nbits = (uint8_t)L->hdr_nbits;
+        desc[f].num_refs = (uint8_t)L->num_refs;
+        desc[f].flags = H264GPU_SKIP_OFF | H264GPU_PRED_REF;      /* the reference's coding decisions */
+        desc[f].nal_header = (uint8_t)L->nal_header;
+        rd[f].region_first = (uint32_t)r;
+        rd[f].hint_off = desc[f].hint_off;
+        rd[f].mb_w = (uint16_t)mb_w; rd[f].mb_h = (uint16_t)mb_h;
+        rd[f].dyn_info_off = (uint32_t)i0;
+        /* the scroll frame's two bands (src/h264_writer.c:598-617) ... */
+        if (L->mv_top_qpel < -32768 || L->mv_top_qpel > 32767 || L->mv_bot_qpel < -32768 || L->mv_bot_qpel > 32767) { rc = H264GPU_ERR_ARG; break; }
+        int split = L->split_row < 0 ? 0 : (L->split_row > mb_h ? mb_h : L->split_row);
+        reg[r].mb_x1 = (int16_t)mb_w; reg[r].mb_y1 = (int16_t)split;
+        reg[r].mv_y_qpel = (int16_t)L->mv_top_qpel; reg[r].ref_idx = (uint8_t)L->ref_top; r++;
+        reg[r].mb_y0 = (int16_t)split; reg[r].mb_x1 = (int16_t)mb_w; reg[r].mb_y1 = (int16_t)mb_h;
+        reg[r].mv_y_qpel = (int16_t)L->mv_bot_qpel; reg[r].ref_idx = (uint8_t)L->ref_bot; r++;
+        /* ... the caller's motion rectangles over them, in list order ... */
+        const ComposerMotionRegion *mr = ov ? (const ComposerMotionRegion *)ov[f].regions : NULL;
+        for (int k = 0; mr && k < ov[f].n_regions; k++) {
+            if (mr[k].mv_x_px < -8192 || mr[k].mv_x_px > 8191 || mr[k].mv_y_px < -8192 || mr[k].mv_y_px > 8191 || mr[k].ref_idx >= L->num_refs) { rc = H264GPU_ERR_ARG; break; }
+            reg[r].mb_x0 = mr[k].mb_x0; reg[r].mb_y0 = mr[k].mb_y0; reg[r].mb_x1 = mr[k].mb_x1; reg[r].mb_y1 = mr[k].mb_y1;
+            reg[r].mv_x_qpel = (int16_t)(4 * mr[k].mv_x_px); reg[r].mv_y_qpel = (int16_t)(4 * mr[k].mv_y_px);
+            reg[r].ref_idx = mr[k].ref_idx; r++;
+        }
+        /* ... and the dynamic rectangle on top of everything */
+        if (d && !rc) {
+            const size_t m = (size_t)(d->mb_x1 - d->mb_x0) * (size_t)(d->mb_y1 - d->mb_y0);
+            reg[r].mb_x0 = d->mb_x0; reg[r].mb_y0 = d->mb_y0; reg[r].mb_x1 = d->mb_x1; reg[r].mb_y1 = d->mb_y1;
+            reg[r].kind = H264GPU_REGION_DYN; reg[r].dyn_base = 0; r++;
+            for (size_t j = 0; j < m; j++) {
+                const ComposerMbInfo *q = &d->mb_info[j];
+                info[i0 + j].mv_x_qpel = q->intra ? 0 : q->mv_x_qpel;
+                info[i0 + j].mv_y_qpel = q->intra ? 0 : q->mv_y_qpel;
+                info[i0 + j].ref_idx = q->intra ? 0 : q->ref_idx;
+                info[i0 + j].kind = q->intra ? H264GPU_MB_DYN_INTRA : H264GPU_MB_DYN_INTER;
+                info[i0 + j].dyn_idx = (uint16_t)j;
+                if (d->mb_bit_off[j + 1] < d->mb_bit_off[j]) rc = H264GPU_ERR_ARG;
+            }
+            memcpy(tab + t0, d->mb_bit_off, (m + 1) * sizeof *tab);
+            if (d->payload_bytes) memcpy(pay + p0, d->payload, d->payload_bytes);
+            dyn[y].payload_off = p0; dyn[y].table_off = t0; dyn[y].n_mbs = (uint32_t)m;
+            dyn[y].payload_bytes = (uint32_t)up(d->payload_bytes, 4);
+            desc[f].dyn_id = (uint32_t)y;
+            i0 += m; t0 += m + 1; p0 += up(d->payload_bytes, 4); y++;
+        }
+        rd[f].region_count = (uint32_t)(r - rd[f].region_first);
+    }
+    if (!rc) {
+        H264GpuHostBatch b;
+        memset(&b, 0, sizeof b);
+        b.desc = desc; b.n_frames = n; b.rdesc = rd; b.regions = reg; b.n_regions = r;
+        b.dyn_info = n_info ? info : NULL; b.n_dyn_info = n_info;
+        b.dyn = n_dyn ? dyn : NULL; b.n_dyn = n_dyn;
+        b.dyn_tab = n_tab ? tab : NULL; b.n_tab = n_tab;
+        b.payload = n_pay ? pay : NULL; b.payload_bytes = n_pay;
+        b.n_hints = hint_stride * (size_t)n; b.slots_bytes = slots; b.max_mbs_per_frame = (int)n_mbs;
+        pthread_mutex_lock(&g_lock);
+        rc = session_init();
+        if (!rc) rc = h264gpu_compose_regions_host(&b, dst, cap, offs, sizes, 0);
+        pthread_mutex_unlock(&g_lock);
+        if (!rc) *total = (size_t)offs[n];
+        else if (rc != H264GPU_ERR_NO_DEVICE) fprintf(stderr, "Error: GPU compose failed (%d: %s)\n", rc, h264gpu_last_error());
+    }
+    free(desc); free(rd); free(reg); free(info); free(dyn); free(tab); free(pay); free(offs);
     return rc;
 }

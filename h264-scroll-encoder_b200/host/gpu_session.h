@@ -28,4 +28,23 @@ typedef struct {
 int gpu_session_compose_legacy(const LegacyFrame *frames, int n, int mb_w, int mb_h,
                                uint8_t *dst, size_t cap, uint32_t *sizes, size_t *total);
 
+/* what rides on top of a legacy frame (include/composer.h); NULL members = nothing */
+typedef struct {
+    const void *regions;      /* ComposerMotionRegion[n_regions] */
+    int n_regions;
+    const void *dyn;          /* ComposerDynRegion or NULL */
+} HintOverlay;
+
+/*
+ * The same for frames with UI hints on top (overlay[i] may be NULL): region lists, per-macroblock neighbour info,
+ * offset tables and payload go through h264gpu_compose_regions_host in one pipelined batch.
+ */
+int gpu_session_compose_hinted(const LegacyFrame *frames, const HintOverlay *overlay, int n, int mb_w, int mb_h,
+                               uint8_t *dst, size_t cap, uint32_t *sizes, size_t *total);
+
+
+/* h264_writer.c: the composer's per-frame sequence with hints on top (frames = ComposerFrameHints[n], include/composer.h).
+   Returns the NAL units appended or -1; on -1 neither the writer nor cfg has changed. */
+int h264_write_hinted_sequence(void *nal_writer, void *composer_config, const void *frames, int n, int *waypoints_made);
+
 #endif

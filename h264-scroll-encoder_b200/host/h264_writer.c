@@ -363,3 +363,48 @@ int h264_write_scroll_sequence(NALWriter *nw, ComposerConfig *cfg, const int *of
     if (waypoints_made) *waypoints_made = made;
     return k;
 }
+
+/*
+ * The same sequence with UI hints on top of every scroll frame (include/composer.h: ComposerFrameHints;
+ * docs/MASTER_DESIGN.md:105-133,142-171).  Waypoint frames stay plain scroll frames.
+ */
+#include "composer.h"
+int h264_write_hinted_sequence(void *nal_writer, void *composer_config, const void *frames_v, int n, int *waypoints_made) {
+    NALWriter *nw = nal_writer;
+    ComposerConfig *cfg = composer_config;
+    const ComposerFrameHints *hf = frames_v;
+    if (n <= 0) return 0;
+    LegacyFrame *fr = malloc(sizeof(LegacyFrame) * 2 * (size_t)n);
+    HintOverlay *ov = calloc(2 * (size_t)n, sizeof(HintOverlay));
+    uint32_t *sizes = malloc(sizeof(uint32_t) * 2 * (size_t)n);
+    if (!fr || !ov || !sizes) { free(fr); free(ov); free(sizes); return -1; }
+    ComposerConfig st = *cfg;                         /* evolve a copy; commit on success */
+    int k = 0, made = 0;
+    for (int i = 0; i < n; i++) {
+        if (h264_needs_waypoint(&st, hf[i].offset_px)) {
+            describe_frame(&st, hf[i].offset_px, 1, &fr[k++]);
+            register_waypoint(&st, hf[i].offset_px);
+            st.frame_num++;
+            made++;
+        }
+        describe_frame(&st, hf[i].offset_px, 0, &fr[k]);
+        ov[k].regions = hf[i].regions;
+        ov[k].n_regions = hf[i].regions ? hf[i].n_regions : 0;
+        ov[k].dyn = hf[i].dyn;
+        k++;
+        st.frame_num++;
+    }
+    size_t total = 0;
+    int rc = gpu_session_compose_hinted(fr, ov, k, cfg->mb_width, cfg->mb_height, nw->output + nw->output_pos,
+                                        nw->output_capacity - nw->output_pos, sizes, &total);
+    free(fr); free(ov); free(sizes);
+    if (rc == H264GPU_ERR_OVERFLOW) {                 /* the reference asserts here (src/nal.c:34,59) */
+        fprintf(stderr, "h264_writer: output buffer overflow\n");
+        abort();
+    }
+    if (rc) return -1;
+    nw->output_pos += total;
+    *cfg = st;
+    if (waypoints_made) *waypoints_made = made;
+    return k;
+}

@@ -51,6 +51,50 @@ void     composer_finish(Composer *c);
  * composes them in one GPU batch.  Returns 0, or -1 on a device error. */
 int      composer_write_scroll_frames(Composer *c, const int *offsets, int n);
 
+/* ---- addition: hinted frames --------------------------------------------
+ *
+ * The UI hints of docs/MASTER_DESIGN.md:58-64,105-133: per frame a list of motion-only rectangles and the
+ * dynamic rectangle whose macroblocks arrive pre-encoded (:142-171).  The reference has no code for them (its only
+ * per-frame input is offset_px, include/composer.h:79); here they ride on top of the scroll frame:
+ *
+ *   composer_write_hinted_frames(c, frames, n) appends, for every frame, exactly what composer_write_scroll_frame(c,
+ *   frames[i].offset_px) would - the waypoint frame first when the offset asks for one (src/composer.c:257-262), with
+ *   the same frame_num / long-term-reference bookkeeping - except that the scroll frame's macroblocks under
+ *   frames[i].regions carry those regions' motion (later regions occlude earlier ones, the dynamic rectangle occludes
+ *   everything, docs/MASTER_DESIGN.md:213-217) and the macroblocks of frames[i].dyn are the caller's pre-encoded bits,
+ *   spliced in at their macroblock addresses.  Waypoint frames are plain scroll frames: they become long-term
+ *   references and must not hold dynamic content.  All n frames go through the GPU in one batch.
+ *   Returns 0, or -1 (invalid hints, device error); on -1 nothing was appended.
+ */
+typedef struct {
+    int16_t mb_x0, mb_y0, mb_x1, mb_y1;   /* half-open macroblock rectangle (clipped to the frame) */
+    int16_t mv_x_px, mv_y_px;             /* displacement in whole pixels, as the reference codes them (x4 quarter-pel) */
+    uint8_t ref_idx;                      /* 0 = RefA, 1 = RefB, 2 + i = waypoint i of this stream */
+} ComposerMotionRegion;
+
+typedef struct {
+    int16_t mv_x_qpel, mv_y_qpel;         /* what neighbours see of a pre-encoded macroblock (their MV predictors) */
+    uint8_t ref_idx;
+    uint8_t intra;                        /* 1: intra coded (neighbours see ref -1, mv 0; src/h264_writer.c:636-640) */
+} ComposerMbInfo;
+
+typedef struct {
+    int16_t mb_x0, mb_y0, mb_x1, mb_y1;   /* where the macroblocks go, row-major inside the rectangle: n = w * h of them */
+    const uint8_t  *payload;              /* their bits, MSB first */
+    size_t          payload_bytes;
+    const uint32_t *mb_bit_off;           /* n + 1 offsets: macroblock j owns payload bits [off[j], off[j + 1]) */
+    const ComposerMbInfo *mb_info;        /* n records */
+} ComposerDynRegion;
+
+typedef struct {
+    int offset_px;                        /* the scroll position underneath (two bands over RefA / RefB / waypoints) */
+    const ComposerMotionRegion *regions;  /* motion-only rectangles over it */
+    int n_regions;
+    const ComposerDynRegion *dyn;         /* the dynamic rectangle on top, or NULL */
+} ComposerFrameHints;
+
+int      composer_write_hinted_frames(Composer *c, const ComposerFrameHints *frames, int n);
+
 #ifdef __cplusplus
 }
 #endif
