@@ -9,6 +9,9 @@ Workload (config.workload): BASELINE.json configs[4] "batched 1024 independent 1
 across 8xB200": every GPU takes 128 streams x 64 frames of the config-3 layout (static chrome, three
 carousels, a two-reference vertical grid, a 25x25-MB spliced dynamic region), so the
 8-GPU run is exactly the 1024-stream batch and per-GPU work is fixed (weak scaling, no collective).
+--workload config4 | config2 | config1 time the other named resolutions the same way (each line with its own
+roofline, cpu_baseline and e2e); the default line carries their kernel-only fractions under "other_configs",
+the side kernels' under "side_kernels" and the per-call latency of the drop-in frame writer under "latency".
 
 A step = one pass of the hot path over the rank's whole batch.
   value   MB/s with all inputs resident in HBM (dense hint maps, payload, descriptors): the compose kernel
@@ -42,6 +45,16 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+class _HintsView:
+    """One frame's hints behaving like the whole batch's array for tests/helpers.py (which slices [f * stride : ...])."""
+
+    def __init__(self, frame_hints, first):
+        self.h, self.first = frame_hints, first
+
+    def __getitem__(self, sl):
+        return self.h[sl.start - self.first:sl.stop - self.first]
 
 
 class ClockSampler:
@@ -125,37 +138,51 @@ def bind_to_gpu_numa_node(index):
 
 # --------------------------------------------------------------------------------------- reference arm
 
-def cpu_sample(po, streams=2, frames=8):
-    """Bounded sample of the same workload as dense hints for the CPU code."""
+def cpu_sample(po, args):
+    """Bounded sample of the selected workload as dense hints for the CPU code: (batch, hints[n, mbs], tables[n, stride] | None,
+    payload | None, what)."""
     from h264_scroll_encoder_b200 import workloads, abi
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    b = workloads.make_config5(streams, frames)
+    wl = args.workload
+    if wl == "compose":
+        b, what = workloads.make_config5(2, 8), "2 streams x 8 frames of the config-5 workload"
+    elif wl == "config4":
+        b, what = workloads.make_config4(4), "4 frames of config 4"
+    elif wl == "config2":
+        b, what = workloads.make_config2(16), "16 frames of config 2"
+    else:
+        b, what = workloads.make_config1(1, 32), "32 frames of config 1 (coded with their own num_refs; one header for all)"
     hints = np.zeros((b.n_frames, b.n_mbs), abi.HINT)
     for f in range(b.n_frames):
         r0, rc = int(b.rdesc["region_first"][f]), int(b.rdesc["region_count"][f])
-        hints[f] = po.raster_regions_numpy(b.regions[r0:r0 + rc], b.mb_w, b.mb_h, b.dyn_info[int(b.rdesc["dyn_info_off"][f]):])
-    # per-frame tables re-based on one shared payload buffer
-    tab = np.zeros((b.n_frames, 626), np.uint32)
-    for f in range(b.n_frames):
-        t0 = int(b.dyn["table_off"][f])
-        tab[f] = b.dyn_tab[t0:t0 + 626] + np.uint32(8 * int(b.dyn["payload_off"][f]))
-    return b, np.ascontiguousarray(hints), np.ascontiguousarray(tab), b.payload
+        di = b.dyn_info[int(b.rdesc["dyn_info_off"][f]):] if b.dyn is not None else None
+        hints[f] = po.raster_regions_numpy(b.regions[r0:r0 + rc], b.mb_w, b.mb_h, di)
+    tab = None
+    if b.dyn is not None:                                    # per-frame tables re-based on one shared payload buffer
+        stride = int(b.dyn["n_mbs"][0]) + 1
+        tab = np.zeros((b.n_frames, stride), np.uint32)
+        for f in range(b.n_frames):
+            t0 = int(b.dyn["table_off"][f])
+            tab[f] = b.dyn_tab[t0:t0 + stride] + np.uint32(8 * int(b.dyn["payload_off"][f]))
+        tab = np.ascontiguousarray(tab)
+    return b, np.ascontiguousarray(hints), tab, b.payload, what
 
 
-def run_cpu(po, threads, target_seconds, kind=None):
+def run_cpu(po, threads, target_seconds, args, kind=None):
     """Time the reference's CPU path (oracle/_ref when present, else the oracle port) on `threads` threads."""
     use_ref = po.have_ref() if kind is None else (kind == "reference")
     chk = po.Ref() if use_ref else po.Oracle()
-    b, hints, tab, payload = cpu_sample(po)
-    hdr = b.desc["hdr_bits"][0].copy()
-    nb = int(b.desc["hdr_nbits"][0])
+    b, hints, tab, payload, what = cpu_sample(po, args)
+    hdr = b.desc["hdr_bits"][b.n_frames - 1].copy()
+    nb = int(b.desc["hdr_nbits"][b.n_frames - 1])
+    nrefs = int(b.desc["num_refs"][b.n_frames - 1])
+    stride = tab.shape[1] if tab is not None else 0
     # calibrate reps on one thread
-    t1, _ = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, 2, 0, hdr, nb, payload, tab, 626, 1)
+    t1, _ = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, nrefs, 0, hdr, nb, payload, tab, stride, 1)
     reps = max(1, int(target_seconds / max(t1, 1e-6)))
     res = [None] * threads
 
     def work(i):
-        res[i] = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, 2, 0, hdr, nb, payload, tab, 626, reps)
+        res[i] = chk.time_hinted(hints, b.n_frames, b.mb_w, b.mb_h, nrefs, 0, hdr, nb, payload, tab, stride, reps)
 
     ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     t0 = time.perf_counter()
@@ -166,8 +193,8 @@ def run_cpu(po, threads, target_seconds, kind=None):
     wall = time.perf_counter() - t0
     mbs = threads * reps * b.n_frames * b.n_mbs
     return {"value": mbs / wall, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": "%d threads x %d passes over %d frames (2 streams x 8 frames of the config-5 workload, "
-                      "%d MBs/frame, dense hints), %.1f s wall" % (threads, reps, b.n_frames, b.n_mbs, wall)}, wall, reps
+            "sample": "%d threads x %d passes over %d frames (%s, %d MBs/frame, dense hints), %.1f s wall"
+                      % (threads, reps, b.n_frames, what, b.n_mbs, wall)}, wall, reps
 
 
 def main_reference(args):
@@ -179,7 +206,7 @@ def main_reference(args):
     threads = os.cpu_count() or 1
     vals, walls = [], []
     for i in range(args.warmup + args.steps):
-        r, wall, reps = run_cpu(po, threads, target_seconds=max(1.0, 20.0 / max(args.steps + args.warmup, 1)))
+        r, wall, reps = run_cpu(po, threads, max(1.0, 20.0 / max(args.steps + args.warmup, 1)), args)
         if i >= args.warmup:
             vals.append(r["value"]); walls.append(wall)
         last = r
@@ -194,14 +221,71 @@ def main_reference(args):
     return 0
 
 
-def workload_config(args):
-    return {"workload": "config5: batched independent 1080p UI streams, %d streams x %d frames per GPU "
-                        "(1920x1088 = 120x68 MBs, config-3 layout with a 25x25-MB spliced dynamic region, "
-                        "num_refs 2, skip OFF, reference predictor)" % (args.streams, args.frames),
-            "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "mbs_per_frame": 8160,
-            "l2_policy": "inputs larger than L2: %.0f MB of hints + payload per GPU per step vs 126 MB L2"
-                         % ((args.streams * args.frames * (8160 * 8 + 23500)) / 1e6),
-            "sharding": "streams block-partitioned over ranks, no collective"}
+def build_batch(args, rank=0, world=1):
+    """The rank's batch of the selected workload (region lists + payload; every frame an independent unit of work)."""
+    from h264_scroll_encoder_b200 import workloads, sharding
+    wl = args.workload
+    if wl == "compose":                                       # config 5: weak scaling, args.streams streams per rank
+        first, count = sharding.shard_streams(args.streams * world, rank, world)
+        return workloads.make_config5(count, args.frames, stream0=first)
+    if wl == "config4":                                       # 64 frames (t = 0..63) x copies: 133 MB of hints at 8 copies
+        return workloads.repeat_batch(workloads.make_config4(64), args.copies or 8)
+    if wl == "config2":                                       # 250 frames x copies: 720p + splice, 167 MB at 16 copies
+        return workloads.repeat_batch(workloads.make_config2(250), args.copies or 16)
+    if wl == "config1":                                       # 248 frames x streams: 228 MB of hints at 32 streams
+        return workloads.make_config1(args.copies or 32, 248)
+    raise SystemExit("unknown workload " + wl)
+
+
+def workload_config(args, b=None):
+    names = {
+        "compose": "config5: batched independent 1080p UI streams, %d streams x %d frames per GPU (1920x1088 = 120x68 MBs, "
+                   "config-3 layout with a 25x25-MB spliced dynamic region, num_refs 2, skip OFF, reference predictor)"
+                   % (args.streams, args.frames),
+        "config4": "config4: 3840x2160 (240x135 MBs) full-frame scroll with per-row varying MVs, every MB a non-zero mvd, "
+                   "64 frames x %d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or 8),
+        "config2": "config2: 1280x720 legacy scroll 0->720->0 at speed 4 with a 25x25-MB spliced dynamic region, 250 frames x "
+                   "%d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or 16),
+        "config1": "config1: experiments/scroll-encoder twin, 1280x720, 248 frames from offset 496 at speed 1 (first frame the "
+                   "waypoint frame, num_refs 2 -> 3) x %d streams per GPU, skip OFF, reference predictor" % (args.copies or 32),
+    }
+    shape = {"compose": (args.streams * args.frames, 8160), "config4": (64 * (args.copies or 8), 32400),
+             "config2": (250 * (args.copies or 16), 3600), "config1": (248 * (args.copies or 32), 3600)}[args.workload]
+    cfg = {"workload": names[args.workload], "sharding": "streams block-partitioned over ranks, no collective",
+           "frames_per_gpu": shape[0], "mbs_per_frame": shape[1],
+           "l2_policy": "inputs larger than L2: %.0f MB of dense hints (+ the spliced payload) per GPU per step vs 126 MB L2"
+                        % (8 * shape[0] * shape[1] / 1e6)}
+    if args.workload == "compose":
+        cfg.update({"streams_per_gpu": args.streams, "frames_per_stream": args.frames})
+    if b is not None:
+        assert (b.n_frames, b.n_mbs) == shape
+    return cfg
+
+
+def algorithmic_bytes(b, sizes):
+    """hints once (8 B/MB) + payload once + offset tables + output once + descriptors."""
+    n = b.n_frames
+    s_dyn = tab = 0
+    if b.dyn is not None:
+        ends = b.dyn["table_off"].astype(np.int64) + b.dyn["n_mbs"].astype(np.int64)
+        s_dyn = int((b.dyn_tab[ends] // 8).sum())
+        tab = int(4 * (b.dyn["n_mbs"].astype(np.int64) + 1).sum())
+    return 8 * n * b.n_mbs + s_dyn + tab + int(sizes.sum()) + 64 * n
+
+
+def check_bit_exact(po, b, hints_of, frames_of, n_check=64, seed=11):
+    """>= n_check frames of the timed run's output against the reference's own functions (oracle/_ref) or the port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    chk, kind = (po.Ref(), "reference") if po.have_ref() else (po.Oracle(), "port")
+    pick = np.random.default_rng(seed).choice(b.n_frames, min(n_check, b.n_frames), replace=False)
+    for f in pick:
+        f = int(f)
+        want = helpers.checker_frame(chk, b, hints_of(f), f)
+        got = frames_of(f)
+        if not np.array_equal(got, want):
+            return {"bit_exact": False, "frames_checked": int(len(pick)), "checker": kind, "first_bad_frame": f}
+    return {"bit_exact": True, "frames_checked": int(len(pick)), "checker": kind}
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -212,22 +296,25 @@ def main_ours(args):
     from h264_scroll_encoder_b200 import binding, workloads, abi
     dist = None
     if world > 1:
-        import torch
+        # the data path has no collective (nothing reduces across streams): the process group only carries the barrier
+        # around the timed region and the max / sum of the timings - gloo, no NCCL anywhere
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
     numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     gc = binding.GpuComposer(local)      # raises if the CUDA library or a B200 is missing: no fallback
     L = gc.lib
 
-    b = workloads.make_config5(args.streams, args.frames, stream0=rank * args.streams)
+    b = build_batch(args, rank, world)
     n, n_mbs = b.n_frames, b.n_mbs
+    has_dyn = b.dyn is not None
     total_mbs = n * n_mbs
 
     # ---- device-resident inputs -------------------------------------------------------------------
-    pay_pad = np.concatenate([b.payload, np.zeros(16, np.uint8)])
     d_desc, d_rdesc, d_reg = gc.to_device(b.desc), gc.to_device(b.rdesc), gc.to_device(b.regions)
-    d_info, d_dyn, d_tab, d_pay = gc.to_device(b.dyn_info), gc.to_device(b.dyn), gc.to_device(b.dyn_tab), gc.to_device(pay_pad)
+    d_info = d_dyn = d_tab = d_pay = None
+    if has_dyn:
+        pay_pad = np.concatenate([b.payload, np.zeros(16, np.uint8)])
+        d_info, d_dyn, d_tab, d_pay = gc.to_device(b.dyn_info), gc.to_device(b.dyn), gc.to_device(b.dyn_tab), gc.to_device(pay_pad)
     d_hints = gc.alloc(8 * b.hint_stride * n)
     d_out = gc.alloc(b.slot_cap * n)
     d_sizes = gc.alloc(4 * n)
@@ -276,7 +363,7 @@ def main_ours(args):
         gc.raster_regions(d_rdesc, n, n_mbs, d_reg, d_info, d_hints)
     gc.check(L.h264gpu_event_record(ev1, None))
     raster_ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / 5
-    raster_bytes = 8 * total_mbs + b.regions.nbytes + b.rdesc.nbytes + b.dyn_info.nbytes     # map written, lists and dyn-info read
+    raster_bytes = 8 * total_mbs + b.regions.nbytes + b.rdesc.nbytes + (b.dyn_info.nbytes if has_dyn else 0)   # map written, lists and dyn-info read
 
     if hasattr(L, "h264gpu_debug_stage_cycles"):                  # timing-instrumented experiment build only
         cyc = (ctypes.c_uint64 * 16)()
@@ -288,116 +375,35 @@ def main_ours(args):
     ablate = bool(os.environ.get("H264SCROLL_BENCH_NOCHECK"))      # timing experiments on deliberately incomplete kernels
     assert ablate or ((sizes <= b.slot_cap).all() and (sizes > 5).all()), "a frame overflowed its slot"
     s_out = int(sizes.sum())
-    s_dyn = int(sum(int(b.dyn_tab[int(b.dyn["table_off"][f]) + 625]) for f in range(n)) // 8)
-    b_alg = 8 * total_mbs + s_dyn + 4 * 626 * n + s_out + 64 * n
+    b_alg = algorithmic_bytes(b, sizes)
+
+    # ---- the metric says "bit-exact": sampled frames of the timed run against the reference's functions ----
+    exact = None
+    if rank == 0 and not ablate and not args.no_check:
+        po_ = ge.load_oracle()
+        exact = check_bit_exact(
+            po_, b,
+            lambda f: _HintsView(d_hints.download(abi.HINT, count=b.n_mbs, offset=8 * b.hint_stride * f), b.hint_stride * f),
+            lambda f: d_out.download(np.uint8, count=int(sizes[f]), offset=int(b.desc["out_off"][f])))
+        assert exact["bit_exact"], "GPU output differs from the %s checker in frame %d" % (exact["checker"], exact["first_bad_frame"])
 
     # ---- end to end: host buffers in, packed Annex-B stream out, every step ------------------------
-    # The batch goes through in chunks of frames on a few streams, so that the H2D of one chunk, the kernels of
-    # another and the D2H of a third overlap (PCIe is full duplex).  Every byte of input still crosses the bus
-    # every step and every byte of the packed stream comes back.
-    def pinned(a):
-        a = np.ascontiguousarray(a)
-        p = L.h264gpu_host_alloc(max(a.nbytes, 16))
-        v = np.ctypeslib.as_array((ctypes.c_uint8 * max(a.nbytes, 1)).from_address(p))
-        v[:a.nbytes] = a.view(np.uint8).reshape(-1)
-        return p
+    # ONE C-ABI call (h264gpu_compose_regions_host, the call a host application makes): pinned host region lists +
+    # payload in, packed Annex-B stream out.  The library cuts the batch into frame chunks and keeps upload, kernels and
+    # download on three streams (PCIe is full duplex); every input byte crosses the bus every step, every stream byte
+    # comes back.
     n_chunks = max(1, min(args.e2e_chunks, n))
-    bounds = [n * c // n_chunks for c in range(n_chunks + 1)]
-
-    def edge(arr_off, item, f, total):        # byte offset where frame f's share of a per-frame-indexed array starts
-        return int(arr_off[f]) * item if f < n else total
-    arrays = [  # (host array, device buffer, byte range of frames [f0, f1))
-        (b.desc, d_desc, lambda f: f * b.desc.itemsize),
-        (b.rdesc, d_rdesc, lambda f: f * b.rdesc.itemsize),
-        (b.regions, d_reg, lambda f: edge(b.rdesc["region_first"], b.regions.itemsize, f, b.regions.nbytes)),
-        (b.dyn_info, d_info, lambda f: edge(b.rdesc["dyn_info_off"], b.dyn_info.itemsize, f, b.dyn_info.nbytes)),
-        (b.dyn, d_dyn, lambda f: f * b.dyn.itemsize),
-        (b.dyn_tab, d_tab, lambda f: edge(b.dyn["table_off"], 4, f, b.dyn_tab.nbytes)),
-        (b.payload, d_pay, lambda f: edge(b.dyn["payload_off"], 1, f, b.payload.nbytes)),
-    ]
-    ups = [(pinned(a), d, rng) for a, d, rng in arrays]
-    h2d_bytes = sum(a.nbytes for a, _, _ in arrays)
-    chunk_frames = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
-    chunk_cap = b.slot_cap * chunk_frames // 2
-    d_packed_c = gc.alloc(chunk_cap * n_chunks)
-    d_offs_c = gc.alloc(8 * (chunk_frames + 1) * n_chunks)
-    h_out = L.h264gpu_host_alloc(b.slot_cap * n // 2)
-    h_offs = L.h264gpu_host_alloc(8 * (chunk_frames + 1) * n_chunks)
-    offs_view = np.ctypeslib.as_array((ctypes.c_uint64 * ((chunk_frames + 1) * n_chunks)).from_address(h_offs))
-    streams = [L.h264gpu_stream_create() for _ in range(min(args.e2e_streams, n_chunks))]
-    LAG = args.e2e_lag
-
-    zero_copy = args.e2e_zero_copy      # measured slower than the copy engine (8.8 vs 7.3 ms per step): off by default
-    h_out_c = L.h264gpu_host_alloc(chunk_cap * n_chunks) if zero_copy else None
-
-    def e2e_step_zero_copy():
-        # the pack kernel writes the Annex-B stream of each chunk (and its frame offsets) straight into pinned host
-        # memory: the device->host transfer happens inside the kernel, no size has to come back before it starts
-        for c in range(n_chunks):
-            f0, f1, st = bounds[c], bounds[c + 1], streams[c % len(streams)]
-            for p, d, rng in ups:
-                o0, o1 = rng(f0), rng(f1)
-                if o1 > o0:
-                    gc.check(L.h264gpu_memcpy_h2d(d.ptr + o0, p + o0, o1 - o0, st))
-            gc.check(L.h264gpu_raster_regions(d_rdesc.ptr + f0 * b.rdesc.itemsize, f1 - f0, n_mbs, d_reg.ptr, d_info.ptr,
-                                              d_hints.ptr, st))
-            gc.check(L.h264gpu_compose_batch(d_desc.ptr + f0 * b.desc.itemsize, f1 - f0, d_hints.ptr, d_dyn.ptr, d_tab.ptr,
-                                             d_pay.ptr, d_out.ptr, d_sizes.ptr + 4 * f0, st))
-            oo = 8 * (chunk_frames + 1) * c
-            gc.check(L.h264gpu_pack_frames(d_desc.ptr + f0 * b.desc.itemsize, d_sizes.ptr + 4 * f0, f1 - f0, d_out.ptr,
-                                           h_out_c + chunk_cap * c, h_offs + oo, st))
-        for st in streams:
-            gc.check(L.h264gpu_stream_sync(st))
-        total = 0
-        for c in range(n_chunks):
-            tot = int(offs_view[(chunk_frames + 1) * c + (bounds[c + 1] - bounds[c])])
-            assert tot <= chunk_cap, "packed chunk larger than its buffer"
-            total += tot
-        return total
-
-    def e2e_step_staged():
-        total = 0
-        for c in range(n_chunks + LAG):
-            if c < n_chunks:
-                f0, f1, st = bounds[c], bounds[c + 1], streams[c % len(streams)]
-                for p, d, rng in ups:
-                    o0, o1 = rng(f0), rng(f1)
-                    if o1 > o0:
-                        gc.check(L.h264gpu_memcpy_h2d(d.ptr + o0, p + o0, o1 - o0, st))
-                gc.check(L.h264gpu_raster_regions(d_rdesc.ptr + f0 * b.rdesc.itemsize, f1 - f0, n_mbs, d_reg.ptr, d_info.ptr,
-                                                  d_hints.ptr, st))
-                gc.check(L.h264gpu_compose_batch(d_desc.ptr + f0 * b.desc.itemsize, f1 - f0, d_hints.ptr, d_dyn.ptr, d_tab.ptr,
-                                                 d_pay.ptr, d_out.ptr, d_sizes.ptr + 4 * f0, st))
-                oo = 8 * (chunk_frames + 1) * c
-                gc.check(L.h264gpu_pack_frames(d_desc.ptr + f0 * b.desc.itemsize, d_sizes.ptr + 4 * f0, f1 - f0, d_out.ptr,
-                                               d_packed_c.ptr + chunk_cap * c, d_offs_c.ptr + oo, st))
-                gc.check(L.h264gpu_memcpy_d2h(h_offs + oo, d_offs_c.ptr + oo, 8 * (f1 - f0 + 1), st))
-            d = c - LAG
-            if d >= 0:
-                st = streams[d % len(streams)]
-                gc.check(L.h264gpu_stream_sync(st))
-                tot = int(offs_view[(chunk_frames + 1) * d + (bounds[d + 1] - bounds[d])])
-                assert tot <= chunk_cap, "packed chunk larger than its buffer"
-                gc.check(L.h264gpu_memcpy_d2h(h_out + total, d_packed_c.ptr + chunk_cap * d, tot, st))
-                total += tot
-        for st in streams:
-            gc.check(L.h264gpu_stream_sync(st))
-        return total
-
-    # The same pipeline behind ONE C-ABI call (h264gpu_compose_regions_host): the library cuts the batch into chunks and
-    # drives streams, events and copies itself, so no Python sits between the enqueues.  This is the call a host
-    # application makes; the two functions above are kept for comparison (--e2e-python).
     hb, hb_keep = gc.make_host_batch(b, pinned=True)
-    h_stream_cap = b.slot_cap * n // 2
+    h2d_bytes = b.h2d_bytes()
+    h_stream_cap = b.slot_cap * n // 2 if has_dyn else b.slot_cap * n
+    h_out = L.h264gpu_host_alloc(h_stream_cap)
     h_offs_all = L.h264gpu_host_alloc(8 * (n + 1))
     h_sizes_all = L.h264gpu_host_alloc(4 * n)
     offs_all_view = np.ctypeslib.as_array((ctypes.c_uint64 * (n + 1)).from_address(h_offs_all))
 
-    def e2e_step_capi():
+    def e2e_step():
         gc.compose_regions_host(hb, h_out, h_stream_cap, h_offs_all, h_sizes_all, n_chunks)
         return int(offs_all_view[n])
-
-    e2e_step = e2e_step_zero_copy if zero_copy else (e2e_step_staged if args.e2e_python else e2e_step_capi)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -410,7 +416,7 @@ def main_ours(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert ablate or d2h == s_out, "packed stream size differs from the sum of the frame sizes"
     e2e_launches = 5 * n_chunks                                  # raster + compose (2 instantiations) + pack (2 kernels) per chunk
-    if e2e_step is e2e_step_capi and not ablate:
+    if not ablate:
         # the stream the call returned is the concatenation of the slots the kernel-only run left on the device
         fo = np.array(offs_all_view, dtype=np.uint64)
         assert np.array_equal(fo[1:] - fo[:-1], sizes.astype(np.uint64)), "end-to-end frame sizes differ from the kernel-only run"
@@ -422,13 +428,8 @@ def main_ours(args):
     # ---- reduce over ranks (max time) ------------------------------------------------------------
     ms_step, e2e_step_s = ms / args.steps, e2e_s
     if dist is not None:
-        import torch
-        t = torch.tensor([ms_step, e2e_step_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_step_s = float(t[0]), float(t[1])
-        tm = torch.tensor([float(total_mbs), float(b_alg)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.SUM)
-        job_mbs = float(tm[0])
+        from h264_scroll_encoder_b200 import sharding
+        (ms_step, e2e_step_s), (job_mbs, _) = sharding.reduce_job(dist, "cpu", [ms_step, e2e_step_s], [float(total_mbs), float(b_alg)])
     else:
         job_mbs = float(total_mbs)
 
@@ -439,20 +440,19 @@ def main_ours(args):
             "metric": METRIC, "value": job_mbs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "config": workload_config(args, b), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks) + (4 * n if e2e_step is e2e_step_capi else 0)), "ms_per_step": 1e3 * e2e_step_s,
+                    "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks) + 4 * n), "ms_per_step": 1e3 * e2e_step_s,
                     "chunks": n_chunks, "gpu_launches_per_step": e2e_launches, "host_numa_node": numa_node,
-                    "path": ("pinned host region lists + payload -> H2D -> raster -> compose -> pack writes the Annex-B stream "
-                             "into pinned host memory (D2H inside the kernel)" if zero_copy else
-                             ("one h264gpu_compose_regions_host call: " if e2e_step is e2e_step_capi else "") +
-                             "pinned host region lists + payload -> H2D -> raster -> compose -> pack -> D2H packed stream")
-                            + ", in %d frame chunks over %d streams" % (n_chunks, 3 if e2e_step is e2e_step_capi else len(streams))},
+                    "path": "one h264gpu_compose_regions_host call: pinned host region lists + payload -> H2D -> raster -> compose "
+                            "-> pack -> D2H packed stream, in %d frame chunks over 3 streams" % n_chunks},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": "of " + peak_kind, "traffic": None, "kernel": "compose_frames_kernel",
                          "algorithmic_bytes_per_launch": int(b_alg), "bytes_per_mb": b_alg / total_mbs,
                          "kernel_ms": ms / args.steps},
         }
+        if exact is not None:
+            line.update(exact)
         line["raster"] = {"kernel": "raster_regions_kernel", "ms": raster_ms, "algorithmic_bytes": int(raster_bytes),
                           "achieved": raster_bytes / (raster_ms * 1e-3) / 1e9, "unit": "GB/s",
                           "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak}
@@ -464,13 +464,70 @@ def main_ours(args):
                 pass
         if world == 1 and not args.no_cpu:
             po = ge.load_oracle()
-            cb, _, _ = run_cpu(po, 1, target_seconds=12.0)
+            cb, _, _ = run_cpu(po, 1, 10.0, args)
             line["cpu_baseline"] = cb
+        if world == 1 and args.workload == "compose" and not args.no_extras:
+            line.update(default_line_extras(args, gc))
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def quick_kernel_fraction(gc, args, wl):
+    """Kernel-only timing of another named configuration (inputs resident in HBM, larger than L2): its roofline fraction."""
+    from h264_scroll_encoder_b200 import abi
+    a = argparse.Namespace(**vars(args))
+    a.workload, a.copies = wl, 0
+    b = build_batch(a)
+    L, n = gc.lib, b.n_frames
+    d_desc, d_rdesc, d_reg = gc.to_device(b.desc), gc.to_device(b.rdesc), gc.to_device(b.regions)
+    d_info = d_dyn = d_tab = d_pay = None
+    if b.dyn is not None:
+        d_info, d_dyn, d_tab = gc.to_device(b.dyn_info), gc.to_device(b.dyn), gc.to_device(b.dyn_tab)
+        d_pay = gc.to_device(np.concatenate([b.payload, np.zeros(16, np.uint8)]))
+    d_hints, d_out, d_sizes = gc.alloc(8 * b.hint_stride * n), gc.alloc(b.slot_cap * n), gc.alloc(4 * n)
+    gc.raster_regions(d_rdesc, n, b.n_mbs, d_reg, d_info, d_hints)
+    ev0, ev1 = L.h264gpu_event_create(), L.h264gpu_event_create()
+    for _ in range(3):
+        gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
+    gc.sync()
+    steps = 5
+    gc.check(L.h264gpu_event_record(ev0, None))
+    for _ in range(steps):
+        gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
+    gc.check(L.h264gpu_event_record(ev1, None))
+    ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / steps
+    sizes = d_sizes.download(np.uint32)
+    assert (sizes <= b.slot_cap).all() and (sizes > 5).all()
+    exact = check_bit_exact(ge.load_oracle(), b,
+                            lambda f: _HintsView(d_hints.download(abi.HINT, count=b.n_mbs, offset=8 * b.hint_stride * f), b.hint_stride * f),
+                            lambda f: d_out.download(np.uint8, count=int(sizes[f]), offset=int(b.desc["out_off"][f])), n_check=16)
+    b_alg = algorithmic_bytes(b, sizes)
+    peak, _ = peaks()
+    for x in (d_desc, d_rdesc, d_reg, d_info, d_dyn, d_tab, d_pay, d_hints, d_out, d_sizes):
+        if x is not None:
+            x.free()
+    return {"workload": workload_config(a, b)["workload"], "kernel_ms": ms, "value": n * b.n_mbs / (ms * 1e-3), "unit": UNIT,
+            "bytes_per_mb": b_alg / (n * b.n_mbs), "achieved": b_alg / (ms * 1e-3) / 1e9, "frac": b_alg / (ms * 1e-3) / 1e9 / peak,
+            "bit_exact": exact["bit_exact"], "frames_checked": exact["frames_checked"]}
+
+
+def default_line_extras(args, gc):
+    """What the default line carries beside the config-5 numbers, so that the driver records them too."""
+    extras = {"other_configs": {}, "side_kernels": {}}
+    for wl in ("config4", "config2", "config1"):
+        extras["other_configs"][wl] = quick_kernel_fraction(gc, args, wl)
+    a = argparse.Namespace(**vars(args))
+    a.no_cpu, a.steps, a.warmup = True, 10, 3
+    for name, fn in (("rewrite", main_rewrite), ("unescape", main_unescape)):
+        ln = fn(a)
+        extras["side_kernels"][name] = {"kernel": ln["roofline"]["kernel"], "ms": ln["ms_per_step"], "frac": ln["roofline"]["frac"],
+                                        "achieved": ln["roofline"]["achieved"], "unit": "GB/s", "workload": ln["config"]["workload"]}
+    a.no_cpu = args.no_cpu
+    extras["latency"] = main_latency(a)["resolutions"]
+    return extras
 
 
 # ------------------------------------------------------------------------ second workload: slice rewrite
@@ -544,8 +601,7 @@ def main_rewrite(args):
                          "algorithmic_bytes_per_launch": int(n * S + out_bytes)}}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_rewrite_baseline(src[:S].copy(), S)
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 def cpu_rewrite_baseline(rbsp, S):
@@ -633,8 +689,46 @@ def main_unescape(args):
         wall = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": reps * S / wall, "unit": "B/s", "cores": 1, "kind": kind,
                                 "sample": "%d calls of ebsp_to_rbsp on one %d-byte payload, %.1f s wall" % (reps, S, wall)}
-    print(json.dumps(line))
-    return 0
+    return line
+
+
+def main_latency(args):
+    """Per-call latency of the drop-in frame writer: h264_write_scroll_p_frame (one frame per call, the reference's API,
+    src/composer.c:255-264) through this library on the GPU, and the reference's own function on one host core."""
+    ge.load_package()
+    from h264_scroll_encoder_b200 import binding, workloads
+    gc = binding.GpuComposer(0)
+    lib = gc.lib
+    lib.h264_write_scroll_p_frame.restype = ctypes.c_size_t
+    out = {}
+    po = ge.load_oracle()
+    for (w, h) in ((1280, 720), (1920, 1088)):
+        offs = [int(o) for o in workloads.legacy_schedule(400, 1, 480)]      # below the first waypoint: scroll frames only
+        cfg = binding.ComposerConfig()
+        lib.composer_config_init(ctypes.byref(cfg), w, h)
+        lib.composer_config_set_sps_params(ctypes.byref(cfg), 4, 2, 4)
+        lib.composer_config_set_pps_params(ctypes.byref(cfg), 1, 1)
+        cfg.frame_num = 2
+        buf = np.zeros(8 << 20, np.uint8)
+        nw = binding.NALWriter()
+        lat = []
+        for i, o in enumerate(offs):
+            if i % 100 == 0:
+                lib.nal_writer_init(ctypes.byref(nw), ctypes.c_void_p(buf.ctypes.data), ctypes.c_size_t(buf.size), None, ctypes.c_size_t(0))
+            t0 = time.perf_counter()
+            n = lib.h264_write_scroll_p_frame(ctypes.byref(nw), ctypes.byref(cfg), o)
+            lat.append(time.perf_counter() - t0)
+            assert n > 0
+        lat = np.array(lat[50:]) * 1e6
+        e = {"us_per_call_median": float(np.median(lat)), "us_per_call_p90": float(np.percentile(lat, 90)), "calls": int(len(lat))}
+        if po.have_ref() and not args.no_cpu:
+            t, nbytes, nals = po.Ref().time_legacy(w, h, np.array(offs, np.int32), reps=5)
+            e["reference_us_per_call"] = 1e6 * t / nals
+            e["reference_kind"] = "reference (h264_write_scroll_p_frame of /root/reference, one host core)"
+        out["%dx%d" % (w, h)] = e
+    return {"metric": "frame_writer_latency", "unit": "us per h264_write_scroll_p_frame call", "higher_is_better": False,
+            "path": "pinned descriptors read by the kernels over PCIe -> raster -> compose writes the NAL unit and its size into pinned "
+                    "host memory -> one stream sync -> memcpy into the NALWriter", "resolutions": out}
 
 
 def main():
@@ -646,23 +740,24 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="compose", choices=["compose", "rewrite", "unescape"],
-                    help="compose = the north-star metric (default); rewrite = batched I-slice rewrite (SURVEY 8f)")
+    ap.add_argument("--workload", default="compose", choices=["compose", "config4", "config2", "config1", "rewrite", "unescape", "latency"],
+                    help="compose = the north-star metric on config 5 (default); config4 / config2 / config1 = the other named "
+                         "resolutions; rewrite / unescape = side kernels (SURVEY 8f); latency = per-call latency of the frame writer")
+    ap.add_argument("--copies", type=int, default=0, help="config4/2/1: copies of the configuration's frames per GPU (0 = enough to exceed L2)")
     ap.add_argument("--slices", type=int, default=128)
     ap.add_argument("--slice-bytes", type=int, default=1382400)
-    ap.add_argument("--e2e-zero-copy", action="store_true",
-                    help="end-to-end path whose pack kernel writes into pinned host memory instead of a separate D2H copy")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not move the process to the GPU's NUMA node")
-    ap.add_argument("--e2e-python", action="store_true", help="drive the end-to-end pipeline from Python (chunk by chunk) instead of the single C-ABI call")
-    ap.add_argument("--e2e-streams", type=int, default=4)
-    ap.add_argument("--e2e-lag", type=int, default=2, help="chunks in flight before the first packed chunk is fetched")
+    ap.add_argument("--no-check", action="store_true", help="skip the bit-exact check of sampled frames")
+    ap.add_argument("--no-extras", action="store_true", help="default line without other_configs / side_kernels / latency")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="frame chunks the end-to-end path pipelines over streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.workload == "rewrite":
-        return main_rewrite(args)
-    if args.workload == "unescape":
-        return main_unescape(args)
+    if args.workload in ("rewrite", "unescape", "latency"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the compose workloads only"}))
+            return 0
+        print(json.dumps({"rewrite": main_rewrite, "unescape": main_unescape, "latency": main_latency}[args.workload](args)))
+        return 0
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

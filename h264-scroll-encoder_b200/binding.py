@@ -217,10 +217,11 @@ class GpuComposer:
         hb = HostBatch()
         hb.desc, hb.n_frames, hb.rdesc = ptr(b.desc), b.n_frames, ptr(b.rdesc)
         hb.regions, hb.n_regions = ptr(b.regions), len(b.regions)
-        hb.dyn_info, hb.n_dyn_info = ptr(b.dyn_info), len(b.dyn_info)
-        hb.dyn, hb.n_dyn = ptr(b.dyn), len(b.dyn)
-        hb.dyn_tab, hb.n_tab = ptr(b.dyn_tab), len(b.dyn_tab)
-        hb.payload, hb.payload_bytes = ptr(b.payload), b.payload.size
+        n_of = lambda a: 0 if a is None else len(a)
+        hb.dyn_info, hb.n_dyn_info = ptr(b.dyn_info), n_of(b.dyn_info)
+        hb.dyn, hb.n_dyn = ptr(b.dyn), n_of(b.dyn)
+        hb.dyn_tab, hb.n_tab = ptr(b.dyn_tab), n_of(b.dyn_tab)
+        hb.payload, hb.payload_bytes = ptr(b.payload), n_of(b.payload)
         hb.n_hints = int((b.desc["hint_off"] + b.desc["mb_w"].astype(np.int64) * b.desc["mb_h"]).max())
         hb.slots_bytes = int((b.desc["out_off"] + b.desc["out_cap"]).max())
         hb.max_mbs_per_frame = int((b.desc["mb_w"].astype(np.int64) * b.desc["mb_h"]).max())

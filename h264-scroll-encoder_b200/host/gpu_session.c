@@ -148,6 +148,56 @@ static int compose_chunk(const LegacyFrame *fr, int n, int mb_w, int mb_h,
     return 0;
 }
 
+/*
+ * One frame per call - what composer_write_scroll_frame does (src/composer.c:255-264) - is latency, not throughput:
+ * the reference takes ~144 us for a 1280x720 frame.  So no staging copies and no packing here: the three small
+ * descriptors sit in pinned host memory and the kernels read them from there, the compose kernel stores the frame's
+ * bytes and its size straight into pinned host memory, and the host waits once.
+ *     raster_regions (descriptors over PCIe -> dense map in HBM) -> compose_batch (Annex-B bytes over PCIe) -> sync
+ */
+static int compose_one(const LegacyFrame *L, int mb_w, int mb_h, uint8_t *dst, size_t cap, uint32_t *size_out, size_t *written) {
+    const size_t n_mbs = (size_t)mb_w * mb_h;
+    const uint32_t slot = legacy_slot_cap((int)n_mbs);
+    /* pinned: desc | rdesc | 2 regions | size | slot */
+    const size_t p_desc = 0, p_rd = 64, p_reg = 128, p_size = 192, p_slot = 256, p_end = p_slot + slot;
+    int rc = ensure(8 * up(n_mbs, 2), p_end);
+    if (rc) return rc;
+    if (L->mv_top_qpel < -32768 || L->mv_top_qpel > 32767 || L->mv_bot_qpel < -32768 || L->mv_bot_qpel > 32767) return H264GPU_ERR_ARG;
+    H264GpuFrameDesc *desc = (H264GpuFrameDesc *)(S.pin + p_desc);
+    H264GpuRasterDesc *rd = (H264GpuRasterDesc *)(S.pin + p_rd);
+    H264GpuRegion *r = (H264GpuRegion *)(S.pin + p_reg);
+    volatile uint32_t *h_size = (volatile uint32_t *)(S.pin + p_size);
+    memset(desc, 0, sizeof *desc);
+    memcpy(desc->hdr_bits, L->hdr, sizeof L->hdr);
+    desc->out_cap = slot;
+    desc->dyn_id = H264GPU_NO_DYN;
+    desc->mb_w = (uint16_t)mb_w; desc->mb_h = (uint16_t)mb_h;
+    desc->hdr_nbits = (uint8_t)L->hdr_nbits;
+    desc->num_refs = (uint8_t)L->num_refs;
+    desc->flags = H264GPU_SKIP_OFF | H264GPU_PRED_REF;
+    desc->nal_header = (uint8_t)L->nal_header;
+    memset(rd, 0, sizeof *rd);
+    rd->region_count = 2;
+    rd->mb_w = (uint16_t)mb_w; rd->mb_h = (uint16_t)mb_h;
+    const int split = L->split_row < 0 ? 0 : (L->split_row > mb_h ? mb_h : L->split_row);
+    memset(r, 0, 2 * sizeof *r);
+    r[0].mb_x1 = (int16_t)mb_w; r[0].mb_y1 = (int16_t)split;
+    r[0].mv_y_qpel = (int16_t)L->mv_top_qpel; r[0].ref_idx = (uint8_t)L->ref_top;
+    r[1].mb_y0 = (int16_t)split; r[1].mb_x1 = (int16_t)mb_w; r[1].mb_y1 = (int16_t)mb_h;
+    r[1].mv_y_qpel = (int16_t)L->mv_bot_qpel; r[1].ref_idx = (uint8_t)L->ref_bot;
+    *h_size = 0;
+    rc = h264gpu_raster_regions(rd, 1, (int)n_mbs, r, NULL, (H264GpuMbHint *)S.dev, NULL);
+    if (!rc) rc = h264gpu_compose_batch(desc, 1, (const H264GpuMbHint *)S.dev, NULL, NULL, NULL, S.pin + p_slot, (uint32_t *)(S.pin + p_size), NULL);
+    if (!rc) rc = h264gpu_stream_sync(NULL);
+    if (rc) return rc;
+    const uint32_t sz = *h_size;
+    if (sz > slot || sz > cap) return H264GPU_ERR_OVERFLOW;
+    memcpy(dst, S.pin + p_slot, sz);
+    *size_out = sz;
+    *written = sz;
+    return 0;
+}
+
 int gpu_session_compose_legacy(const LegacyFrame *frames, int n, int mb_w, int mb_h,
                                uint8_t *dst, size_t cap, uint32_t *sizes, size_t *total) {
     if (n <= 0) { *total = 0; return 0; }
@@ -155,7 +205,9 @@ int gpu_session_compose_legacy(const LegacyFrame *frames, int n, int mb_w, int m
     pthread_mutex_lock(&g_lock);
     int rc = session_init();
     size_t done_bytes = 0;
-    if (!rc) {
+    if (!rc && n == 1) {
+        rc = compose_one(frames, mb_w, mb_h, dst, cap, sizes, &done_bytes);
+    } else if (!rc) {
         /* bound device scratch to ~1 GiB per launch */
         size_t per_frame = (size_t)mb_w * mb_h * 8 + 2 * (size_t)legacy_slot_cap(mb_w * mb_h) + 256;
         int chunk = (int)((1ull << 30) / per_frame);

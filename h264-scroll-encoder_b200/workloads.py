@@ -304,3 +304,70 @@ def make_random(mb_w, mb_h, n_frames, seed, num_refs=2, flags=0, p_dyn=0.1, mv_r
         pays.append(pay)
     slot = ((b.n_mbs * 16 + sum(len(p) for p in pays) // max(n_frames, 1) * 2 + 4096) + 15) & ~15
     return _finish(b, headers, regs, num_refs, flags, slot, (infos, tabs, pays))
+
+
+def make_config1(n_streams=1, n_frames=248):
+    """Config 1 (experiments/scroll-encoder twin): 1280x720, offsets from 496 px at speed 1 between 0 and 704
+    (experiments/scroll-encoder/src/main.c:387-415); that program writes the waypoint frame INSTEAD of the scroll frame
+    (:418-424), num_refs goes 2 -> 3 behind it.  Slice headers and the two bands per frame come from the host library's
+    state machine (include/h264_writer.h; checked against the reference CLI's stream in tests/test_gpu_legacy_api.py).
+    n_streams copies of the stream make the batch larger than L2."""
+    import ctypes as C
+    from . import binding
+    lib = binding.load_library()
+    b = Batch(80, 45)
+    b.name = "config1: %d x %d frames 1280x720 scroll-encoder twin (waypoint at 496 px, num_refs 2 -> 3)" % (n_streams, n_frames)
+    cfg = binding.ComposerConfig()
+    lib.composer_config_init(C.byref(cfg), 1280, 720)
+    lib.composer_config_set_sps_params(C.byref(cfg), 4, 2, 4)
+    lib.composer_config_set_pps_params(C.byref(cfg), 1, 1)
+    cfg.frame_num = 2
+    headers, regs, nrefs, nalh = [], [], [], []
+    out5, hdr = (C.c_int * 5)(), (C.c_uint64 * 4)()
+    for i in range(n_frames):
+        pos = (i + 496) % (2 * 704)
+        off = pos if pos < 704 else 2 * 704 - pos
+        wf = int(lib.h264_needs_waypoint(C.byref(cfg), off))
+        nbits = lib.h264_p_slice_header_bits(C.byref(cfg), wf, hdr)
+        bits = "".join(format(int(hdr[w]), "064b") for w in range(4))[:nbits]
+        lib.h264_scroll_regions(C.byref(cfg), off, wf, out5)
+        split = max(0, min(int(out5[0]), 45))
+        headers.append(bits)
+        regs.append(np.concatenate([region(0, 0, 80, split, mvy_q=4 * int(out5[2]), ref=int(out5[1])),
+                                    region(0, split, 80, 45, mvy_q=4 * int(out5[4]), ref=int(out5[3]))]))
+        nrefs.append(2 + cfg.num_waypoints)
+        nalh.append(0x41 if wf else 0x01)
+        if wf:                                                   # register the waypoint (src/h264_writer.c:771-777)
+            w = cfg.waypoints[cfg.num_waypoints]
+            w.offset_px, w.long_term_idx, w.valid = off, 2 + cfg.num_waypoints, 1
+            cfg.num_waypoints += 1
+        cfg.frame_num += 1
+    slot = ((b.n_mbs * 6 + 256) + 15) & ~15
+    b = _finish(b, headers * n_streams, regs * n_streams, 2, 0, slot, None, np.array(nalh * n_streams, np.uint8))
+    b.desc["num_refs"] = np.array(nrefs * n_streams, np.uint8)
+    return b
+
+
+def repeat_batch(b, times):
+    """`times` copies of a region-list batch back to back (frame-indexed arrays re-based): the same frames as independent
+    units of work, to make a batch larger than L2."""
+    if times <= 1:
+        return b
+    n = b.n_frames
+    r = Batch(b.mb_w, b.mb_h)
+    r.name, r.slot_cap = b.name + " x%d" % times, b.slot_cap
+    r.desc, r.rdesc = np.tile(b.desc, times), np.tile(b.rdesc, times)
+    k = np.repeat(np.arange(times, dtype=np.uint64), n)
+    r.desc["hint_off"] = np.arange(n * times, dtype=np.uint64) * np.uint64(b.hint_stride)
+    r.desc["out_off"] = np.arange(n * times, dtype=np.uint64) * np.uint64(b.slot_cap)
+    r.rdesc["hint_off"] = r.desc["hint_off"]
+    r.rdesc["region_first"] = (r.rdesc["region_first"].astype(np.uint64) + k * np.uint64(len(b.regions))).astype(np.uint32)
+    r.regions = np.tile(b.regions, times)
+    if b.dyn is not None:
+        r.dyn = np.tile(b.dyn, times)
+        r.dyn["table_off"] = r.dyn["table_off"] + k * np.uint64(len(b.dyn_tab))
+        r.dyn["payload_off"] = r.dyn["payload_off"] + k * np.uint64(len(b.payload))
+        r.desc["dyn_id"] = (np.tile(b.desc["dyn_id"], times).astype(np.uint64) + k * np.uint64(n)).astype(np.uint32)
+        r.rdesc["dyn_info_off"] = (r.rdesc["dyn_info_off"].astype(np.uint64) + k * np.uint64(len(b.dyn_info))).astype(np.uint32)
+        r.dyn_info, r.dyn_tab, r.payload = np.tile(b.dyn_info, times), np.tile(b.dyn_tab, times), np.tile(b.payload, times)
+    return r
