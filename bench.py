@@ -111,29 +111,52 @@ def dist_env():
 
 
 def bind_to_gpu_numa_node(index):
-    """Run this process on the CPUs of the NUMA node GPU `index` hangs off, BEFORE any pinned memory is allocated:
-    the end-to-end path moves ~0.5 GB per step per GPU through pinned host buffers, and with several ranks on a
-    two-socket host buffers on the wrong node cross the socket link twice.  Returns the node (or None)."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bdf = bus.lower()[-12:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
-        if node < 0:
-            return None
+    """Run this process on the CPUs next to GPU `index`, BEFORE any pinned memory is allocated (pinned pages are placed
+    where the allocating thread runs): the end-to-end path moves ~0.5 GB per step per GPU through pinned host buffers,
+    and with several ranks on a multi-socket host buffers on the wrong node cross the socket link twice.
+    Sources, in order: the GPU's numa_node in sysfs; NVML's CPU affinity for the device (what `nvidia-smi topo` prints)
+    when sysfs says -1 (virtualised hosts); a host with one NUMA node needs no binding.
+    Returns what was done: {"node": n | None, "cpus": count, "how": "..."}."""
+    def cpus_of_node(node):
         cpus = set()
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:                                             # noqa: BLE001
-        return None
+        return cpus
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        nodes = []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = -1
+        try:
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        except (OSError, ValueError):
+            pass
+        allowed = os.sched_getaffinity(0)
+        if node >= 0:
+            cpus = cpus_of_node(node) & allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return {"node": node, "cpus": len(cpus), "how": "sysfs numa_node of the GPU"}
+        if len(nodes) <= 1:
+            return {"node": nodes[0] if nodes else 0, "cpus": len(allowed), "how": "host has a single NUMA node: nothing to bind"}
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + i for w, m in enumerate(mask) for i in range(64) if (int(m) >> i) & 1} & allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            on = [n for n in nodes if cpus_of_node(n) & cpus]
+            return {"node": on[0] if len(on) == 1 else None, "cpus": len(cpus), "how": "NVML CPU affinity of the GPU (sysfs numa_node is -1)"}
+        return {"node": None, "cpus": len(allowed), "how": "no topology information (sysfs numa_node -1, NVML affinity = all CPUs)"}
+    except Exception as e:                                        # noqa: BLE001
+        return {"node": None, "cpus": len(os.sched_getaffinity(0)), "how": "not bound: %r" % (e,)}
 
 
 # --------------------------------------------------------------------------------------- reference arm
@@ -300,7 +323,8 @@ def main_ours(args):
         # around the timed region and the max / sum of the timings - gloo, no NCCL anywhere
         import torch.distributed as dist
         dist.init_process_group("gloo")
-    numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
+    numa = {"node": None, "cpus": len(os.sched_getaffinity(0)), "how": "--no-numa-bind"} if args.no_numa_bind else bind_to_gpu_numa_node(local)
+    numa_node = numa["node"]
     gc = binding.GpuComposer(local)      # raises if the CUDA library or a B200 is missing: no fallback
     L = gc.lib
 
@@ -443,7 +467,7 @@ def main_ours(args):
             "config": workload_config(args, b), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": job_mbs / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h + 8 * (n + n_chunks) + 4 * n), "ms_per_step": 1e3 * e2e_step_s,
-                    "chunks": n_chunks, "gpu_launches_per_step": e2e_launches, "host_numa_node": numa_node,
+                    "chunks": n_chunks, "gpu_launches_per_step": e2e_launches, "host_numa_node": numa_node, "host_binding": numa,
                     "path": "one h264gpu_compose_regions_host call: pinned host region lists + payload -> H2D -> raster -> compose "
                             "-> pack -> D2H packed stream, in %d frame chunks over 3 streams" % n_chunks},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
