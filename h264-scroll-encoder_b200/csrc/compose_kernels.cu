@@ -1,33 +1,35 @@
 /*
  * compose_kernels.cu - sm_100a kernels of the P-slice composer.
  *
- * compose_frames_kernel (v4): one CTA composes one frame at a time (grid-stride over frames).
- * A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns one
- * segment, a tile is up to 256 consecutive segments.
+ * compose_frames_kernel: persistent grid (SMs x 2 CTAs of 512 threads, grid-stride over frames); one CTA composes one
+ * frame at a time, all of its warps moving through the stages together (two CTAs per SM overlap each other's barriers;
+ * a warp-specialised coder / packer split of the same work was measured at 1.2-1.9x the time, profiles/r2_kernel_experiments.txt).
+ * A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns one segment, a tile is up to 512
+ * consecutive segments (4096 macroblocks).
  *
- *   stage    the hints of the tile plus the row above it are copied global -> shared with
- *            16-byte cp.async into a swizzled layout (every thread later reads its own 64 bytes
- *            with conflict-free 128-bit loads); the copy of the next tile - of the next frame
- *            when this one ends - is in flight while the current tile is composed
- *   decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test,
- *            mvd, closed-form Exp-Golomb -> a <= 32-bit code + length in registers.  Where a whole
- *            warp sits in uniform motion the constant code is taken instead
- *            (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
+ *   stage    the hints of the tile plus the row above it are copied global -> shared with 16-byte cp.async into a
+ *            swizzled layout (every thread later reads its own 64 bytes with conflict-free 128-bit loads); the copy of
+ *            the next tile - of the next frame when this one ends - is in flight while the current tile is composed.
+ *            The next frame's whole dense map is sent to L2 a frame ahead (cp.async.bulk.prefetch.L2), and the frame's
+ *            pre-encoded payload comes to shared memory with ONE bulk copy through the TMA unit
+ *            (cp.async.bulk.shared.global, completion counted on an mbarrier)
+ *   decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test, mvd, closed-form
+ *            Exp-Golomb -> a <= 32-bit code + length in registers.  Where a whole warp sits in uniform motion the
+ *            constant code is taken instead (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
  *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
  *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
- *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word
- *            integer (picked per warp), shifts it to its slice bit offset and stores whole words;
+ *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word integer (picked per
+ *            warp), shifts it to its slice bit offset and stores whole words into the shared-memory window (32 KB);
  *            partial first/last words of neighbouring threads are merged by shuffle
- *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice
- *            trailer - becomes 16-byte work items that are spread over all lanes of the CTA:
- *            one lane splices one pre-encoded MB (copy_bits, src/h264_writer.c:228) with funnel
- *            shifts, whole words as plain stores, edge words with shared-memory atomicOr
- *   emit     emulation prevention (src/nal.c:24-50) on 16-byte groups: zero-byte masks,
- *            a bit-parallel run-parity rule, prefix sum of the insert counts; groups
- *            without insertions leave as re-aligned 32-bit words (one byte-permute each)
+ *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice trailer - becomes 16-byte
+ *            work items that are spread over all lanes of the CTA: one lane splices one pre-encoded MB (copy_bits,
+ *            src/h264_writer.c:228) with funnel shifts, whole words as plain stores, edge words with atomicOr
+ *   emit     (emit_stage.cuh) emulation prevention (src/nal.c:24-50) on 16-byte groups: the rare groups - a zero byte
+ *            inside, the frame's tail - are compacted into a list first and worked through densely; groups without
+ *            insertions leave as re-aligned 32/128-bit words; the window is cleared with one st.bulk
  *
- * The Annex-B start code, the NAL header byte and the host-written slice header are
- * the first bits of the same bit string, so the window image is the output image.
+ * The Annex-B start code, the NAL header byte and the host-written slice header are the first bits of the same bit
+ * string, so the window image is the output image.
  */
 #include <cuda_runtime.h>
 #include "mb_codec.cuh"
