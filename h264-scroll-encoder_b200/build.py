@@ -31,6 +31,19 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+STAMP = os.path.join(OBJ, "flags.stamp")
+
+
+def _flags_changed():
+    """The objects were built with other flags (an experiment variant built through H264SCROLL_NVCC_EXTRA): everything is
+    stale, whatever the mtimes say - tests and the bench must never run a variant by accident."""
+    want = " ".join(NVCC_FLAGS + CFLAGS)
+    try:
+        return open(STAMP).read() != want
+    except OSError:
+        return os.path.isdir(OBJ) and any(f.endswith(".o") for f in os.listdir(OBJ))
+
+
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cu, c = _sources()
@@ -38,6 +51,7 @@ def build(force=False, verbose=False):
     hdrs += [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc")) if f.endswith((".cuh", ".h"))]
     hdrs += [os.path.join(PKG, "host", f) for f in os.listdir(os.path.join(PKG, "host")) if f.endswith(".h")]
     os.makedirs(OBJ, exist_ok=True)
+    force = force or _flags_changed()
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(PKG, "csrc"), "-I" + os.path.join(PKG, "host")]
     objs, log = [], []
     for f in cu:
@@ -56,6 +70,7 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("gcc failed for %s:\n%s" % (f, r.stderr))
         objs.append(o)
+    open(STAMP, "w").write(" ".join(NVCC_FLAGS + CFLAGS))
     if force or _stale(LIB, objs):
         r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                  "-cudart", "static"], capture_output=True, text=True)
