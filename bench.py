@@ -477,6 +477,18 @@ def main_ours(args):
         }
         if exact is not None:
             line.update(exact)
+        # the end-to-end number against what this pool's hosts can move with `world` ranks copying both ways at once
+        # (profiles/pcie_scaling.json, measured by scripts/pcie_scaling.py on one 8 x B200 box)
+        try:
+            tab = json.load(open(os.path.join(ROOT, "profiles", "pcie_scaling.json")))["ranks"].get(str(world))
+            if tab:
+                bw = tab["both"]["per_rank_mean_gbs"]
+                floor_ms = max(h2d_bytes, d2h) / (bw * 1e9) * 1e3
+                line["e2e"]["bus_ceiling"] = {"both_ways_gbs_per_rank": bw, "floor_ms_per_step": floor_ms,
+                                              "floor_over_measured": floor_ms / (1e3 * e2e_step_s),
+                                              "source": "profiles/pcie_scaling.json (concurrent pinned copies, %d ranks)" % world}
+        except Exception:                                         # noqa: BLE001
+            pass
         line["raster"] = {"kernel": "raster_regions_kernel", "ms": raster_ms, "algorithmic_bytes": int(raster_bytes),
                           "achieved": raster_bytes / (raster_ms * 1e-3) / 1e9, "unit": "GB/s",
                           "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak}
