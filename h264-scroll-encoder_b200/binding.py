@@ -17,7 +17,7 @@ GPU_SYMBOLS = [
     "h264gpu_malloc", "h264gpu_free", "h264gpu_host_alloc", "h264gpu_host_free", "h264gpu_memcpy_h2d",
     "h264gpu_memcpy_d2h", "h264gpu_memset", "h264gpu_stream_create", "h264gpu_stream_destroy",
     "h264gpu_stream_sync", "h264gpu_event_create", "h264gpu_event_destroy", "h264gpu_event_record",
-    "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_raster_regions", "h264gpu_pack_frames",
+    "h264gpu_event_elapsed_ms", "h264gpu_compose_batch", "h264gpu_compose_batch_ex", "h264gpu_raster_regions", "h264gpu_pack_frames",
     "h264gpu_compose_host", "h264gpu_compose_regions_host", "h264gpu_launch_count", "h264gpu_canonicalize_hints",
     "h264gpu_rewrite_slices", "h264gpu_rewrite_chunk_bytes", "h264gpu_unescape_nals", "h264gpu_unescape_chunk_bytes",
     "h264gpu_parse_annexb", "h264gpu_parse_annexb_scratch_words"]
@@ -83,6 +83,7 @@ def load_library(path=None):
     L.h264gpu_event_record.argtypes = [vp, vp]
     L.h264gpu_event_elapsed_ms.argtypes = [vp, vp]; L.h264gpu_event_elapsed_ms.restype = C.c_float
     L.h264gpu_compose_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
+    L.h264gpu_compose_batch_ex.argtypes = [vp, ci, vp, sz, vp, vp, vp, vp, vp, vp]
     L.h264gpu_raster_regions.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     L.h264gpu_pack_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.h264gpu_canonicalize_hints.argtypes = [vp, sz, vp]
@@ -232,10 +233,18 @@ class GpuComposer:
         self.check(self.lib.h264gpu_compose_regions_host(C.byref(hb), h_stream, stream_cap, h_offsets, h_sizes, n_chunks))
 
     # ---- device-pointer calls --------------------------------------------------------------------
-    def compose_batch(self, d_desc, n, d_hints, d_dyn, d_tab, d_payload, d_out, d_sizes, stream=None):
+    def compose_batch(self, d_desc, n, d_hints, d_dyn, d_tab, d_payload, d_out, d_sizes, stream=None, n_hints=None):
+        """n_hints=None: the hints the device buffer holds (its size / 8) - the call then also hands the TMA unit a tensor
+        map of the dense maps (h264gpu_compose_batch_ex); n_hints=0: plain h264gpu_compose_batch."""
         p = lambda b: b.ptr if b is not None else None
-        self.check(self.lib.h264gpu_compose_batch(p(d_desc), n, p(d_hints), p(d_dyn), p(d_tab), p(d_payload),
-                                                  p(d_out), p(d_sizes), stream))
+        if n_hints is None:
+            n_hints = d_hints.nbytes // 8
+        if n_hints:
+            self.check(self.lib.h264gpu_compose_batch_ex(p(d_desc), n, p(d_hints), n_hints, p(d_dyn), p(d_tab), p(d_payload),
+                                                         p(d_out), p(d_sizes), stream))
+        else:
+            self.check(self.lib.h264gpu_compose_batch(p(d_desc), n, p(d_hints), p(d_dyn), p(d_tab), p(d_payload),
+                                                      p(d_out), p(d_sizes), stream))
 
     def raster_regions(self, d_rdesc, n, max_mbs, d_regions, d_dyn_info, d_hints, stream=None):
         p = lambda b: b.ptr if b is not None else None

@@ -263,10 +263,24 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
     H264GpuCtx *ctx = current();
     if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_desc || !d_hints || !d_out || !d_sizes) return fail(H264GPU_ERR_ARG, "null argument");
-    cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload,
+    cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, 0, d_dyn, d_dyn_tab, d_payload,
                                                d_out, d_sizes, ctx->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
     if (n_frames > 0) g_launches.fetch_add(2);        /* reference-mode kernel + SPEC-mode kernel */
+    return H264GPU_OK;
+}
+
+int h264gpu_compose_batch_ex(const H264GpuFrameDesc *d_desc, int n_frames,
+                             const H264GpuMbHint *d_hints, size_t n_hints, const H264GpuDynDesc *d_dyn,
+                             const uint32_t *d_dyn_tab, const uint8_t *d_payload,
+                             uint8_t *d_out, uint32_t *d_sizes, void *stream) {
+    H264GpuCtx *ctx = current();
+    if (!ctx) return H264GPU_ERR_NO_DEVICE;
+    if (n_frames < 0 || !d_desc || !d_hints || !d_out || !d_sizes) return fail(H264GPU_ERR_ARG, "null argument");
+    cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, n_hints, d_dyn, d_dyn_tab, d_payload,
+                                               d_out, d_sizes, ctx->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
+    if (n_frames > 0) g_launches.fetch_add(2);
     return H264GPU_OK;
 }
 
@@ -401,7 +415,7 @@ int h264gpu_compose_host(const H264GpuFrameDesc *h_desc, int n_frames,
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "canonicalize launch", e);
     g_launches.fetch_add(1);
     e = h264scroll::launch_compose((const H264GpuFrameDesc *)(base + o_desc), n_frames,
-                                   (const H264GpuMbHint *)(base + o_hint),
+                                   (const H264GpuMbHint *)(base + o_hint), n_hints,
                                    (const H264GpuDynDesc *)(base + o_dyn),
                                    (const uint32_t *)(base + o_tab), (const uint8_t *)(base + o_pay),
                                    (uint8_t *)(base + o_out), (uint32_t *)(base + o_sz), ctx->sm_count, st);
@@ -591,7 +605,7 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
             if (e == cudaSuccess) e = h264scroll::launch_raster((const H264GpuRasterDesc *)(D + o_rd) + f0, f1 - f0, b->max_mbs_per_frame,
                                                                 (const H264GpuRegion *)(D + o_reg), (const H264GpuMbHint *)(D + o_info),
                                                                 (H264GpuMbHint *)(D + o_hint), s_k);
-            if (e == cudaSuccess) e = h264scroll::launch_compose((const H264GpuFrameDesc *)(D + o_desc) + f0, f1 - f0, (const H264GpuMbHint *)(D + o_hint),
+            if (e == cudaSuccess) e = h264scroll::launch_compose((const H264GpuFrameDesc *)(D + o_desc) + f0, f1 - f0, (const H264GpuMbHint *)(D + o_hint), b->n_hints,
                                                                  (const H264GpuDynDesc *)(D + o_dyn), (const uint32_t *)(D + o_tab),
                                                                  (const uint8_t *)(D + o_pay), (uint8_t *)(D + o_slots), (uint32_t *)(D + o_sz) + f0,
                                                                  ctx->sm_count, s_k);

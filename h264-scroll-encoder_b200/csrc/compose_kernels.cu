@@ -32,6 +32,8 @@
  * string, so the window image is the output image.
  */
 #include <cuda_runtime.h>
+#include <cuda.h>
+#include <string.h>
 #include "mb_codec.cuh"
 #include "kernel_util.cuh"
 #include "emit_stage.cuh"
@@ -45,6 +47,9 @@ constexpr int NW = NT / 32;
 constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass */
 constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
 constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
+constexpr int TBOX_ROWS = 32;            /* TMA box: 32 rows of 128 bytes (4 KB) of the dense map seen as a [rows][32 x u32] tensor */
+constexpr int TBOX_BYTES = TBOX_ROWS * 128;
+static_assert((HBS * 64) % TBOX_BYTES == 0, "the hint tile buffer is a whole number of TMA boxes");
 constexpr u32 FULL = 0xFFFFFFFFu;
 constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
 constexpr int EPASS = EMIT_EG * NT;      /* emit: groups per pass */
@@ -60,9 +65,10 @@ __device__ unsigned long long g_stage_cycles[8];
 #define STAGE_MARK(i) do { } while (0)
 #endif
 
-struct __align__(16) ComposeSmem {
+struct __align__(1024) ComposeSmem {
+    uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks; 1024-byte aligned: the TMA unit's 128-byte
+                                            swizzle works on shared-memory address bits 4-9) */
     u32 win[CH + 8];                     /* slice words [wbase, wbase + CH) of the frame, MSB first (+ read-ahead pad); zero where unwritten */
-    uint4 hbuf[HBS * 4];                 /* the staged hint tile (swizzled 16-byte chunks) */
     union {
         uint4 items[LCAP];               /* work queue (compose stages) */
         u32 gi[EPASS];                   /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
@@ -77,6 +83,7 @@ struct __align__(16) ComposeSmem {
                                             invalidates it: pay_staged = 0, the splice reads global memory again) */
     };
     u64 pay_full;                        /* mbarrier: the frame's payload has landed (bulk copy) */
+    u64 hints_full;                      /* mbarrier: the hint tile has landed (TMA tensor loads) */
     const u32 *pay_smem;                 /* payload word i of the frame = pay_smem[i] for i < pay_staged */
     u32 pay_staged;
     u32 n_list;
@@ -100,10 +107,11 @@ struct FrameGeo {
     int n_seg;            /* tpr * H */
     int seg_max;          /* segments per tile */
     u32 tpr_magic;        /* s / tpr == umulhi(s, tpr_magic) for s < 2^25 (tpr > 1) */
+    int tma_seg0;         /* >= 0: the frame's tiles come by TMA; 64-byte segment index of its first hint in the map (even); -1: cp.async */
 };
 
 __device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict__ descs, int f,
-                                             const H264GpuMbHint *__restrict__ hints) {
+                                             const H264GpuMbHint *__restrict__ hints, unsigned long long tma_hints = 0) {
     const uint4 *dq = (const uint4 *)(descs + f);
     const uint4 d2 = __ldg(dq + 2), d3 = __ldg(dq + 3);
     FrameGeo g;
@@ -112,8 +120,12 @@ __device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict_
     g.H = (int)(d3.z >> 16);
     g.tpr = (g.W + MPT - 1) / MPT;
     g.n_seg = g.tpr * g.H;
-    g.seg_max = min(NT, HBS - g.tpr - 1);
+    g.seg_max = min(NT, HBS - g.tpr - 2);                    /* (one slot in reserve: a TMA tile starts on a 128-byte row) */
     g.tpr_magic = 0xFFFFFFFFu / (u32)g.tpr + 1u;
+    /* TMA: the map's rows are 128 bytes = 16 hints; the frame must start on a row, tile the map with whole segments, and
+       end inside the rows the tensor map covers (tma_hints: 0 when the launch has no tensor map) */
+    const u64 h0 = (u64)d2.x | ((u64)d2.y << 32);
+    g.tma_seg0 = ((g.W & 7) == 0 && (h0 & 15u) == 0 && h0 + (u64)g.W * (u64)g.H <= tma_hints && (h0 >> 3) < 0x7FFF0000ull) ? (int)(h0 >> 3) : -1;
     return g;
 }
 
@@ -141,6 +153,33 @@ __device__ __noinline__ void stage_hints_ragged(uint4 *buf, const uint2 *fh, int
             if (x < W) cp_async8(buf_s + 16u * pc, fh + gi);
             if (x + 1 < W) cp_async8(buf_s + 16u * pc + 8u, fh + gi + 1);
         }
+    }
+}
+
+/* TMA: 2-D tensor load of one box (TBOX_ROWS rows of 128 bytes from row `row` on) into 128-byte-swizzled shared memory */
+__device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *tmap, int row, u64 *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
+}
+
+/*
+ * The same tile by TMA (frames whose geometry allows it, FrameGeo::tma_seg0 >= 0): the dense map is a [rows][128 bytes]
+ * tensor, the tile a run of rows fetched as boxes of TBOX_ROWS rows by ONE thread; SWIZZLE_128B puts 16-byte chunk c of
+ * the tile at chunk c ^ ((c >> 3) & 7) - hint_swizzle, the layout the readers use.  The tile starts on a row: slot q
+ * holds segment (seg0 + s0 - tpr - 1 - shift) + q with shift = parity of the first segment wanted.  Rows in front of the
+ * frame arrive with whatever the map holds there (zeros outside the tensor); the readers' side overwrites those slots.
+ */
+__device__ __forceinline__ void stage_hints_tma(ComposeSmem &sm, const CUtensorMap *tmap, const FrameGeo &g, int s0, int n) {
+    if (threadIdx.x == 0) {
+        const int abs_base = g.tma_seg0 + s0 - g.tpr - 1;
+        const int shift = abs_base & 1;
+        const int n_rows = (n + g.tpr + 1 + shift + 1) >> 1;
+        const int boxes = (n_rows + TBOX_ROWS - 1) / TBOX_ROWS;
+        /* the buffer was read (and, in a frame's first tile, partly written) through the generic proxy: order that first */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&sm.hints_full, (u32)(boxes * TBOX_BYTES));
+        for (int i = 0; i < boxes; i++)
+            tma_load_box((char *)sm.hbuf + i * TBOX_BYTES, tmap, ((abs_base - shift) >> 1) + i * TBOX_ROWS, &sm.hints_full);
     }
 }
 
@@ -298,8 +337,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                       const H264GpuDynDesc *__restrict__ dyns,
                       const u32 *__restrict__ dyn_tab,
                       const uint8_t *__restrict__ payload,
-                      uint8_t *__restrict__ out, u32 *__restrict__ sizes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                      uint8_t *__restrict__ out, u32 *__restrict__ sizes,
+                      const __grid_constant__ CUtensorMap hint_map, unsigned long long tma_hints) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     ComposeSmem &sm = *reinterpret_cast<ComposeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -313,10 +353,13 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             sm.n_items[0] = 0; sm.n_items[1] = 0; sm.n_list = 0;
 #if COMPOSE_BULK_OPS
             mbar_init(&sm.pay_full, 1);
+            mbar_init(&sm.hints_full, 1);
             mbar_init_fence();
 #endif
         }
     }
+    __syncthreads();                   /* (the mbarriers exist before anybody waits on them) */
+    u32 hpar = 0;                      /* phase of sm.hints_full the next TMA-staged tile completes */
     u32 spar = 0;                      /* which sm.scan buffer the next block scan uses */
 #if COMPOSE_BULK_OPS
     u32 pay_par = 0;                   /* phase of sm.pay_full the next payload copy completes */
@@ -327,8 +370,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #if COMPOSE_TIMING
     long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
 #endif
-    FrameGeo geo = load_geo(descs, f, hints);
-    stage_hints(sm.hbuf, geo, 0, min(geo.seg_max, geo.n_seg));
+    FrameGeo geo = load_geo(descs, f, hints, tma_hints);
+    if (geo.tma_seg0 >= 0) stage_hints_tma(sm, &hint_map, geo, 0, min(geo.seg_max, geo.n_seg));
+    else stage_hints(sm.hbuf, geo, 0, min(geo.seg_max, geo.n_seg));
     cp_async_commit();
 
     while (f < n_frames) {
@@ -401,7 +445,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         const int f_next = next_own_frame<SPEC>(descs, f + (int)gridDim.x, n_frames, (int)gridDim.x);
         FrameGeo geo_next = geo;
         if (f_next < n_frames) {
-            geo_next = load_geo(descs, f_next, hints);
+            geo_next = load_geo(descs, f_next, hints, tma_hints);
 #if COMPOSE_BULK_OPS
             /* the next frame's dense hint map goes to L2 a whole frame ahead (bulk prefetch): its tile copies find it there */
             const u32 n_bytes = (8u * (u32)(geo_next.W * geo_next.H)) & ~15u;
@@ -418,6 +462,17 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             /* ---- stage: this tile's hints have landed ---------- */
             STAGE_MARK(7);                                      /* frame setup / loop glue */
             if (tile0) cp_async_wait_but_last(); else cp_async_wait_all();   /* (the payload's group may still be in flight) */
+            int shift = 0;                                      /* TMA tiles start on a 128-byte row: slots may sit one further */
+            if (geo.tma_seg0 >= 0) {
+                mbar_wait(&sm.hints_full, hpar);
+                hpar ^= 1u;
+                shift = (geo.tma_seg0 + s0 - geo.tpr - 1) & 1;
+                if (tile0) {
+                    /* the slots in front of the frame's first segment hold the neighbours "above the picture": unavailable */
+                    const int n_sent = 4 * (geo.tpr + 1 + shift);
+                    for (int c = tid; c < n_sent; c += NT) sm.hbuf[hint_swizzle((u32)c)] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
+                }
+            }
             __syncthreads();
             STAGE_MARK(0);                                      /* wait for the hint tile (and for the slowest warp of the tile before) */
 
@@ -428,7 +483,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const int nmb = active ? min(MPT, W - MPT * col) : 0;
             const int g0 = row * W + MPT * col;                 /* raster index of the segment's first MB */
             const bool first = col == 0, lastseg = col == geo.tpr - 1;
-            const int qo = tid + geo.tpr + 1, qa = tid + 1;     /* slots of the own segment and of the one above */
+            const int qo = tid + geo.tpr + 1 + shift, qa = tid + 1 + shift;     /* slots of the own segment and of the one above */
 
             uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
             uint2 abv[MPT + 2];                                 /* abv[j] = hint above-left of MB j */
@@ -516,7 +571,8 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             if (!last || f_next < n_frames) {
                 const FrameGeo &gn = last ? geo_next : geo;
                 const int sn = last ? 0 : s0 + n;
-                stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
+                if (gn.tma_seg0 >= 0) stage_hints_tma(sm, &hint_map, gn, sn, min(gn.seg_max, gn.n_seg - sn));
+                else stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
             }
             cp_async_commit();
             if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
@@ -886,8 +942,42 @@ pack_copy_kernel(const H264GpuFrameDesc *__restrict__ descs, const u32 *__restri
 
 /* ---------------------------------------------------------------- launch */
 
+/*
+ * The dense hint maps as a 2-D tensor for the TMA unit: rows of 128 bytes (16 hints, 32 x u32), boxes of TBOX_ROWS rows,
+ * 128-byte swizzle.  Only the whole rows of the n_hints the caller vouches for are covered.  Returns the hints covered
+ * (0: no tensor map - the kernel stages every tile with cp.async).
+ */
+static unsigned long long make_hint_map(CUtensorMap *map, const H264GpuMbHint *d_hints, size_t n_hints) {
+    memset(map, 0, sizeof *map);
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {                                       /* (the driver entry point is process-wide; a benign race at worst) */
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = (EncodeFn)fn;
+        else cudaGetLastError();
+        looked = true;
+    }
+    const cuuint64_t rows = (cuuint64_t)(n_hints / 16);
+    if (!encode || rows == 0 || ((uintptr_t)d_hints & 127u)) return 0;
+    const cuuint64_t dims[2] = {32, rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TBOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)d_hints, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        memset(map, 0, sizeof *map);
+        return 0;
+    }
+    return (unsigned long long)rows * 16ull;
+}
+
 cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
-                           const H264GpuMbHint *d_hints, const H264GpuDynDesc *d_dyn,
+                           const H264GpuMbHint *d_hints, size_t n_hints, const H264GpuDynDesc *d_dyn,
                            const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
@@ -901,9 +991,11 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
         ctas_per_sm = 1;
     const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
     int grid = n_frames < resident ? n_frames : resident;
+    CUtensorMap hint_map;
+    const unsigned long long tma_hints = COMPOSE_BULK_OPS ? make_hint_map(&hint_map, d_hints, n_hints) : (memset(&hint_map, 0, sizeof hint_map), 0ull);
     /* reference-mode frames, then the frames with SPEC flags (that launch returns at once when there are none) */
-    compose_frames_kernel<false><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
-    compose_frames_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes);
+    compose_frames_kernel<false><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes, hint_map, tma_hints);
+    compose_frames_kernel<true><<<grid, NT, smem, stream>>>(d_desc, n_frames, d_hints, d_dyn, d_dyn_tab, d_payload, d_out, d_sizes, hint_map, tma_hints);
     return cudaGetLastError();
 }
 

@@ -20,11 +20,11 @@
 #define COMPOSE_ITEM_SLOTS   1024    /* work-queue items per round */
 #endif
 #ifndef COMPOSE_HINT_SLOTS
-#define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 34)   /* 64-byte segment slots per staged hint tile: a full tile for frames
-                                                         up to 264 MBs wide, at least 2 segments per tile at the widest */
+#define COMPOSE_HINT_SLOTS   (COMPOSE_THREADS + 64)   /* 64-byte segment slots per staged hint tile (a whole number of 4 KB TMA boxes):
+                                                         a full tile for frames up to 496 MBs wide, at least 2 segments per tile at the widest */
 #endif
 #ifndef COMPOSE_PAYBUF16
-#define COMPOSE_PAYBUF16     1664    /* 16-byte chunks of a frame's payload staged in shared memory (26 KB: a 25x25-MB region at ~300 bits per MB) */
+#define COMPOSE_PAYBUF16     1536    /* 16-byte chunks of a frame's payload staged in shared memory (26 KB: a 25x25-MB region at ~300 bits per MB) */
 #endif
 #ifndef COMPOSE_BULK_OPS
 #define COMPOSE_BULK_OPS     1       /* sm_100 bulk operations: payload staged by one cp.async.bulk (TMA unit) on an mbarrier, next frame's hints
@@ -43,8 +43,9 @@
 
 namespace h264scroll {
 
+/* n_hints = hints the caller vouches for behind d_hints (0: unknown - no TMA tensor map, every tile by cp.async) */
 cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
-                           const H264GpuMbHint *d_hints, const H264GpuDynDesc *d_dyn,
+                           const H264GpuMbHint *d_hints, size_t n_hints, const H264GpuDynDesc *d_dyn,
                            const uint32_t *d_dyn_tab, const uint8_t *d_payload,
                            uint8_t *d_out, uint32_t *d_sizes, int sm_count, cudaStream_t stream);
 

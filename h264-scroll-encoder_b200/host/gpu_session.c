@@ -123,8 +123,8 @@ static int compose_chunk(const LegacyFrame *fr, int n, int mb_w, int mb_h,
     if (!rc) rc = h264gpu_raster_regions((const H264GpuRasterDesc *)(D + p_rd), n, (int)n_mbs,
                                          (const H264GpuRegion *)(D + p_reg), NULL,
                                          (H264GpuMbHint *)(D + d_hints), NULL);
-    if (!rc) rc = h264gpu_compose_batch((const H264GpuFrameDesc *)(D + p_desc), n,
-                                        (const H264GpuMbHint *)(D + d_hints), NULL, NULL, NULL,
+    if (!rc) rc = h264gpu_compose_batch_ex((const H264GpuFrameDesc *)(D + p_desc), n,
+                                        (const H264GpuMbHint *)(D + d_hints), hint_stride * (size_t)n, NULL, NULL, NULL,
                                         D + d_slots, (uint32_t *)(D + d_sizes), NULL);
     if (!rc) rc = h264gpu_pack_frames((const H264GpuFrameDesc *)(D + p_desc), (const uint32_t *)(D + d_sizes), n,
                                       D + d_slots, D + d_packed, (uint64_t *)(D + d_offs), NULL);
@@ -187,7 +187,7 @@ static int compose_one(const LegacyFrame *L, int mb_w, int mb_h, uint8_t *dst, s
     r[1].mv_y_qpel = (int16_t)L->mv_bot_qpel; r[1].ref_idx = (uint8_t)L->ref_bot;
     *h_size = 0;
     rc = h264gpu_raster_regions(rd, 1, (int)n_mbs, r, NULL, (H264GpuMbHint *)S.dev, NULL);
-    if (!rc) rc = h264gpu_compose_batch(desc, 1, (const H264GpuMbHint *)S.dev, NULL, NULL, NULL, S.pin + p_slot, (uint32_t *)(S.pin + p_size), NULL);
+    if (!rc) rc = h264gpu_compose_batch_ex(desc, 1, (const H264GpuMbHint *)S.dev, up(n_mbs, 2), NULL, NULL, NULL, S.pin + p_slot, (uint32_t *)(S.pin + p_size), NULL);
     if (!rc) rc = h264gpu_stream_sync(NULL);
     if (rc) return rc;
     const uint32_t sz = *h_size;

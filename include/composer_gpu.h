@@ -175,6 +175,20 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
                           void *stream);
 
 /*
+ * The same for a caller that can say how many hints lie behind d_hints (n_hints, e.g. the size it allocated): the dense
+ * maps are then also described to the TMA unit as a 2-D tensor (rows of 128 bytes, 128-byte swizzle), and frames that start
+ * on a row - hint_off a multiple of 16, mb_w a multiple of 8, d_hints 128-byte aligned - get their hint tiles by tensor
+ * loads instead of per-thread copies.  Results are identical; h264gpu_compose_batch is this call with n_hints = 0.
+ */
+int h264gpu_compose_batch_ex(const H264GpuFrameDesc *d_desc, int n_frames,
+                             const H264GpuMbHint *d_hints, size_t n_hints,
+                             const H264GpuDynDesc *d_dyn,
+                             const uint32_t *d_dyn_tab,
+                             const uint8_t *d_payload,
+                             uint8_t *d_out, uint32_t *d_sizes,
+                             void *stream);
+
+/*
  * Expand region lists into dense hint maps on the device
  * (replaces the per-MB region test of src/h264_writer.c:598-620).  The descriptors live in device memory, so nothing
  * about them can be refused here: region_count > H264GPU_MAX_REGIONS is invalid, the kernel then paints the first
