@@ -47,7 +47,7 @@ constexpr int NW = NT / 32;
 constexpr int CH = COMPOSE_WINDOW_WORDS; /* window: slice words staged per pass */
 constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
 constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
-constexpr int TBOX_ROWS = 32;            /* TMA box: 32 rows of 128 bytes (4 KB) of the dense map seen as a [rows][32 x u32] tensor */
+constexpr int TBOX_ROWS = 96;            /* TMA box: 96 rows of 128 bytes (12 KB) of the dense map seen as a [rows][32 x u32] tensor: three boxes per tile */
 constexpr int TBOX_BYTES = TBOX_ROWS * 128;
 static_assert((HBS * 64) % TBOX_BYTES == 0, "the hint tile buffer is a whole number of TMA boxes");
 constexpr u32 FULL = 0xFFFFFFFFu;
