@@ -389,6 +389,11 @@ def main_ours(args):
     raster_ms = L.h264gpu_event_elapsed_ms(ev0, ev1) / 5
     raster_bytes = 8 * total_mbs + b.regions.nbytes + b.rdesc.nbytes + (b.dyn_info.nbytes if has_dyn else 0)   # map written, lists and dyn-info read
 
+    if hasattr(L, "h264gpu_debug_trace"):                         # event-trace experiment build only
+        tr = (ctypes.c_uint64 * (32 * 1024))()
+        L.h264gpu_debug_trace(tr)
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.frombuffer(tr, np.uint64).tofile("gpurun_out/trace.bin")
     if hasattr(L, "h264gpu_debug_stage_cycles"):                  # timing-instrumented experiment build only
         cyc = (ctypes.c_uint64 * 16)()
         L.h264gpu_debug_stage_cycles(cyc)

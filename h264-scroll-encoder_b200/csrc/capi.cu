@@ -19,6 +19,9 @@
 #if defined(COMPOSE_TIMING) && COMPOSE_TIMING
 namespace h264scroll { cudaError_t read_stage_cycles(unsigned long long *h8); }
 #endif
+#if defined(COMPOSE_TRACE) && COMPOSE_TRACE
+namespace h264scroll { cudaError_t read_trace(unsigned long long *h); }
+#endif
 
 namespace {
 
@@ -656,6 +659,12 @@ int h264gpu_compose_regions_host(const H264GpuHostBatch *b, uint8_t *h_stream, s
     return rc;
 }
 
+#if defined(COMPOSE_TRACE) && COMPOSE_TRACE
+/* experiments only: the per-warp event trace of one CTA (32 warps x 1024 events) */
+int h264gpu_debug_trace(unsigned long long *h) {
+    return h264scroll::read_trace(h) == cudaSuccess ? H264GPU_OK : H264GPU_ERR_CUDA;
+}
+#endif
 #if defined(COMPOSE_TIMING) && COMPOSE_TIMING
 /* experiments only: per-stage clock64() sums of thread 0 of every CTA since the last call */
 int h264gpu_debug_stage_cycles(unsigned long long *h8) {

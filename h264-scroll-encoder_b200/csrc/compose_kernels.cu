@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <string.h>
+#define COMPOSE_TRACE_TU 1
 #include "mb_codec.cuh"
 #include "kernel_util.cuh"
 #include "emit_stage.cuh"
@@ -77,6 +78,7 @@ struct __align__(1024) ComposeSmem {
         struct {
             u32 gpre[EPASS];             /* emit: bytes inserted before a listed group */
             unsigned short elist[EPASS]; /* emit: pass-local indices of the listed groups */
+            unsigned short elist2[EPASS];/* emit: the listed groups that go out byte-wise */
         };
         uint4 paybuf[PAYBUF16];          /* the frame's pre-encoded payload, staged with cp.async at frame start and dead
                                             by the time the frame's emit stage runs (an emit in the middle of a frame
@@ -86,7 +88,7 @@ struct __align__(1024) ComposeSmem {
     u64 hints_full;                      /* mbarrier: the hint tile has landed (TMA tensor loads) */
     const u32 *pay_smem;                 /* payload word i of the frame = pay_smem[i] for i < pay_staged */
     u32 pay_staged;
-    u32 n_list;
+    u32 n_list, n_list2;
     u32 scan[2][NW + 1];                 /* double buffered: one barrier per block scan */
     uint2 scan2[NW + 1];
     u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state), double buffered */
@@ -97,6 +99,7 @@ struct __align__(1024) ComposeSmem {
     u32 n_pay_words;
     u32 cap;                             /* output slot capacity */
     uint8_t *fout;                       /* output slot */
+    TRACE_FIELDS
 };
 
 /* geometry of a frame as the tile loop needs it */
@@ -256,7 +259,7 @@ __device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wba
         Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
         /* a spliced macroblock whose payload words (and the read-ahead word) are all staged reads shared memory */
         const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
-        consume_item(it, sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
+        consume_item(it, (const u32 *)&sm.items[i], sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
     }
 }
 
@@ -273,6 +276,18 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
                                               int skip_spec_in = 0, int pred_spec_in = 0) {
     const int skip_spec = GEN ? skip_spec_in : 0, pred_spec = GEN ? pred_spec_in : 0;
     u32 kinds = 0;
+    /* spliced macroblocks: their payload ranges come from the offset table in global memory - all loads of the segment
+       are issued here, in front of the votes, so that they overlap instead of queueing one round trip behind the other */
+#pragma unroll
+    for (int k = 0; k < MPT; k++) {
+        code[k] = 0u; len[k] = 0u;
+        const u32 hy = own[1 + k].y;
+        if (k < nmb && (hy & 0xFF00u) != 0u) {
+            const u32 di = hy >> 16;
+            code[k] = __ldg(tab + di);
+            len[k] = __ldg(tab + di + 1);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < MPT; k++) {
         const uint2 h = own[1 + k], a = own[k], b = abv[k + 1], c = abv[k + 2];
@@ -290,17 +305,27 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
             uni = ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
         }
         u32 kd = MBK_NONE;
-        code[k] = 0u; len[k] = 0u;
         if (__all_sync(FULL, uni || dyn || !present)) {
             if (present && !dyn) kd = decide_mb_uniform(h.y, num_refs, skip_spec, code[k], len[k]);
-        } else if (present && !dyn) {
-            kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, code[k], len[k]);
+        } else {
+            /* somebody needs the predictor.  The code is a function of (own hint, A, B, C) alone: along a region's
+               horizontal edge all four repeat from macroblock to macroblock, and the answer of the macroblock before
+               is taken over (a whole row of such macroblocks costs the predictor once per segment, not eight times) */
+            bool same = false;
+            if (k > 0)
+                same = ((h.x ^ a.x) | (h.y ^ a.y) | (a.x ^ own[k - 1].x) | (a.y ^ own[k - 1].y) |
+                        (b.x ^ abv[k].x) | (b.y ^ abv[k].y) | (c.x ^ b.x) | (c.y ^ b.y)) == 0u;
+            if (k > 0 && __all_sync(FULL, uni || same || dyn || !present)) {
+                if (present && !dyn) {
+                    if (same) { kd = (kinds >> (4 * (k - 1))) & 0xFu; code[k] = code[k - 1]; len[k] = len[k - 1]; }
+                    else kd = decide_mb_uniform(h.y, num_refs, skip_spec, code[k], len[k]);
+                }
+            } else if (present && !dyn) {
+                kd = decide_mb(h.x, h.y, a.x, a.y, b.x, b.y, c.x, c.y, num_refs, pred_spec, skip_spec, code[k], len[k]);
+            }
         }
         if (present && dyn) {
-            const u32 di = h.y >> 16;
-            const u32 b0 = __ldg(tab + di);
-            len[k] = __ldg(tab + di + 1) - b0 + (skip_spec ? 0u : 1u);
-            code[k] = b0;
+            len[k] = len[k] - code[k] + (skip_spec ? 0u : 1u);
             kd = MBK_DYN;
         }
         kinds |= kd << (4 * k);
@@ -351,6 +376,10 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
         for (int i = tid; i < (CH + 8) / 4; i += NT) w4[i] = make_uint4(0u, 0u, 0u, 0u);
         if (tid == 0) {
             sm.n_items[0] = 0; sm.n_items[1] = 0; sm.n_list = 0;
+#if COMPOSE_TRACE
+            for (int i = 0; i < 32; i++) sm.tr_n[i] = 0;
+            sm.tr_on = 0;
+#endif
 #if COMPOSE_BULK_OPS
             mbar_init(&sm.pay_full, 1);
             mbar_init(&sm.hints_full, 1);
@@ -366,6 +395,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
     bool pay_pending = false;          /* this frame's payload copy has not been waited for yet */
 #endif
     u32 ipar = 0;                      /* which sm.n_items counter the current tile uses */
+#if COMPOSE_TRACE
+    int trace_frame = 0;
+#endif
 
 #if COMPOSE_TIMING
     long long stage_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stage_t = clock64();
@@ -431,8 +463,15 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 sm.tab = tab; sm.pay_words = pay_words; sm.n_pay_words = n_pay_words;
                 sm.pay_smem = pay_smem; sm.pay_staged = staged;
                 sm.cap = cap; sm.fout = out + out_off;
+#if COMPOSE_TRACE
+                sm.tr_on = (trace_frame >= 4 && trace_frame < 7) ? 1u : 0u;
+#endif
             }
         }
+#if COMPOSE_TRACE
+        trace_frame++;
+#endif
+        TRACE(1);
         const int kc = (W - 1) & 7;                            /* position of a row's last MB inside its segment */
 
         /* frame state every thread tracks identically (all of it follows from block-wide totals) */
@@ -473,7 +512,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     for (int c = tid; c < n_sent; c += NT) sm.hbuf[hint_swizzle((u32)c)] = make_uint4(0u, HINT_Y_UNAVAIL, 0u, HINT_Y_UNAVAIL);
                 }
             }
+            TRACE(10);
             __syncthreads();
+            TRACE(11);
             STAGE_MARK(0);                                      /* wait for the hint tile (and for the slowest warp of the tile before) */
 
             /* ---- load: own segment, the one above, the hints beside them ------------------------ */
@@ -563,18 +604,12 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
             /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
             u32 total;
+            TRACE(12);
             const u32 O = bitpos + group_excl_scan<NW, 0>(L, sm.scan[spar], tid >> 5, total);
             spar ^= 1u;
             const u32 total_items = sm.n_items[ipar];
+            TRACE(13);
             STAGE_MARK(2);                                      /* prefixes, bit counts, scan (incl. its barrier) */
-            /* ---- stage: everybody is past its loads from the hint tile: start the copy of the next one ---- */
-            if (!last || f_next < n_frames) {
-                const FrameGeo &gn = last ? geo_next : geo;
-                const int sn = last ? 0 : s0 + n;
-                if (gn.tma_seg0 >= 0) stage_hints_tma(sm, &hint_map, gn, sn, min(gn.seg_max, gn.n_seg - sn));
-                else stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
-            }
-            cp_async_commit();
             if (tid == 0) sm.n_items[ipar ^ 1u] = 0;               /* the next tile's counter; nobody adds to it before the next barrier */
             const u32 E = O + L;
             const u32 end = bitpos + total;
@@ -670,6 +705,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     }
                 }
 
+                TRACE(14);
                 STAGE_MARK(3);                                  /* stage next tile, header, concatenation path + merge */
                 /* ---- queue: items of this tile in rounds of LCAP, one lane per item ----------- */
                 for (u32 r0 = 0; r0 < total_items; r0 += (u32)LCAP) {
@@ -686,7 +722,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                                     prev = g0 + k;
                                     if (slot < (u32)LCAP) {
                                         uint2 h = make_uint2(0u, 0u);
-                                        if (kd == MBK_LONG) h = __ldg(geo.fh + g0 + k);   /* the staged tile is being replaced */
+                                        if (kd == MBK_LONG) h = staged_hint(hb, qo, k);    /* (the tile is replaced only behind the queue stage) */
                                         const Item it = make_item(kd, code[k], len[k], bit, pre, h.x, h.y);
                                         sm.items[slot] = make_uint4(it.x, it.y, it.z, it.w);
                                     }
@@ -698,21 +734,39 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                         if (owns_trailer && slot < (u32)LCAP)
                             sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
                     }
-                    cp_async_wait_but_last();                              /* the staged payload has landed (the next hint tile may still be on its way) */
-#if COMPOSE_BULK_OPS
+#if !COMPOSE_BULK_OPS
+                    cp_async_wait_all();                                   /* the staged payload has landed */
+#else
                     if (pay_pending) { mbar_wait(&sm.pay_full, pay_par); pay_par ^= 1u; pay_pending = false; }
 #endif
+                    TRACE(15);
                     __syncthreads();
+                    TRACE(16);
                     STAGE_MARK(6);                              /* queue: push + wait for the slowest writer */
                     consume_round(sm, min((u32)LCAP, total_items - r0), wbase, num_refs);
+                    TRACE(17);
                 }
 
                 STAGE_MARK(4);                                  /* queue */
                 const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */
+                /* ---- stage: everybody is past its loads from the hint tile (the last ones fetch the hints of the long codes
+                       in the push loop, in front of a barrier): start the copy of the next tile - of the next frame's first
+                       when this is the last.  (A tile written in several window passes pushes again: its last pass stages) */
+                if (fits) {
+                    if (!last || f_next < n_frames) {
+                        const FrameGeo &gn = last ? geo_next : geo;
+                        const int sn = last ? 0 : s0 + n;
+                        if (gn.tma_seg0 >= 0) stage_hints_tma(sm, &hint_map, gn, sn, min(gn.seg_max, gn.n_seg - sn));
+                        else stage_hints(sm.hbuf, gn, sn, min(gn.seg_max, gn.n_seg - sn));
+                    }
+                    cp_async_commit();
+                }
                 if (!(last || !fits)) break;                               /* keep filling the window with the next tile */
 
                 /* ---- emit: emulation prevention + store of frame words [wbase, e_hi) --------- */
+                TRACE(18);
                 __syncthreads();
+                TRACE(19);
                 const u32 e_hi = fits ? w_stop : wbase + CH;
                 const u32 chunk_byte0 = wbase << 2;
                 const int chunk_bytes = e_hi > wbase ? (int)((fits ? min(e_hi << 2, total_bytes) : (e_hi << 2)) - chunk_byte0) : 0;
@@ -722,7 +776,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 if (tid == 0) sm.pay_staged = 0;                               /* the emit stage reuses the payload buffer */
                 ins_total += emit_window<ComposeSmem, NT>(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
                 if (chunk_bytes > 0) zpar ^= 1u;
-                __syncthreads();                                               /* window fully consumed */
+                TRACE(20);
+                __syncthreads();
+                TRACE(21);                                                     /* window fully consumed */
                 {   /* clear the words this window used */
                     const u32 used = min((u32)CH, w_last - wbase + 1u);
 #if COMPOSE_BULK_OPS
@@ -754,6 +810,9 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #endif
 }
 
+#if COMPOSE_TRACE
+cudaError_t read_trace(unsigned long long *h) { return cudaMemcpyFromSymbol(h, g_trace, sizeof(unsigned long long) * TRACE_WARPS * TRACE_EVENTS); }
+#endif
 #if COMPOSE_TIMING
 cudaError_t read_stage_cycles(unsigned long long *h8) {
     cudaError_t e = cudaMemcpyFromSymbol(h8, g_stage_cycles, sizeof(unsigned long long) * 8);
@@ -989,6 +1048,9 @@ cudaError_t launch_compose(const H264GpuFrameDesc *d_desc, int n_frames,
     int ctas_per_sm = 0;                  /* resident CTAs per SM for this build (registers / shared memory) */
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, compose_frames_kernel<false>, NT, smem) != cudaSuccess || ctas_per_sm < 1)
         ctas_per_sm = 1;
+#ifdef COMPOSE_FORCE_CTAS_PER_SM              /* experiments: fewer CTAs per SM than fit */
+    ctas_per_sm = COMPOSE_FORCE_CTAS_PER_SM;
+#endif
     const int resident = sm_count * ctas_per_sm;      /* persistent grid: a multiple of the SM count */
     int grid = n_frames < resident ? n_frames : resident;
     CUtensorMap hint_map;

@@ -3,7 +3,7 @@
  * nal_write_unit, src/nal.c:24-84), shared by the compose kernel and the slice-rewrite kernel.
  *
  * The window holds slice bytes as MSB-first 32-bit words.  Smem must provide: u32 win[]; u32 gi[EPASS], gpre[EPASS];
- * unsigned short elist[EPASS]; u32 n_list; uint2 scan2[]; u32 zrun[2]; u32 cap; uint8_t *fout.
+ * unsigned short elist[EPASS], elist2[EPASS]; u32 n_list, n_list2; uint2 scan2[]; u32 zrun[2]; u32 cap; uint8_t *fout.
  * NTH = threads of the CTA (all of them call emit_window).
  */
 #ifndef H264SCROLL_EMIT_STAGE_CUH
@@ -84,6 +84,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
         const bool roomy = chunk_byte0 + 16u * (u32)q0 + 24u * (u32)min(EPASS, n_groups - q0) +
                            (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
         /* ---- classify ---- */
+        if (tid == 0) sm.n_list2 = 0;                        /* (read last in front of the previous pass's closing barrier) */
 #pragma unroll 1                                             /* (code size matters more than the loop overhead) */
         for (int r = 0; r < EG; r++) {
             const int gl = tid + NT * r, q = q0 + gl;
@@ -107,22 +108,31 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                 if (slow) sm.elist[base + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)gl;
             }
         }
+        TRACE(30);
         __syncthreads();
+        TRACE(31);
         const u32 nl = sm.n_list;
         /* ---- masks ---- */
         for (u32 i = (u32)tid; i < nl; i += NT) {
             const int gl = sm.elist[i], q = q0 + gl;
             const int vb = min(chunk_bytes - 16 * q, 16);
             const u32 ins = group_insert_mask(sm.win, q, ((const uint4 *)sm.win)[q], vb, chunk_byte0, zrun_in);
-            sm.gi[gl] = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
+            const u32 g = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
+            sm.gi[gl] = g;
+            /* most listed groups turn out clean (a lone zero byte): the few that do insert - or are partial, or sit next
+               to the slot's end - go into a second list, so that the byte-wise phase is as short as its real work */
+            if (!(roomy && g == GI_CLEAN)) sm.elist2[atomicAdd(&sm.n_list2, 1u)] = (unsigned short)gl;
         }
+        TRACE(32);
         __syncthreads();
+        TRACE(33);
         if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
         /* ---- offsets ---- */
         u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
         u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
         u32 tlo, thi;
         group_excl_scan_x2<NW, 0>(lo, hi, sm.scan2, tid >> 5, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
+        TRACE(34);
         const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
         if (lookback) {
             /* slice rewrite: where this chunk's bytes go depends on the insertions of the chunks before it (single pass
@@ -175,13 +185,15 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                 }
             }
         }
+        TRACE(35);
         __syncthreads();
+        TRACE(36);
         /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
-        for (u32 i = (u32)tid; i < 4u * nl; i += NT) {        /* four lanes per group, a word each: the phase is as long as its longest lane */
-            const int gl = sm.elist[i >> 2], q = q0 + gl;
+        const u32 nl2 = sm.n_list2;
+        for (u32 i = (u32)tid; i < 4u * nl2; i += NT) {       /* four lanes per group, a word each: the phase is as long as its longest lane */
+            const int gl = sm.elist2[i >> 2], q = q0 + gl;
             const u32 sub = i & 3u;
             const u32 gg = sm.gi[gl];
-            if (roomy && gg == GI_CLEAN) continue;           /* turned out clean: stored above */
             const u32 ins = gg >> 16;
             const int vbs = (int)((gg >> 8) & 0xFFu) - 4 * (int)sub;           /* valid bytes from this word on */
             if (vbs <= 0) continue;
@@ -198,6 +210,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                 }
             }
         }
+        TRACE(37);
         ins_total += t0 + t1 + t2 + t3;
         if (q0 + EPASS < n_groups) __syncthreads();          /* list, counts and offsets are reused by the next pass (the caller
                                                                  puts a barrier behind the last one) */

@@ -19,6 +19,29 @@ constexpr u32 FULL_MASK = 0xFFFFFFFFu;
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
+/* ---- experiments: per-warp event trace of one CTA (COMPOSE_TRACE=1) -------------------------
+   lane 0 of every warp of CTA TRACE_CTA appends (event id << 48 | clock64) to g_trace[warp][..]; TRACE(id) just before a
+   barrier is the warp's arrival, just behind it the departure: arrival - previous departure = the warp's work */
+#ifndef COMPOSE_TRACE
+#define COMPOSE_TRACE 0
+#endif
+#if COMPOSE_TRACE && defined(COMPOSE_TRACE_TU)    /* (the translation unit that owns the trace buffer) */
+constexpr int TRACE_EVENTS = 1024, TRACE_WARPS = 32, TRACE_CTA = 5;
+__device__ unsigned long long g_trace[TRACE_WARPS][TRACE_EVENTS];
+__device__ __forceinline__ void trace_event(int id, volatile unsigned int *tr_n, volatile unsigned int *tr_on) {
+    if (blockIdx.x == TRACE_CTA && (threadIdx.x & 31) == 0 && *tr_on) {
+        const int w = threadIdx.x >> 5;
+        const unsigned int n = tr_n[w];
+        if (n < (unsigned)TRACE_EVENTS) { g_trace[w][n] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); tr_n[w] = n + 1; }
+    }
+}
+#define TRACE_FIELDS unsigned int tr_n[32]; unsigned int tr_on;
+#define TRACE(id) trace_event(id, sm.tr_n, &sm.tr_on)
+#else
+#define TRACE_FIELDS
+#define TRACE(id) do { } while (0)
+#endif
+
 /* ---- cp.async (LDGSTS) ---------------------------------------------------------------------- */
 __device__ __forceinline__ void cp_async16(u32 dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");

@@ -406,76 +406,97 @@ HSD u32 pay_ld32(const u32 *pw, u32 n_words, u32 p) {
     return fshl(pay_word(pw, n_words, wi), pay_word(pw, n_words, wi + 1u), (int)(p & 31u));
 }
 
-/* copy `len` payload bits from payload bit `src` to slice bit `dst` (copy_bits, src/h264_writer.c:228-240):
-   whole window words are plain stores, the partial words at both ends are OR-ed in */
-HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 n_words, u32 src, u32 len) {
+/* word wi of a bit source as an MSB-first word; sel = 0x0123 for payload bytes (a byte stream: big-endian words),
+   0x3210 for words that are MSB-first already; indices outside [0, n_words) read as zero */
+HSD u32 src_raw(const u32 *p, u32 sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(*p, 0u, sel);                         /* (generic load: the source may sit in shared memory) */
+#else
+    return sel == 0x0123u ? bswap32(*p) : *p;
+#endif
+}
+HSD u32 src_word(const u32 *pw, u32 n_words, int wi, u32 sel) {
+    return (u32)wi < n_words ? src_raw(pw + wi, sel) : 0u;
+}
+
+/*
+ * copy `len` bits from bit `src` (>= -1: bit -1 reads as zero) of the MSB-first source pw[] to slice bit `dst`
+ * (copy_bits, src/h264_writer.c:228-240), word by word of the DESTINATION: window word j takes
+ * fshl(source word, next source word, shift) - one load, one funnel shift, one store per word, the same for every word;
+ * the first and the last word are masked and OR-ed in (their other bits belong to the neighbours), first_or is added
+ * to the first word.
+ */
+HSD void splice_bits(u32 *win, u32 wbase, u32 wcap, u32 dst, const u32 *pw, u32 n_words, int src, u32 len, u32 first_or, u32 sel) {
+    if (!len) return;
     const u32 s = dst & 31u;
-    if (s && len) {
-        const u32 hb = len < 32u - s ? len : 32u - s;
-        const u32 v = (pay_ld32(pw, n_words, src) >> (32u - hb)) << (32u - s - hb);
-        const u32 j = (dst >> 5) - wbase;
-        if (j < wcap && v) WIN_OR(&win[j], v);
-        dst += hb; src += hb; len -= hb;
-    }
-    u32 j = (dst >> 5) - wbase;
-    const u32 nw = len >> 5, tb = len & 31u;
-    if (nw) {
-        u32 wi = src >> 5;
-        const u32 sh = src & 31u;
-        if (j < wcap && j + nw <= wcap && wi + nw < n_words) {
-            /* the whole run lies inside the window and the payload: no per-word checks */
-            const u32 *p = pw + wi;
-            u32 *d = win + j;
-            u32 a = pay_raw(p);
-            u32 i = 0;
-            for (; i + 4u <= nw; i += 4u) {                  /* four independent loads in flight */
-                const u32 b0 = pay_raw(p + i + 1u), b1 = pay_raw(p + i + 2u), b2 = pay_raw(p + i + 3u), b3 = pay_raw(p + i + 4u);
-                d[i] = fshl(a, b0, (int)sh);
-                d[i + 1u] = fshl(b0, b1, (int)sh);
-                d[i + 2u] = fshl(b1, b2, (int)sh);
-                d[i + 3u] = fshl(b2, b3, (int)sh);
-                a = b3;
-            }
-            for (; i < nw; i++) {
-                const u32 b = pay_raw(p + i + 1u);
-                d[i] = fshl(a, b, (int)sh);
-                a = b;
-            }
-        } else {
-            u32 a = pay_word(pw, n_words, wi);
-            for (u32 i = 0; i < nw; i++) {
-                const u32 b = pay_word(pw, n_words, ++wi);
-                if (j + i < wcap) win[j + i] = fshl(a, b, (int)sh);
-                a = b;
-            }
+    const u32 nd = (s + len + 31u) >> 5;                     /* window words touched */
+    const u32 j = (dst >> 5) - wbase;
+    const int d0 = src - (int)s;                             /* source bit under bit 0 of the first window word (>= -32) */
+    const int wi = d0 >> 5;                                  /* (arithmetic shift: floor) */
+    const int sh = d0 & 31;
+    const u32 e = (s + len) & 31u;
+    const u32 mf = 0xFFFFFFFFu >> s, ml = e ? ~(0xFFFFFFFFu >> e) : 0xFFFFFFFFu;
+    if (j < wcap && j + nd <= wcap && (u32)(wi + (int)nd) < n_words) {
+        /* everything lies inside the window and the source: no per-word checks */
+        const u32 *p = pw + wi;
+        u32 *d = win + j;
+        u32 a = wi >= 0 ? src_raw(p, sel) : 0u;
+        u32 b = src_raw(p + 1, sel);
+        u32 v = (fshl(a, b, sh) & mf) | first_or;
+        if (nd == 1u) { WIN_OR(d, v & (ml | first_or)); return; }
+        WIN_OR(d, v);
+        a = b;
+        u32 i = 1;
+        for (; i + 4u < nd; i += 4u) {                       /* four independent loads in flight */
+            const u32 b0 = src_raw(p + i + 1u, sel), b1 = src_raw(p + i + 2u, sel), b2 = src_raw(p + i + 3u, sel), b3 = src_raw(p + i + 4u, sel);
+            d[i] = fshl(a, b0, sh);
+            d[i + 1u] = fshl(b0, b1, sh);
+            d[i + 2u] = fshl(b1, b2, sh);
+            d[i + 3u] = fshl(b2, b3, sh);
+            a = b3;
         }
-    }
-    if (tb) {
-        const u32 v = (pay_ld32(pw, n_words, src + 32u * nw) >> (32u - tb)) << (32u - tb);
-        if (j + nw < wcap && v) WIN_OR(&win[j + nw], v);
+        for (; i + 1u < nd; i++) {
+            b = src_raw(p + i + 1u, sel);
+            d[i] = fshl(a, b, sh);
+            a = b;
+        }
+        v = fshl(a, src_raw(p + nd, sel), sh) & ml;
+        if (v) WIN_OR(d + (nd - 1u), v);
+    } else {
+        u32 a = src_word(pw, n_words, wi, sel);
+        for (u32 i = 0; i < nd; i++) {
+            const u32 b = src_word(pw, n_words, wi + 1 + (int)i, sel);
+            u32 v = fshl(a, b, sh);
+            if (i == 0u) v = (v & mf) | first_or;
+            if (i == nd - 1u) v &= ml | (i == 0u ? first_or : 0u);
+            if (j + i < wcap && v) WIN_OR(&win[j + i], v);
+            a = b;
+        }
     }
 }
 
-/* one queue item -> window */
-HSD void consume_item(const Item &it, u32 *win, u32 wbase, u32 wcap, int num_refs, const u32 *pw, u32 n_words) {
+/* one queue item -> window; self = the item's four words in memory (+ two readable words behind them) */
+HSD void consume_item(const Item &it, const u32 *self, u32 *win, u32 wbase, u32 wcap, int num_refs, const u32 *pw, u32 n_words) {
     u32 bit = it.x & IT_BIT_MASK;
     const u32 type = it.x >> 30;
     u32 pre = type == IT_LONG ? (it.y & 0xFFFFFFu) : it.y;
-    u32 src = it.z, n = it.w;
-    const bool fused = type == IT_DYN && pre == 1u && src != 0u;
-    const u32 bit0 = bit;
-    if (fused) { src -= 1u; n += 1u; pre = 0u; }              /* mb_skip_run = 0, a single '1' in front: splice from one bit early, set that bit afterwards */
+    u32 first_or = 0u;
+    int src = (int)it.z;
+    u32 n = it.w;
+    if (type == IT_DYN && pre == 1u) {
+        /* mb_skip_run = 0, a single '1' in front: splice from one bit early, that bit set in the first word */
+        first_or = 0x80000000u >> (bit & 31u);
+        src -= 1; n += 1u; pre = 0u;
+    }
     if (pre) {
         const u32 pn = 2u * flo32(pre) + 1u;                 /* ue(run): run + 1 in 2m+1 bits */
         win_or64(win, wbase, wcap, bit, (u64)pre, pn);
         bit += pn;
     }
-    if (type == IT_BITS) {
-        if (n) win_or64(win, wbase, wcap, bit, (u64)src, n);
-    } else if (type == IT_DYN) {
-        splice_bits(win, wbase, wcap, bit, pw, n_words, src, n);
-        const u32 j = (bit0 >> 5) - wbase;
-        if (fused && j < wcap) WIN_OR(&win[j], 0x80000000u >> (bit0 & 31u));
+    if (type != IT_LONG) {
+        /* a short code is a one-word source: the item's own z word, its bits right-aligned */
+        const bool dyn = type == IT_DYN;
+        splice_bits(win, wbase, wcap, bit, dyn ? pw : self + 2, dyn ? n_words : 3u, dyn ? src : 32 - (int)n, n, first_or, dyn ? 0x0123u : 0x3210u);
     } else {
         MbEntry e;
         int bl = encode_p16x16_body((int)(it.y >> 24), (int)it.z, (int)it.w, num_refs, e);

@@ -32,7 +32,8 @@ struct __align__(16) RewriteSmem {
     u32 gi[EPASS];                       /* emit: insert mask << 16 | valid bytes << 8 | insert count of each group */
     u32 gpre[EPASS];                     /* emit: bytes inserted before a listed group */
     unsigned short elist[EPASS];         /* emit: pass-local indices of the listed groups */
-    u32 n_list;
+    unsigned short elist2[EPASS];        /* emit: the listed groups that go out byte-wise */
+    u32 n_list, n_list2;
     uint2 scan2[NW + 1];
     u32 zrun[2];                         /* zero bytes closing the bytes emitted so far (rbsp_to_ebsp state) */
     u32 cap;                             /* output slot capacity */

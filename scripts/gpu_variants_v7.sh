@@ -15,6 +15,7 @@ for tag in "$@"; do
   tail -3 gpurun_out/parity_$tag.log | cut -c1-300
   if [ $rc -eq 124 ]; then echo "$tag: parity HUNG - stopping"; break; fi
   if [ $rc -ne 0 ]; then echo "$tag: parity FAILED rc=$rc"; fi
+  cp variants/$tag.so h264-scroll-encoder_b200/libh264scroll_b200.so   # (the tests rebuild the library when the variant was built with other flags)
   timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_$tag.log 2> gpurun_out/bench_$tag.err
   python - <<P
 import json

@@ -266,7 +266,10 @@ extern "C" uint32_t emu_compose_frame(const H264GpuFrameDesc *desc, const H264Gp
                 } else bit += T.Ls;
                 if (T.trailer) { Item it; it.x = bit | (IT_BITS << 30); it.y = 0; it.z = tr_code; it.w = tr_len; items.push_back(it); }
             }
-            for (auto &it : items) consume_item(it, win.data(), wbase, CH, num_refs, pay_words, n_pay_words);
+            for (auto &it : items) {
+                const u32 self[6] = {it.x, it.y, it.z, it.w, 0u, 0u};      /* the item as it lies in the queue */
+                consume_item(it, self, win.data(), wbase, CH, num_refs, pay_words, n_pay_words);
+            }
 
             const bool fits = w_last - wbase < CH;
             if (!(last || !fits)) break;
