@@ -259,7 +259,8 @@ __device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wba
         Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
         /* a spliced macroblock whose payload words (and the read-ahead word) are all staged reads shared memory */
         const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
-        consume_item(it, (const u32 *)&sm.items[i], sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, n_words);
+        /* (every staged word can be read: past the payload's end they are zero) */
+        consume_item(it, (const u32 *)&sm.items[i], sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, in_smem ? staged : n_words);
     }
 }
 
@@ -454,6 +455,13 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 for (u32 c = (u32)tid; c < n16; c += NT) cp_async16(dst + 16u * c, (const void *)(a0 + 16u * (uintptr_t)c));
 #endif
                 staged = 4u * n16 > w_skip ? 4u * n16 - w_skip : 0u;
+                if (n16 + 2u <= (u32)PAYBUF16) {
+                    /* the words behind the last whole chunk (up to three) and zero words to read ahead into go in by hand:
+                       the macroblocks at the payload's end are spliced from shared memory like all the others */
+                    const u32 wi = 4u * n16 + (u32)tid;
+                    if (tid < 8) ((u32 *)sm.paybuf)[wi] = wi < w_skip + n_pay_words ? __ldg((const u32 *)a0 + wi) : 0u;
+                    staged = 4u * n16 + 8u - w_skip;
+                }
                 pay_smem = (const u32 *)sm.paybuf + w_skip;
                 for (u32 o = 16u * n16 + 128u * (u32)tid; o < 4u * (w_skip + n_pay_words); o += 128u * NT) prefetch_l2((const uint8_t *)a0 + o);
             }
