@@ -15,6 +15,13 @@
 namespace h264scroll {
 
 constexpr int EMIT_EG = 4;                /* 16-byte groups per thread per pass */
+#ifndef EMIT_CLASSIFY_UNROLL
+#define EMIT_CLASSIFY_UNROLL 2
+#endif
+#ifndef EMIT_STORE_UNROLL
+#define EMIT_STORE_UNROLL 2
+#endif
+constexpr int EMIT_CU = EMIT_CLASSIFY_UNROLL, EMIT_SU = EMIT_STORE_UNROLL;   /* (by two: fully unrolled loops cost more in code size than they save, 0.871 vs 0.862 ms) */
 
 /* out of line: the backward scan is rare */
 static __device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in) { return zeros_before(win, b, zrun_in); }
@@ -85,7 +92,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                            (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
         /* ---- classify ---- */
         if (tid == 0) sm.n_list2 = 0;                        /* (read last in front of the previous pass's closing barrier) */
-#pragma unroll 1                                             /* (code size matters more than the loop overhead) */
+#pragma unroll EMIT_CU                         /* (code size matters more than the loop overhead) */
         for (int r = 0; r < EG; r++) {
             const int gl = tid + NT * r, q = q0 + gl;
             const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
@@ -143,7 +150,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
         }
         /* ---- store: clean groups ---- */
         u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
-#pragma unroll 1
+#pragma unroll EMIT_SU
         for (int r = 0; r < EG; r++) {
             const int gl = tid + NT * r, q = q0 + gl;
             const u32 g = sm.gi[gl];
