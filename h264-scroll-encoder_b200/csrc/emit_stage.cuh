@@ -26,6 +26,22 @@ constexpr int EMIT_CU = EMIT_CLASSIFY_UNROLL, EMIT_SU = EMIT_STORE_UNROLL;   /* 
 /* out of line: the backward scan is rare */
 static __device__ __noinline__ u32 zeros_before_win(const u32 *win, u32 b, u32 zrun_in) { return zeros_before(win, b, zrun_in); }
 
+/* the same in front of group q (byte 16 q), a whole group per step: inside a run of zero bytes - an all-zero macroblock
+   is two or three groups long - this is the longest lane of the masks phase, and its steps are dependent loads */
+static __device__ __noinline__ u32 zeros_before_group(const u32 *win, int q, u32 zrun_in) {
+    u32 r = 0;
+    for (int i = q - 1; i >= 0; i--) {
+        const uint4 w = ((const uint4 *)win)[i];
+        if (w.x | w.y | w.z | w.w) {
+            const u32 v = w.w ? w.w : w.z ? w.z : w.y ? w.y : w.x;          /* the last word that is not zero */
+            r += w.w ? 0u : w.z ? 4u : w.y ? 8u : 12u;
+            return r + ((v & 0xFFu) ? 0u : (v & 0xFF00u) ? 1u : (v & 0xFF0000u) ? 2u : 3u);
+        }
+        r += 16u;
+    }
+    return r + zrun_in;
+}
+
 /* exact insert mask of group q of the window (src/nal.c:24-50 in closed form) */
 __device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w, int vb, u32 chunk_byte0, u32 zrun_in) {
     const u32 valid = (1u << vb) - 1u;
@@ -35,7 +51,7 @@ __device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w,
     const bool need = ((w.x >> 26) == 0u) && (keep & 1u);                /* a first byte <= 3 may close a zero run of the bytes before */
     if (!(need || (z & (z << 1)))) return 0u;
     u32 rin = 0;
-    if (need && (q == 0 || (win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_win(win, 16u * (u32)q, zrun_in);
+    if (need && (q == 0 || (win[4 * q - 1] & 0xFFu) == 0u)) rin = zeros_before_group(win, q, zrun_in);
     const u32 m3 = zero_nib(w.x & 0xFCFCFCFCu) | (zero_nib(w.y & 0xFCFCFCFCu) << 4) |
                    (zero_nib(w.z & 0xFCFCFCFCu) << 8) | (zero_nib(w.w & 0xFCFCFCFCu) << 12);
     return epb_group_mask(z, m3 & keep, vb, rin);
