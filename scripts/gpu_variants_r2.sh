@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU box: smoke + parity subset + kernel-only bench for prebuilt library variants (variants/<tag>.so).
-# Usage: gpu_variants_v7.sh tag1 tag2 ...   A variant that hangs (timeout) ends the whole run.
+# Usage: gpu_variants_r2.sh tag1 tag2 ...   A variant that hangs (timeout) ends the whole run.
 mkdir -p gpurun_out
 cp h264-scroll-encoder_b200/libh264scroll_b200.so /tmp/orig.so
 for tag in "$@"; do
