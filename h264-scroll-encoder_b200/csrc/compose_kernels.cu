@@ -56,15 +56,6 @@ constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
 constexpr int EPASS = EMIT_EG * NT;      /* emit: groups per pass */
 static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
 
-#ifndef COMPOSE_EMIT_WARPS
-#define COMPOSE_EMIT_WARPS 1             /* 1: the emit stage warp by warp (two barriers per window), 0: CTA-wide lists (five) */
-#endif
-#if COMPOSE_EMIT_WARPS
-#define EMIT_WINDOW(sm, b0, nb, ins, zp) (emit_window_fits<ComposeSmem, NT>(sm, b0, nb, ins) ? emit_window_warps<ComposeSmem, NT>(sm, b0, nb, ins, zp) \
-                                                                                       : emit_window<ComposeSmem, NT>(sm, b0, nb, ins, zp))
-#else
-#define EMIT_WINDOW(sm, b0, nb, ins, zp) emit_window<ComposeSmem, NT>(sm, b0, nb, ins, zp)
-#endif
 #ifndef COMPOSE_TIMING
 #define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
 #endif
@@ -646,7 +637,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     if (pay_pending) { mbar_wait(&sm.pay_full, pay_par); pay_par ^= 1u; pay_pending = false; }
 #endif
                     if (tid == 0) sm.pay_staged = 0;                       /* the emit stage reuses the payload buffer */
-                    ins_total += emit_window<ComposeSmem, NT>(sm, wbase << 2, (int)(src << 2), ins_total, zpar);   /* (rare: the careful way) */
+                    ins_total += emit_window<ComposeSmem, NT>(sm, wbase << 2, (int)(src << 2), ins_total, zpar);
                     zpar ^= 1u;
                     __syncthreads();                                       /* window consumed */
                     if (tid < 4) { const u32 c = sm.win[src + tid]; sm.win[src + tid] = 0u; sm.win[tid] = c; }
@@ -791,7 +782,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 if (pay_pending) { mbar_wait(&sm.pay_full, pay_par); pay_par ^= 1u; pay_pending = false; }
 #endif
                 if (tid == 0) sm.pay_staged = 0;                               /* the emit stage reuses the payload buffer */
-                ins_total += EMIT_WINDOW(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
+                ins_total += emit_window<ComposeSmem, NT>(sm, chunk_byte0, chunk_bytes, ins_total, zpar);
                 if (chunk_bytes > 0) zpar ^= 1u;
                 TRACE(20);
                 __syncthreads();
