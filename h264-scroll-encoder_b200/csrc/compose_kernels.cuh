@@ -30,14 +30,16 @@
 #define COMPOSE_BULK_OPS     1       /* sm_100 bulk operations: payload staged by one cp.async.bulk (TMA unit) on an mbarrier, next frame's hints
                                         sent to L2 by cp.async.bulk.prefetch, window cleared by st.bulk; 0: cp.async / store loops */
 #endif
+/* slice rewrite: 256-thread CTAs on 16 KB chunks, five per SM (measured: 512 x 2 on 32 KB 0.192 ms, 256 x 4 0.171, 256 x 5
+   0.157, 128 x 8..10 on 8 KB 0.160-0.164: the chunk's load -> build -> look-back -> store chain wants many CTAs in flight) */
 #ifndef REWRITE_THREADS
-#define REWRITE_THREADS      512
+#define REWRITE_THREADS      256
 #endif
 #ifndef REWRITE_MIN_CTAS
-#define REWRITE_MIN_CTAS     2
+#define REWRITE_MIN_CTAS     5
 #endif
 #ifndef REWRITE_WINDOW_WORDS
-#define REWRITE_WINDOW_WORDS 8192    /* string words per rewrite chunk (32 KB) */
+#define REWRITE_WINDOW_WORDS 4096    /* string words per rewrite chunk (16 KB = 4 groups of 16 bytes per thread) */
 #endif
 #define COMPOSE_MAX_MB_W  H264GPU_MAX_MB_W
 

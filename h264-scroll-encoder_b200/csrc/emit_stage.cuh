@@ -241,5 +241,169 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
     return ins_total - ins_in;
 }
 
+/*
+ * The same stage, warp by warp: warp w owns groups [128 w, 128 w + 128) of the window (lane l those with index = l mod 32,
+ * conflict-free 128-bit loads).  Flags and counts travel by ballot and shuffle instead of through shared memory, the rare
+ * groups are listed per warp (positions from the ballots, no atomics) and worked through by the warp that owns them, and
+ * the CTA meets ONCE, for the warps' insert totals - two barriers per window (with the caller's) instead of five.
+ * One pass: the window must not hold more than 4 * NTH groups; a window that could touch the slot's end goes the careful way
+ * (emit_window) - emit_window_fits tells (ins_bound = what may have been inserted before the window), the caller picks.
+ * Used by the slice-rewrite kernel (0.197 -> see DESIGN.md 3.4); in the compose kernel it costs more in registers around
+ * the call than it saves (profiles/r2_kernel_experiments.txt, w1-w3).
+ */
+template <class Smem, int NTH>
+__device__ __forceinline__ bool emit_window_fits(const Smem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_bound) {
+    const int n_groups = (chunk_bytes + 15) >> 4;
+    return n_groups <= EMIT_EG * NTH && chunk_byte0 + 24u * (u32)n_groups + ins_bound + 4u <= sm.cap;
+}
+#ifndef EMIT_WARPS_INLINE
+#define EMIT_WARPS_INLINE __noinline__
+#endif
+template <class Smem, int NTH>
+__device__ EMIT_WARPS_INLINE u32 emit_window_warps(Smem &sm, u32 chunk_byte0, int chunk_bytes, u32 ins_total, u32 zpar,
+                                                   volatile u32 *lookback = nullptr, int lookback_c = 0) {
+    constexpr int NW = NTH / 32, EG = EMIT_EG;
+    constexpr u32 FULL = 0xFFFFFFFFu;
+    static_assert(EG == 4, "four rounds of 32 groups per warp");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    const u32 zrun_in = sm.zrun[zpar];
+    uint8_t *fout = sm.fout;
+    u32 *fout32 = (u32 *)fout;
+    const int g0 = 128 * warp;                                   /* the warp's first group */
+    unsigned short *wlist = sm.elist + g0, *wlist2 = sm.elist2 + g0;
+
+    /* (the loops over the four rounds stay rolled, their results in shared memory: what this function keeps in registers
+       the kernel around it has to give up across the call) */
+    /* ---- classify: which groups need a look (a zero byte inside, a first byte <= 3 behind one, the partial last group) ---- */
+    int n_slow = 0;
+#pragma unroll 1
+    for (int r = 0; r < EG; r++) {
+        const int q = g0 + 32 * r + lane;
+        const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
+        bool slow = false;
+        if (vb > 0) {
+            const uint4 w = ((const uint4 *)sm.win)[q];
+            const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+            slow = (hz & 0x80808080u) != 0u || vb < 16;
+            if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
+            /* the holder of the window's last byte hands the zero run to the next window */
+            if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
+        }
+        sm.gi[q] = (u32)vb << 8;
+        const u32 m = __ballot_sync(FULL, slow);
+        if (slow) wlist[n_slow + __popc(m & lt)] = (unsigned short)(32 * r + lane);
+        n_slow += __popc(m);
+    }
+    __syncwarp();
+    /* ---- masks: one lane per listed group of the warp ---- */
+    for (int i = lane; i < n_slow; i += 32) {
+        const int q = g0 + wlist[i];
+        const int vb = min(chunk_bytes - 16 * q, 16);
+        const u32 ins = group_insert_mask(sm.win, q, ((const uint4 *)sm.win)[q], vb, chunk_byte0, zrun_in);
+        sm.gi[q] = (ins << 16) | ((u32)vb << 8) | (u32)__popc(ins);
+    }
+    __syncwarp();
+    /* ---- counts: per lane four groups, packed 16-bit fields; scan over the lanes; the warp's total to the CTA ---- */
+    u32 il = (sm.gi[g0 + lane] & 0xFFu) | ((sm.gi[g0 + 32 + lane] & 0xFFu) << 16);
+    u32 ih = (sm.gi[g0 + 64 + lane] & 0xFFu) | ((sm.gi[g0 + 96 + lane] & 0xFFu) << 16);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 a = __shfl_up_sync(FULL, il, d), b = __shfl_up_sync(FULL, ih, d);
+        if (lane >= d) { il += a; ih += b; }
+    }
+    const u32 tl = __shfl_sync(FULL, il, 31), th = __shfl_sync(FULL, ih, 31);      /* the rounds' totals */
+    if (lane == 0) sm.scan2[warp].x = (tl & 0xFFFFu) + (tl >> 16) + (th & 0xFFFFu) + (th >> 16);
+    __syncthreads();
+    u32 v = lane < NW ? sm.scan2[lane].x : 0u;
+    u32 round_base = lane < warp ? v : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { v += __shfl_xor_sync(FULL, v, d); round_base += __shfl_xor_sync(FULL, round_base, d); }
+    const u32 total = v;
+    if (lookback) {
+        /* slice rewrite: the insertions of the chunks before this one - one thread looks back, everybody picks the result up */
+        if (tid == 0) sm.scan2[NW].x = chunk_lookback(lookback, lookback_c, total);
+        __syncthreads();
+        ins_total = sm.scan2[NW].x;
+    }
+    round_base += ins_total;                                     /* bytes inserted before the round's first group */
+    /* ---- store ---- */
+    u32 n_ins = 0;
+#pragma unroll 1
+    for (int r = 0; r < EG; r++) {
+        const int q = g0 + 32 * r + lane;
+        const u32 g = sm.gi[q];
+        const u32 incl = ((r & 2) ? ih : il) >> (16 * (r & 1)) & 0xFFFFu;
+        const u32 before = round_base + incl - (g & 0xFFu);
+        round_base += ((r & 2) ? th : tl) >> (16 * (r & 1)) & 0xFFFFu;
+        const bool bytewise = (g >> 8) != 0u && g != GI_CLEAN;
+        const u32 bm = __ballot_sync(FULL, bytewise);
+        if (bytewise) {
+            sm.gpre[q] = before;
+            wlist2[n_ins + (u32)__popc(bm & lt)] = (unsigned short)(32 * r + lane);
+        }
+        n_ins += (u32)__popc(bm);
+        if (g != GI_CLEAN) continue;
+        const u32 D = chunk_byte0 + 16u * (u32)q + before;         /* output byte of the group's first byte */
+        const uint4 w = ((const uint4 *)sm.win)[q];
+        const u32 s = (4u - (D & 3u)) & 3u;                      /* source bytes before the first aligned word */
+        u32 *dst = fout32 + ((D + s) >> 2);
+        if (s == 0u) {
+            const uint4 o = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
+                                       __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
+            if ((D & 15u) == 0u) *(uint4 *)dst = o;
+            else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
+        } else {
+            /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too
+               (the warp's first and last group do not look at the other warps' groups: bytes) */
+            const int ql = 32 * r + lane;
+            const bool prev_clean = ql > 0 && sm.gi[q - 1] == GI_CLEAN;
+            const bool next_clean = ql < 127 && sm.gi[q + 1] == GI_CLEAN;
+            const u32 wn = sm.win[4 * q + 4];
+            const u32 sel = realign_selector(s);
+            dst[0] = __byte_perm(w.x, w.y, sel);
+            dst[1] = __byte_perm(w.y, w.z, sel);
+            dst[2] = __byte_perm(w.z, w.w, sel);
+            const u32 o3 = __byte_perm(w.w, wn, sel);
+            if (next_clean) dst[3] = o3;
+            else {                                               /* (1..3 bytes, no loop) */
+                uint8_t *t = fout + D + s + 12u;
+                t[0] = (uint8_t)o3;
+                if (s < 3u) t[1] = (uint8_t)(o3 >> 8);
+                if (s < 2u) t[2] = (uint8_t)(o3 >> 16);
+            }
+            if (!prev_clean) {
+                uint8_t *h = fout + D;
+                h[0] = (uint8_t)(w.x >> 24);
+                if (s > 1u) h[1] = (uint8_t)(w.x >> 16);
+                if (s > 2u) h[2] = (uint8_t)(w.x >> 8);
+            }
+        }
+    }
+    __syncwarp();
+    /* ---- store: the groups that insert or are partial, four lanes each, a word per lane ---- */
+    for (u32 i = (u32)lane; i < 4u * n_ins; i += 32u) {
+        const int q = g0 + wlist2[i >> 2];
+        const u32 sub = i & 3u;
+        const u32 gg = sm.gi[q];
+        const u32 ins = gg >> 16;
+        const int vbs = (int)((gg >> 8) & 0xFFu) - 4 * (int)sub;               /* valid bytes from this word on */
+        if (vbs <= 0) continue;
+        const u32 wv = sm.win[4 * q + (int)sub];
+        u32 pos = chunk_byte0 + 16u * (u32)q + sm.gpre[q] + 4u * sub + (u32)__popc(ins & ((1u << (4u * sub)) - 1u));
+        u32 is = ins >> (4u * sub);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < vbs) {
+                if (is & 1u) fout[pos++] = 3;
+                fout[pos++] = (uint8_t)(wv >> (24 - 8 * k));
+                is >>= 1;
+            }
+        }
+    }
+    return lookback ? ins_total + total : total;
+}
+
 }  /* namespace h264scroll */
 #endif

@@ -186,7 +186,10 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
     __syncthreads();
     volatile u32 *st = state + 1 + (size_t)sl * max_chunks;
     /* (with a look-back the emit stage returns the insertions up to and including this chunk) */
-    const u32 ins_incl = emit_window<RewriteSmem, NT>(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
+    /* (the insertions before this chunk are not known yet: at most one per two bytes) */
+    const u32 ins_incl = emit_window_fits<RewriteSmem, NT>(sm, (u32)byte0, chunk_bytes, (u32)(byte0 / 2u + 1u))
+                             ? emit_window_warps<RewriteSmem, NT>(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c)
+                             : emit_window<RewriteSmem, NT>(sm, (u32)byte0, chunk_bytes, 0u, 0u, st, c);
     if (tid == 0 && byte0 + (u64)chunk_bytes >= total_bytes) sizes[sl] = (u32)total_bytes + ins_incl;   /* the slice's last chunk */
 }
 
