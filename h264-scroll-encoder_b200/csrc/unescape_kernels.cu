@@ -41,6 +41,7 @@ struct __align__(16) UnescapeSmem {
     u32 gpre[UT * UG];                   /* bytes removed before a listed group */
     unsigned short list[UT * UG];        /* groups that go byte by byte */
     u32 n_list;
+    u32 n_cand;                          /* groups that may hold a removal (listed in front of the masks phase) */
     uint2 scan[UW + 1];
     u32 ticket;
     u32 base;
@@ -102,7 +103,7 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UnescapeSmem &sm = *reinterpret_cast<UnescapeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_list = 0; }   /* chunks in launch order: everything below a ticket is running or done */
+    if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_list = 0; sm.n_cand = 0; }   /* chunks in launch order: everything below a ticket is running or done */
     __syncthreads();
     const int ticket = (int)sm.ticket;
     /* tickets walk chunk-major over the payloads (chunk c of every payload before chunk c + 1 of any): the CTAs in flight
@@ -130,39 +131,57 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    /* ---- removal masks ---- */
-    u32 rm[UG], cnt[UG];
+    /* ---- candidates: a removal needs a 0x03 byte in the group and a zero byte in it or right in front - a cheap exact
+            test that few groups pass.  Those are listed and their masks computed by as many lanes as there are candidates:
+            worked out in place, one candidate would take its whole warp through the mask code (two warps in three had one) ---- */
 #pragma unroll
     for (int r = 0; r < UG; r++) {
         const int g = tid + UT * r;
         const int vb = min(max(chunk_bytes - 16 * g, 0), 16);
-        rm[r] = 0u;
+        bool cand = false;
         if (vb > 0) {
             const uint4 w = sm.data[g];
             const u32 prev = (&sm.halo_lo)[g].w;             /* the word in front of the group (halo_lo sits right before data) */
-            const u32 next = (&sm.data[0])[g + 1].x;         /* the word behind it (halo_hi right after data) */
-            const u32 valid = vb == 16 ? 0xFFFFu : (1u << vb) - 1u;
-            /* cheap exact tests first: a removal needs a 0x03 byte in the group and a zero byte in it or right in front */
             const u32 x3 = 0x03030303u;
             const u32 has3 = (((w.x ^ x3) - 0x01010101u) & ~(w.x ^ x3)) | (((w.y ^ x3) - 0x01010101u) & ~(w.y ^ x3)) |
                              (((w.z ^ x3) - 0x01010101u) & ~(w.z ^ x3)) | (((w.w ^ x3) - 0x01010101u) & ~(w.w ^ x3));
             const u32 has0 = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) | ((w.z - 0x01010101u) & ~w.z) |
                              ((w.w - 0x01010101u) & ~w.w) | ((prev - 0x01010101u) & ~prev & 0x80000000u);
-            if ((has3 & 0x80808080u) && (has0 & 0x80808080u)) {
-                const u32 t = mask16(w, 0x03030303u, UFULL) & valid;
-                const u32 z = mask16(w, 0u, UFULL), l3 = mask16(w, 0u, 0xFCFCFCFCu);
-                const u32 zp = nib_le(zero_bytes(prev)) >> 2;            /* zero flags of the two bytes in front: bit 0 = byte -2, bit 1 = byte -1 */
-                const u32 z1 = (z << 1) | (zp >> 1), z2 = (z << 2) | zp; /* byte j-1 zero, byte j-2 zero */
-                /* a next byte must exist: inside the payload (bytes past its end were staged as 0xFF or are masked here) */
-                const u64 left = d.src_bytes - (byte0 + 16u * (u64)g);   /* payload bytes from the group's first byte on */
-                u32 nx = (l3 >> 1) | ((nib_le(zero_bytes(next & 0xFCFCFCFCu)) & 1u) << 15);
-                if (left <= 16u) nx &= (1u << (u32)(left - 1u)) - 1u;   /* byte j + 1 exists only for j + 1 < left */
-                rm[r] = t & z1 & z2 & nx;
-            }
+            cand = (has3 & 0x80808080u) && (has0 & 0x80808080u);
         }
-        cnt[r] = (u32)__popc(rm[r]);
-        sm.gi[g] = (rm[r] << 8) | cnt[r];
+        sm.gi[g] = 0u;
+        const u32 m = __ballot_sync(UFULL, cand);
+        if (m) {
+            u32 at = 0;
+            if (lane == 0) at = atomicAdd(&sm.n_cand, (u32)__popc(m));
+            at = __shfl_sync(UFULL, at, 0);
+            if (cand) sm.list[at + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)g;
+        }
     }
+    __syncthreads();
+    /* ---- removal masks: one lane per candidate ---- */
+    for (u32 i = (u32)tid; i < sm.n_cand; i += UT) {
+        const int g = sm.list[i];
+        const int vb = min(chunk_bytes - 16 * g, 16);
+        const uint4 w = sm.data[g];
+        const u32 prev = (&sm.halo_lo)[g].w;
+        const u32 next = (&sm.data[0])[g + 1].x;             /* the word behind it (halo_hi right after data) */
+        const u32 valid = vb == 16 ? 0xFFFFu : (1u << vb) - 1u;
+        const u32 t = mask16(w, 0x03030303u, UFULL) & valid;
+        const u32 z = mask16(w, 0u, UFULL), l3 = mask16(w, 0u, 0xFCFCFCFCu);
+        const u32 zp = nib_le(zero_bytes(prev)) >> 2;            /* zero flags of the two bytes in front: bit 0 = byte -2, bit 1 = byte -1 */
+        const u32 z1 = (z << 1) | (zp >> 1), z2 = (z << 2) | zp; /* byte j-1 zero, byte j-2 zero */
+        /* a next byte must exist: inside the payload (bytes past its end were staged as 0xFF or are masked here) */
+        const u64 left = d.src_bytes - (byte0 + 16u * (u64)g);   /* payload bytes from the group's first byte on */
+        u32 nx = (l3 >> 1) | ((nib_le(zero_bytes(next & 0xFCFCFCFCu)) & 1u) << 15);
+        if (left <= 16u) nx &= (1u << (u32)(left - 1u)) - 1u;   /* byte j + 1 exists only for j + 1 < left */
+        const u32 rmv = t & z1 & z2 & nx;
+        sm.gi[g] = (rmv << 8) | (u32)__popc(rmv);
+    }
+    __syncthreads();
+    u32 cnt[UG];
+#pragma unroll
+    for (int r = 0; r < UG; r++) cnt[r] = sm.gi[tid + UT * r] & 0xFFu;
     u32 lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16), tlo, thi;
     scan_x2(lo, hi, sm.scan, tlo, thi);
     const u32 t0 = tlo & 0xFFFFu, t1 = tlo >> 16, t2 = thi & 0xFFFFu, t3 = thi >> 16;
