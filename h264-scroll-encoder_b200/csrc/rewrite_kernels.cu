@@ -120,10 +120,21 @@ rewrite_slices_kernel(const H264GpuRewriteDesc *__restrict__ descs, int n_slices
         if (c > 0) {
             u64 wi = byte0 / 4u;                             /* words before the chunk, newest first, 32 at a time */
             bool open = true;
+            /* a word that lies wholly in the copied data is one funnel shift of two source words, the same shift and the
+               same word distance for all of them: inside a long run of zero bytes (a black stripe of an I_PCM atlas is
+               kilobytes of them) the walk goes on for many steps, and this is all a step costs */
+            const long long delta = (long long)d.src_start_bit - (long long)p0;     /* source bit = string bit + delta */
+            const long long dw = delta >> 5;
+            const int dsh = (int)(delta & 31);
             while (open && wi > 0) {
                 const u64 mine = wi > (u64)tid ? wi - 1u - (u64)tid : ~0ull;
                 u32 v = 0xFFFFFFFFu;
-                if (mine != ~0ull) {
+                const bool inside = mine != ~0ull && 32u * mine >= p0 && 32u * mine + 32u <= e_bit &&
+                                    (u64)((long long)mine + dw) + 1u < (u64)n_src_words;
+                if (__all_sync(FULL, inside)) {
+                    const u32 *q = src + ((long long)mine + dw);
+                    v = fshl(__byte_perm(__ldg(q), 0u, 0x0123u), __byte_perm(__ldg(q + 1), 0u, 0x0123u), dsh);
+                } else if (mine != ~0ull) {
                     v = rewrite_word(d, hdr, src, n_src_words, 32u * mine);
                     if (mine == 1u) v |= 0xFF000000u;        /* byte 4 (the NAL header) and the start code never take part */
                     if (mine == 0u) v = 0xFFFFFFFFu;
