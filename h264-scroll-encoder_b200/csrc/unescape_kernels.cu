@@ -39,9 +39,8 @@ struct __align__(16) UnescapeSmem {
     uint4 halo_hi;                       /* the 16 bytes behind it */
     u32 gi[UT * UG];                     /* per group: removal mask << 8 | removed bytes */
     u32 gpre[UT * UG];                   /* bytes removed before a listed group */
-    unsigned short list[UT * UG];        /* groups that go byte by byte */
-    u32 n_list;
-    u32 n_cand;                          /* groups that may hold a removal (listed in front of the masks phase) */
+    unsigned short list[UT * UG];        /* the candidates (the groups that go byte by byte are among them) */
+    u32 n_cand;                          /* listed groups: those that may hold a removal, the partial last one, those next to the buffer's end */
     uint2 scan[UW + 1];
     u32 ticket;
     u32 base;
@@ -103,7 +102,7 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UnescapeSmem &sm = *reinterpret_cast<UnescapeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_list = 0; sm.n_cand = 0; }   /* chunks in launch order: everything below a ticket is running or done */
+    if (tid == 0) { sm.ticket = atomicAdd(state, 1u); sm.n_cand = 0; }   /* chunks in launch order: everything below a ticket is running or done */
     __syncthreads();
     const int ticket = (int)sm.ticket;
     /* tickets walk chunk-major over the payloads (chunk c of every payload before chunk c + 1 of any): the CTAs in flight
@@ -142,12 +141,14 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
         if (vb > 0) {
             const uint4 w = sm.data[g];
             const u32 prev = (&sm.halo_lo)[g].w;             /* the word in front of the group (halo_lo sits right before data) */
-            const u32 x3 = 0x03030303u;
+            const u32 x3 = 0x03030303u;                      /* (the zero-byte test alone: half the instructions, twice the candidates, 0.1196 vs 0.1165 ms) */
             const u32 has3 = (((w.x ^ x3) - 0x01010101u) & ~(w.x ^ x3)) | (((w.y ^ x3) - 0x01010101u) & ~(w.y ^ x3)) |
                              (((w.z ^ x3) - 0x01010101u) & ~(w.z ^ x3)) | (((w.w ^ x3) - 0x01010101u) & ~(w.w ^ x3));
             const u32 has0 = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) | ((w.z - 0x01010101u) & ~w.z) |
                              ((w.w - 0x01010101u) & ~w.w) | ((prev - 0x01010101u) & ~prev & 0x80000000u);
-            cand = (has3 & 0x80808080u) && (has0 & 0x80808080u);
+            /* (the payload's last partial group and groups next to the output buffer's end go byte by byte too: listed here,
+               so that the store phase below has nothing to list) */
+            cand = ((has3 & 0x80808080u) && (has0 & 0x80808080u)) || vb < 16 || byte0 + 16u * (u64)g + 20u > d.out_cap;
         }
         sm.gi[g] = 0u;
         const u32 m = __ballot_sync(UFULL, cand);
@@ -199,7 +200,7 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
         const u64 D64 = byte0 + 16u * (u64)g - before[r];    /* output byte of the group's first byte */
         const u32 D = (u32)D64;
         const uint4 w = sm.data[g];
-        const bool roomy = D64 + 20u <= cap;
+        const bool roomy = byte0 + 16u * (u64)g + 20u <= cap;   /* (as the candidate test has it: removals only move the group down) */
         if (cnt[r] == 0u && vb == 16 && roomy) {
             const u32 s = (4u - (D & 3u)) & 3u;              /* bytes in front of the first aligned output word */
             u32 *o32 = (u32 *)(dst + D + s);
@@ -232,16 +233,17 @@ unescape_kernel(const H264GpuUnescapeDesc *__restrict__ descs, int n_nals, int m
             }
         } else {
             /* a removal inside, the payload's last partial group, or the end of the output buffer in reach: byte by byte,
-               but not here - one such group would hold its whole warp up.  They are listed and dealt out below */
+               but not here - one such group would hold its whole warp up.  They are among the candidates: dealt out below */
             sm.gpre[g] = before[r];
-            sm.list[atomicAdd(&sm.n_list, 1u)] = (unsigned short)g;
         }
     }
     __syncthreads();
-    for (u32 i = (u32)tid; i < 4u * sm.n_list; i += UT) {   /* four lanes per group, a word each: the phase is as long as its longest lane */
+    for (u32 i = (u32)tid; i < 4u * sm.n_cand; i += UT) {   /* four lanes per group, a word each: the phase is as long as its longest lane */
         const int g = sm.list[i >> 2];
         const u32 sub = i & 3u;
-        const int vbs = min(chunk_bytes - 16 * g, 16) - 4 * (int)sub;    /* valid bytes from this word on */
+        const int vbg = min(chunk_bytes - 16 * g, 16);
+        if ((sm.gi[g] & 0xFFu) == 0u && vbg == 16 && byte0 + 16u * (u64)g + 20u <= cap) continue;   /* turned out plain: stored above */
+        const int vbs = vbg - 4 * (int)sub;                  /* valid bytes from this word on */
         if (vbs <= 0) continue;
         const u32 wv = ((const u32 *)sm.data)[4 * g + (int)sub];
         const u32 rmg = sm.gi[g] >> 8;
