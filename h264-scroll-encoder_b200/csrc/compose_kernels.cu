@@ -250,17 +250,51 @@ __device__ __forceinline__ void simple_words(const u32 (&code)[MPT], const u32 (
     if (!s) H = 0u;
 }
 
-/* the queue's consumer side: one lane per item.  Out of line: its loops get their own register allocation */
-__device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_round, u32 wbase, int num_refs) {
+/*
+ * The queue.  A thread whose macroblocks cannot all go through the concatenation path leaves ONE record - its bit offset,
+ * kinds, codes and lengths as they stand in its registers (plus its own hints when a code is longer than 32 bits and has to be
+ * rebuilt: the hint tile may be on its way out by the time the record is read), eight 16-byte words - and the consumer side
+ * spreads the records' macroblocks over all lanes of the CTA: lane i takes macroblock i & 7 of record i >> 3, finds its bit offset and prefix
+ * from the record, and splices / ORs it in.  (Writing one item per macroblock was the longest stage of a tile for the few
+ * warps that had such threads - nine lanes in 32, eight items each - while the others waited.)
+ */
+constexpr int REC16 = 8;                  /* 16-byte words per record: header, ref keys, 8 codes, 8 lengths, 8 motion vectors */
+constexpr int RCAP = LCAP / REC16;        /* records per round */
+
+__device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_rec, u32 wbase, int num_refs, int skip_spec) {
     const u32 *pw = sm.pay_words, *ps = sm.pay_smem;
     const u32 n_words = sm.n_pay_words, staged = sm.pay_staged;
-    for (u32 i = threadIdx.x; i < n_round; i += NT) {
-        const uint4 q = sm.items[i];
-        Item it; it.x = q.x; it.y = q.y; it.z = q.z; it.w = q.w;
+    for (u32 i = threadIdx.x; i < 8u * n_rec; i += NT) {
+        const uint4 *rec = &sm.items[REC16 * (i >> 3)];
+        const int k = (int)(i & 7u);
+        const uint4 h0 = rec[0], la = rec[4], lb = rec[5];
+        const u32 lens[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        u32 bit = h0.x, len = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j < k) bit += lens[j];
+            if (j == k) len = lens[j];
+        }
+        if (!len) continue;
+        const u32 kinds = h0.y, kd = (kinds >> (4 * k)) & 0xFu;
+        u32 pre = 1u;
+        if (skip_spec) {
+            /* mb_skip_run + 1: distance to the coded macroblock before this one (the thread's own, or the one handed in) */
+            const u32 below = k ? kinds & ((1u << (4 * k)) - 1u) : 0u;
+            const int prev = below ? (int)h0.z + (int)(flo32(below) >> 2) : (int)h0.w;
+            pre = (u32)((int)h0.z + k - prev);
+        }
+        const u32 *cw = (const u32 *)(rec + 2) + k;          /* the code word as it lies in the record */
+        uint2 h = make_uint2(0u, 0u);
+        if (kd == MBK_LONG) {                                /* its own hint, left in the record by the thread */
+            h.x = ((const u32 *)(rec + 6))[k];
+            h.y = (((const u32 *)(rec + 1))[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        }
+        const Item it = make_item(kd, *cw, len, bit, pre, h.x, h.y);
         /* a spliced macroblock whose payload words (and the read-ahead word) are all staged reads shared memory */
-        const bool in_smem = (q.x >> 30) == IT_DYN && ((q.z + q.w + 31u) >> 5) + 1u < staged;
-        /* (every staged word can be read: past the payload's end they are zero) */
-        consume_item(it, (const u32 *)&sm.items[i], sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, in_smem ? staged : n_words);
+        const bool in_smem = (it.x >> 30) == IT_DYN && ((it.z + it.w + 31u) >> 5) + 1u < staged;
+        /* (every staged word can be read: past the payload's end they are zero; a short code is read where it lies) */
+        consume_item(it, cw - 2, sm.win, wbase, (u32)CH, num_refs, in_smem ? ps : pw, in_smem ? staged : n_words);
     }
 }
 
@@ -600,14 +634,8 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #pragma unroll
             for (int k = 0; k < MPT; k++) Ls += len[k];
             const bool cplx = kinds_complex(kinds);
-            u32 n_it = 0;
-            if (cplx) {
-#pragma unroll
-                for (int k = 0; k < MPT; k++) n_it += len[k] ? 1u : 0u;
-            }
-            if (owns_trailer) n_it++;
-            u32 ibase = 0;
-            if (n_it) ibase = atomicAdd(&sm.n_items[ipar], n_it);
+            u32 ibase = 0;                                       /* the thread's record in the queue */
+            if (cplx) ibase = atomicAdd(&sm.n_items[ipar], 1u);
             const u32 L = Ls + (owns_trailer ? tr_len : 0u);
 
             /* ---- bit offsets: prefix sum of the threads' bit counts ----------------- */
@@ -715,32 +743,31 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 
                 TRACE(14);
                 STAGE_MARK(3);                                  /* stage next tile, header, concatenation path + merge */
-                /* ---- queue: items of this tile in rounds of LCAP, one lane per item ----------- */
-                for (u32 r0 = 0; r0 < total_items; r0 += (u32)LCAP) {
+                /* ---- queue: the records of this tile in rounds of RCAP, one lane per macroblock ----------- */
+                for (u32 r0 = 0; r0 < total_items; r0 += (u32)RCAP) {
                     if (r0) __syncthreads();                               /* the previous round is consumed */
-                    if (n_it && ibase < r0 + (u32)LCAP && ibase + n_it > r0) {
-                        u32 slot = ibase - r0, bit = O;
-                        int prev = prev0;
-                        if (cplx) {
+                    if (cplx && ibase - r0 < (u32)RCAP) {
+                        uint4 *rec = &sm.items[REC16 * (ibase - r0)];
+                        rec[0] = make_uint4(O, kinds, (u32)g0, (u32)prev0);
+                        {
+                            const u32 t = kinds ^ (0x11111111u * MBK_LONG);
+                            if ((t - 0x11111111u) & ~t & 0x88888888u) {    /* a code that the consumer rebuilds from predictor and hint */
+                                u32 hx[MPT], key[2] = {0u, 0u};
 #pragma unroll
-                            for (int k = 0; k < MPT; k++) {
-                                const u32 kd = (kinds >> (4 * k)) & 0xFu;
-                                if (len[k]) {
-                                    const u32 pre = skip_spec ? (u32)(g0 + k - prev) : 1u;
-                                    prev = g0 + k;
-                                    if (slot < (u32)LCAP) {
-                                        uint2 h = make_uint2(0u, 0u);
-                                        if (kd == MBK_LONG) h = staged_hint(hb, qo, k);    /* (the tile is replaced only behind the queue stage) */
-                                        const Item it = make_item(kd, code[k], len[k], bit, pre, h.x, h.y);
-                                        sm.items[slot] = make_uint4(it.x, it.y, it.z, it.w);
-                                    }
-                                    slot++;
-                                    bit += len[k];
+                                for (int k = 0; k < MPT; k++) {
+                                    const uint2 h = staged_hint(hb, qo, k);
+                                    hx[k] = h.x;
+                                    key[k >> 2] |= (h.y & 0xFFu) << (8 * (k & 3));
                                 }
+                                rec[1] = make_uint4(key[0], key[1], 0u, 0u);
+                                rec[6] = make_uint4(hx[0], hx[1], hx[2], hx[3]);
+                                rec[7] = make_uint4(hx[4], hx[5], hx[6], hx[7]);
                             }
-                        } else bit += Ls;
-                        if (owns_trailer && slot < (u32)LCAP)
-                            sm.items[slot] = make_uint4(bit | (IT_BITS << 30), 0u, tr_code, tr_len);
+                        }
+                        rec[2] = make_uint4(code[0], code[1], code[2], code[3]);
+                        rec[3] = make_uint4(code[4], code[5], code[6], code[7]);
+                        rec[4] = make_uint4(len[0], len[1], len[2], len[3]);
+                        rec[5] = make_uint4(len[4], len[5], len[6], len[7]);
                     }
 #if !COMPOSE_BULK_OPS
                     cp_async_wait_all();                                   /* the staged payload has landed */
@@ -751,9 +778,11 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     __syncthreads();
                     TRACE(16);
                     STAGE_MARK(6);                              /* queue: push + wait for the slowest writer */
-                    consume_round(sm, min((u32)LCAP, total_items - r0), wbase, num_refs);
+                    consume_round(sm, min((u32)RCAP, total_items - r0), wbase, num_refs, skip_spec);
                     TRACE(17);
                 }
+                /* the slice trailer (mb_skip_run of the skipped tail + rbsp_stop_one_bit) goes in behind its thread's macroblocks */
+                if (owns_trailer) win_or64(sm.win, wbase, (u32)CH, O + Ls, (u64)tr_code, tr_len);
 
                 STAGE_MARK(4);                                  /* queue */
                 const bool fits = w_last - wbase < (u32)CH;                /* the tile's last word lies inside the window */

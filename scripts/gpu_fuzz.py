@@ -41,6 +41,11 @@ def run(n_cases, seed0, gc=None, po=None, orc=None, verbose=True):
                 if verbose:
                     print("MISMATCH case %d seed %d frame %d: %dx%d refs %d flags %d p_dyn %.2f zero%% %d mv %d regions %d (dense %s, regions %s)"
                           % (c, seed0 + c, f, w, h, refs, flags, p_dyn, zp, mvr, nreg, ok1, ok2))
+                    for name, g in (("dense", got[f]), ("regions", out[int(offs[f]):int(offs[f + 1])])):
+                        g = np.asarray(g); n = min(len(g), len(want[f]))
+                        d = np.nonzero(g[:n] != want[f][:n])[0]
+                        print("   %s: %d bytes (want %d), %d differing bytes, first at %s, last at %s" %
+                              (name, len(g), len(want[f]), len(d), d[0] if len(d) else None, d[-1] if len(d) else None))
     if verbose:
         print("fuzz: %d cases, %d frames, %d mismatches, %.1f s" % (n_cases, frames, bad, time.time() - t0))
     return bad, frames
