@@ -313,14 +313,21 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
     u32 kinds = 0;
     /* spliced macroblocks: their payload ranges come from the offset table in global memory - all loads of the segment
        are issued here, in front of the votes, so that they overlap instead of queueing one round trip behind the other */
+    u32 any_dyn = 0;
 #pragma unroll
     for (int k = 0; k < MPT; k++) {
         code[k] = 0u; len[k] = 0u;
-        const u32 hy = own[1 + k].y;
-        if (k < nmb && (hy & 0xFF00u) != 0u) {
-            const u32 di = hy >> 16;
-            code[k] = __ldg(tab + di);
-            len[k] = __ldg(tab + di + 1);
+        any_dyn |= own[1 + k].y;
+    }
+    if (__any_sync(FULL, (any_dyn & 0xFF00u) != 0u)) {           /* (most warps have no spliced macroblock at all) */
+#pragma unroll
+        for (int k = 0; k < MPT; k++) {
+            const u32 hy = own[1 + k].y;
+            if (k < nmb && (hy & 0xFF00u) != 0u) {
+                const u32 di = hy >> 16;
+                code[k] = __ldg(tab + di);
+                len[k] = __ldg(tab + di + 1);
+            }
         }
     }
 #pragma unroll
