@@ -21,6 +21,9 @@ constexpr int EMIT_EG = 4;                /* 16-byte groups per thread per pass 
 #ifndef EMIT_STORE_UNROLL
 #define EMIT_STORE_UNROLL 2
 #endif
+#ifndef EMIT_DIRECT
+#define EMIT_DIRECT 1                     /* 1: a pass without insertions stores its groups straight from the window (see emit_window) */
+#endif
 constexpr int EMIT_CU = EMIT_CLASSIFY_UNROLL, EMIT_SU = EMIT_STORE_UNROLL;   /* (by two: fully unrolled loops cost more in code size than they save, 0.871 vs 0.862 ms) */
 
 /* out of line: the backward scan is rare */
@@ -144,12 +147,37 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
             sm.gi[gl] = g;
             /* most listed groups turn out clean (a lone zero byte): the few that do insert - or are partial, or sit next
                to the slot's end - go into a second list, so that the byte-wise phase is as short as its real work */
-            if (!(roomy && g == GI_CLEAN)) sm.elist2[atomicAdd(&sm.n_list2, 1u)] = (unsigned short)gl;
+            /* (counter: entries in the low half; the high half counts the groups that really insert or sit next to the
+               slot's end - a pass without any takes the direct way out below) */
+            if (!(roomy && g == GI_CLEAN)) sm.elist2[atomicAdd(&sm.n_list2, (ins != 0u || !roomy) ? 0x10001u : 1u) & 0xFFFFu] = (unsigned short)gl;
         }
         TRACE(32);
         __syncthreads();
         TRACE(33);
         if (tid == 0) sm.n_list = 0;                         /* the next pass adds to it only after the barriers below */
+        const u32 l2 = sm.n_list2;
+#if EMIT_DIRECT
+        /* ---- nothing is inserted in this pass and the bytes before it sit on a 16-byte boundary of the slot: every group
+                goes out where it lies, as one 128-bit store - no offsets, no lists (the common case: an insertion needs
+                00 00 0x in the slice, and a frame's only window starts at byte 0 of its slot) ---- */
+        if ((l2 >> 16) == 0u && lookback == nullptr && (ins_total & 15u) == 0u) {
+            uint4 *dst4 = (uint4 *)(fout + chunk_byte0 + ins_total);
+#pragma unroll EMIT_SU
+            for (int r = 0; r < EG; r++) {
+                const int q = q0 + tid + NT * r;
+                if (16 * (q + 1) <= chunk_bytes) {
+                    const uint4 w = ((const uint4 *)sm.win)[q];
+                    dst4[q] = make_uint4(__byte_perm(w.x, 0u, 0x0123u), __byte_perm(w.y, 0u, 0x0123u),
+                                         __byte_perm(w.z, 0u, 0x0123u), __byte_perm(w.w, 0u, 0x0123u));
+                }
+            }
+            const int ql = chunk_bytes >> 4;                 /* the chunk's partial last group, byte by byte */
+            if (tid < (chunk_bytes & 15) && ql >= q0 && ql < q0 + EPASS)
+                fout[chunk_byte0 + ins_total + 16u * (u32)ql + (u32)tid] = (uint8_t)(sm.win[4 * ql + (tid >> 2)] >> (24 - 8 * (tid & 3)));
+            if (q0 + EPASS < n_groups) __syncthreads();
+            continue;
+        }
+#endif
         /* ---- offsets ---- */
         u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
         u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
@@ -212,7 +240,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
         __syncthreads();
         TRACE(36);
         /* ---- store: listed groups that insert, are partial, or sit next to the slot's end ---- */
-        const u32 nl2 = sm.n_list2;
+        const u32 nl2 = l2 & 0xFFFFu;
         for (u32 i = (u32)tid; i < 4u * nl2; i += NT) {       /* four lanes per group, a word each: the phase is as long as its longest lane */
             const int gl = sm.elist2[i >> 2], q = q0 + gl;
             const u32 sub = i & 3u;
