@@ -251,13 +251,20 @@ def build_batch(args, rank=0, world=1):
     if wl == "compose":                                       # config 5: weak scaling, args.streams streams per rank
         first, count = sharding.shard_streams(args.streams * world, rank, world)
         return workloads.make_config5(count, args.frames, stream0=first)
-    if wl == "config4":                                       # 64 frames (t = 0..63) x copies: 133 MB of hints at 8 copies
-        return workloads.repeat_batch(workloads.make_config4(64), args.copies or 8)
-    if wl == "config2":                                       # 250 frames x copies: 720p + splice, 167 MB at 16 copies
-        return workloads.repeat_batch(workloads.make_config2(250), args.copies or 16)
-    if wl == "config1":                                       # 248 frames x streams: 228 MB of hints at 32 streams
-        return workloads.make_config1(args.copies or 32, 248)
+    if wl == "config4":                                       # 64 frames (t = 0..63) x copies: 614 MB of hints at 37 copies
+        return workloads.repeat_batch(workloads.make_config4(64), args.copies or DEFAULT_COPIES[wl])
+    if wl == "config2":                                       # 250 frames x copies: 720p + splice
+        return workloads.repeat_batch(workloads.make_config2(250), args.copies or DEFAULT_COPIES[wl])
+    if wl == "config1":                                       # 248 frames x streams
+        return workloads.make_config1(args.copies or DEFAULT_COPIES[wl], 248)
     raise SystemExit("unknown workload " + wl)
+
+
+# Copies of the other named configurations per GPU and step: larger than L2, and a whole number of frames per resident CTA
+# of the persistent compose grid (148 SMs x 2 CTAs, one frame per CTA at a time) - 64 x 37 = 8 x 296, 248 x 37 = 31 x 296,
+# 250 x 13 = 10.98 x 296 - so that the figure is the kernel's rate, not the last partial wave of a small batch
+# (64 x 8 frames of config 4 were 1.73 waves: 0.170 of the roofline against the 0.206 the same kernel does on 8 whole waves).
+DEFAULT_COPIES = {"config4": 37, "config2": 13, "config1": 37}
 
 
 def workload_config(args, b=None):
@@ -266,14 +273,15 @@ def workload_config(args, b=None):
                    "config-3 layout with a 25x25-MB spliced dynamic region, num_refs 2, skip OFF, reference predictor)"
                    % (args.streams, args.frames),
         "config4": "config4: 3840x2160 (240x135 MBs) full-frame scroll with per-row varying MVs, every MB a non-zero mvd, "
-                   "64 frames x %d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or 8),
+                   "64 frames x %d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or DEFAULT_COPIES["config4"]),
         "config2": "config2: 1280x720 legacy scroll 0->720->0 at speed 4 with a 25x25-MB spliced dynamic region, 250 frames x "
-                   "%d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or 16),
+                   "%d copies per GPU, num_refs 2, skip OFF, reference predictor" % (args.copies or DEFAULT_COPIES["config2"]),
         "config1": "config1: experiments/scroll-encoder twin, 1280x720, 248 frames from offset 496 at speed 1 (first frame the "
-                   "waypoint frame, num_refs 2 -> 3) x %d streams per GPU, skip OFF, reference predictor" % (args.copies or 32),
+                   "waypoint frame, num_refs 2 -> 3) x %d streams per GPU, skip OFF, reference predictor" % (args.copies or DEFAULT_COPIES["config1"]),
     }
-    shape = {"compose": (args.streams * args.frames, 8160), "config4": (64 * (args.copies or 8), 32400),
-             "config2": (250 * (args.copies or 16), 3600), "config1": (248 * (args.copies or 32), 3600)}[args.workload]
+    shape = {"compose": (args.streams * args.frames, 8160), "config4": (64 * (args.copies or DEFAULT_COPIES["config4"]), 32400),
+             "config2": (250 * (args.copies or DEFAULT_COPIES["config2"]), 3600),
+             "config1": (248 * (args.copies or DEFAULT_COPIES["config1"]), 3600)}[args.workload]
     cfg = {"workload": names[args.workload], "sharding": "streams block-partitioned over ranks, no collective",
            "frames_per_gpu": shape[0], "mbs_per_frame": shape[1],
            "l2_policy": "inputs larger than L2: %.0f MB of dense hints (+ the spliced payload) per GPU per step vs 126 MB L2"
