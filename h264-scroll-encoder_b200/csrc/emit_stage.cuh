@@ -60,14 +60,30 @@ __device__ __forceinline__ u32 group_insert_mask(const u32 *win, int q, uint4 w,
     return epb_group_mask(z, m3 & keep, vb, rin);
 }
 
+/*
+ * Classification test: can a byte INSIDE this group (MSB-first words w.x .. w.w = bytes 0..15) be an insertion point because
+ * of two zero bytes that both lie in the group?  True when two neighbouring bytes of the group are zero (a superset: the byte
+ * flags may also mark a 0x01 in front of a zero byte).  An insertion point behind zero bytes of the group BEFORE (byte 0 or 1)
+ * shows as "first byte <= 3 behind a zero byte", which the callers test beside this.  A lone zero byte - one group in sixteen
+ * of random data, most groups of a slice full of long Exp-Golomb codes - does not send the group to the masks phase.
+ */
+__device__ __forceinline__ bool group_zero_pair(uint4 w) {
+    const u32 k = 0x01010101u, m = 0x80808080u;
+    const u32 z0 = (w.x - k) & ~w.x & m, z1 = (w.y - k) & ~w.y & m, z2 = (w.z - k) & ~w.z & m, z3 = (w.w - k) & ~w.w & m;
+    /* flag of byte j sits at bit 31 - 8 j of its word: a word's flags shifted up by one byte, the next word's first flag behind them */
+    const u32 p = (z0 & __funnelshift_l(z1, z0, 8)) | (z1 & __funnelshift_l(z2, z1, 8)) |
+                  (z2 & __funnelshift_l(z3, z2, 8)) | (z3 & (z3 << 8));
+    return p != 0u;
+}
+
 constexpr u32 GI_CLEAN = 16u << 8;        /* sm.gi entry of a full group without insertions: ins << 16 | valid bytes << 8 | count */
 
 /*
  * emit: emulation prevention + store of the window's first chunk_bytes bytes (frame bytes from
  * chunk_byte0 on).  Returns the bytes inserted; leaves the closing zero run in sm.zrun[zpar ^ 1].
  * A pass covers EG 16-byte groups per thread:
- *   classify  a group that holds a zero byte (or starts with a byte <= 3 behind one), the frame's last
- *             partial group, everything next to the slot's end -> list; all other groups are clean
+ *   classify  a group that holds two neighbouring zero bytes (or starts with a byte <= 3 behind a zero byte), the frame's
+ *             last partial group, everything next to the slot's end -> list; all other groups are clean
  *   masks     one lane per listed group: exact insert mask + count
  *   offsets   prefix sum of the counts (packed 16-bit fields, one scan for the EG rounds)
  *   store     clean groups leave as aligned or re-aligned 32/128-bit words; the listed groups that
@@ -118,9 +134,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
             bool slow = false;
             if (vb > 0) {
                 const uint4 w = ((const uint4 *)sm.win)[q];
-                const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                               ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-                slow = (hz & 0x80808080u) != 0u || vb < 16 || !roomy;
+                slow = group_zero_pair(w) || vb < 16 || !roomy;
                 if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
                 /* the holder of the window's last byte hands the zero run to the next window */
                 if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
@@ -312,9 +326,7 @@ __device__ EMIT_WARPS_INLINE u32 emit_window_warps(Smem &sm, u32 chunk_byte0, in
         bool slow = false;
         if (vb > 0) {
             const uint4 w = ((const uint4 *)sm.win)[q];
-            const u32 hz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-            slow = (hz & 0x80808080u) != 0u || vb < 16;
+            slow = group_zero_pair(w) || vb < 16;
             if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
             /* the holder of the window's last byte hands the zero run to the next window */
             if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
