@@ -56,6 +56,9 @@ constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
 constexpr int EPASS = EMIT_EG * NT;      /* emit: groups per pass */
 static_assert(LCAP * 16 >= EPASS * 4, "sm.gi aliases sm.items");
 
+#ifndef COMPOSE_ROW_VOTE
+#define COMPOSE_ROW_VOTE 1               /* 1: frames without a spliced region try one whole-warp "rows of one motion" vote first (decide_segment) */
+#endif
 #ifndef COMPOSE_TIMING
 #define COMPOSE_TIMING 0                 /* 1: thread 0 of every CTA accumulates clock64() per pipeline stage (experiments only) */
 #endif
@@ -308,9 +311,33 @@ __device__ __noinline__ void consume_round(ComposeSmem &sm, u32 n_rec, u32 wbase
 template <int GEN, int DUMMY>
 __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const uint2 (&abv)[MPT + 2], int nmb, bool first, bool row0,
                                               int num_refs, const u32 *__restrict__ tab, u32 (&code)[MPT], u32 (&len)[MPT],
-                                              int skip_spec_in = 0, int pred_spec_in = 0) {
+                                              bool rows, int skip_spec_in = 0, int pred_spec_in = 0) {
     const int skip_spec = GEN ? skip_spec_in : 0, pred_spec = GEN ? pred_spec_in : 0;
     u32 kinds = 0;
+#if COMPOSE_ROW_VOTE
+    if (rows) {
+        /* frames without a spliced region (the reference's own scroll frames, per-row motion): ONE vote - every segment of the
+           warp whole, its own hints all alike and the hints above it all alike.  Macroblocks 1..7 then share their inputs
+           (own, A = own, B, C = B; at a row's end C is D = the same hint): one code for them, macroblock 0 (its A is the
+           segment before, or nothing) by itself */
+        u32 d = own[1].y & 0xFF00u;
+#pragma unroll
+        for (int k = 2; k <= MPT; k++) d |= (own[k].x ^ own[1].x) | (own[k].y ^ own[1].y);
+#pragma unroll
+        for (int k = 2; k <= MPT + 1; k++) d |= (abv[k].x ^ abv[1].x) | (abv[k].y ^ abv[1].y);
+        if (__all_sync(FULL, nmb == 0 || (nmb == MPT && d == 0u))) {
+            u32 c0 = 0u, l0 = 0u, c1 = 0u, l1 = 0u, k0 = MBK_NONE, k1 = MBK_NONE;
+            if (nmb) {
+                k0 = decide_mb(own[1].x, own[1].y, own[0].x, own[0].y, abv[1].x, abv[1].y, abv[2].x, abv[2].y, num_refs, pred_spec, skip_spec, c0, l0);
+                k1 = decide_mb(own[2].x, own[2].y, own[1].x, own[1].y, abv[2].x, abv[2].y, abv[3].x, abv[3].y, num_refs, pred_spec, skip_spec, c1, l1);
+            }
+            code[0] = c0; len[0] = l0;
+#pragma unroll
+            for (int k = 1; k < MPT; k++) { code[k] = c1; len[k] = l1; }
+            return k0 | (k1 * 0x11111110u);
+        }
+    }
+#endif
     /* spliced macroblocks: their payload ranges come from the offset table in global memory - all loads of the segment
        are issued here, in front of the votes, so that they overlap instead of queueing one round trip behind the other */
     u32 any_dyn = 0;
@@ -606,8 +633,8 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             /* ---- decide + code ------------------------------------------------ */
             u32 code[MPT], len[MPT];
             u32 kinds;
-            if (!SPEC) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len);
-            else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, skip_spec, pred_spec);
+            if (!SPEC) kinds = decide_segment<0, 0>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, tab == nullptr);
+            else kinds = decide_segment<1, 1>(own, abv, nmb, first, row == 0, num_refs, tab, code, len, tab == nullptr, skip_spec, pred_spec);
 
             STAGE_MARK(1);                                      /* load + decide */
             /* ---- mb_skip_run prefixes (SPEC skip; with skip OFF the constant bit is already in) ---- */
