@@ -50,6 +50,7 @@ constexpr int LCAP = COMPOSE_ITEM_SLOTS; /* queue items per round */
 constexpr int HBS = COMPOSE_HINT_SLOTS;  /* 64-byte segment slots per staged hint tile */
 constexpr int TBOX_ROWS = 96;            /* TMA box: 96 rows of 128 bytes (12 KB) of the dense map seen as a [rows][32 x u32] tensor: three boxes per tile */
 constexpr int TBOX_BYTES = TBOX_ROWS * 128;
+constexpr u32 PF_AHEAD = 2u * HBS * 64u;   /* bytes of the next frame's dense map sent to L2 a frame ahead: two tiles */
 static_assert((HBS * 64) % TBOX_BYTES == 0, "the hint tile buffer is a whole number of TMA boxes");
 constexpr u32 FULL = 0xFFFFFFFFu;
 constexpr int PAYBUF16 = COMPOSE_PAYBUF16;
@@ -186,6 +187,10 @@ __device__ __forceinline__ void stage_hints_tma(ComposeSmem &sm, const CUtensorM
         mbar_arrive_expect_tx(&sm.hints_full, (u32)(boxes * TBOX_BYTES));
         for (int i = 0; i < boxes; i++)
             tma_load_box((char *)sm.hbuf + i * TBOX_BYTES, tmap, ((abs_base - shift) >> 1) + i * TBOX_ROWS, &sm.hints_full);
+        /* the tile behind this one on its way to L2 (tiles past the two that the frame-ahead prefetch covers) */
+        const int sn = s0 + n;
+        if (64u * (u32)sn >= PF_AHEAD && sn < g.n_seg)
+            bulk_prefetch_l2(g.fh + 8 * (long long)sn, 64u * (u32)min(g.seg_max, g.n_seg - sn));
     }
 }
 
@@ -564,7 +569,10 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
 #if COMPOSE_BULK_OPS
             /* the next frame's dense hint map goes to L2 a whole frame ahead (bulk prefetch): its tile copies find it there */
             const u32 n_bytes = (8u * (u32)(geo_next.W * geo_next.H)) & ~15u;
-            if (tid == 32 && n_bytes) bulk_prefetch_l2(geo_next.fh, n_bytes < (1u << 20) ? n_bytes : (1u << 20));
+            /* (its first two tiles: what lies behind them follows tile by tile, stage_hints_tma - the whole map of a 4K frame
+               a frame ahead, 259 KB x 296 CTAs, does not stay in the 126 MB L2 beside the maps being read: ncu showed 1.7x the
+               hint bytes in DRAM reads on config 4) */
+            if (tid == 32 && n_bytes) bulk_prefetch_l2(geo_next.fh, n_bytes < PF_AHEAD ? n_bytes : PF_AHEAD);
 #endif
         }
 
