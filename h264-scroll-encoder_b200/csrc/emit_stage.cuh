@@ -127,8 +127,11 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                            (lookback ? chunk_byte0 / 2u + 1u : ins_total) + 4u <= cap;
         /* ---- classify ---- */
         if (tid == 0) sm.n_list2 = 0;                        /* (read last in front of the previous pass's closing barrier) */
+        /* rounds of NT groups this pass holds (a 720p scroll frame is a tenth of a window: one round, not four) */
+        const int n_rounds = min(EG, (n_groups - q0 + NT - 1) / NT);
 #pragma unroll EMIT_CU                         /* (code size matters more than the loop overhead) */
         for (int r = 0; r < EG; r++) {
+            if (r >= n_rounds) break;
             const int gl = tid + NT * r, q = q0 + gl;
             const int vb = min(max(chunk_bytes - 16 * q, 0), 16);
             bool slow = false;
@@ -178,6 +181,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
             uint4 *dst4 = (uint4 *)(fout + chunk_byte0 + ins_total);
 #pragma unroll EMIT_SU
             for (int r = 0; r < EG; r++) {
+                if (r >= n_rounds) break;
                 const int q = q0 + tid + NT * r;
                 if (16 * (q + 1) <= chunk_bytes) {
                     const uint4 w = ((const uint4 *)sm.win)[q];
@@ -193,8 +197,10 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
         }
 #endif
         /* ---- offsets ---- */
-        u32 lo = (sm.gi[tid] & 0xFFu) | ((sm.gi[tid + NT] & 0xFFu) << 16);
-        u32 hi = (sm.gi[tid + 2 * NT] & 0xFFu) | ((sm.gi[tid + 3 * NT] & 0xFFu) << 16);
+        u32 lo = sm.gi[tid] & 0xFFu, hi = 0u;                /* (rounds past n_rounds were not classified: nothing there) */
+        if (n_rounds > 1) lo |= (sm.gi[tid + NT] & 0xFFu) << 16;
+        if (n_rounds > 2) hi = sm.gi[tid + 2 * NT] & 0xFFu;
+        if (n_rounds > 3) hi |= (sm.gi[tid + 3 * NT] & 0xFFu) << 16;
         u32 tlo, thi;
         group_excl_scan_x2<NW, 0>(lo, hi, sm.scan2, tid >> 5, tlo, thi);      /* barriers on both sides of every pass: one buffer does */
         TRACE(34);
@@ -210,6 +216,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
         u32 round_base = ins_total;                          /* bytes inserted before the round's first group */
 #pragma unroll EMIT_SU
         for (int r = 0; r < EG; r++) {
+            if (r >= n_rounds) break;
             const int gl = tid + NT * r, q = q0 + gl;
             const u32 g = sm.gi[gl];
             const u32 before = round_base + (((r & 2) ? hi : lo) >> (16 * (r & 1)) & 0xFFFFu);
@@ -228,7 +235,7 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
             } else {
                 /* re-aligned words; the bytes shared with a neighbour are whole-word stores only when the neighbour is clean too */
                 const bool prev_clean = gl > 0 && sm.gi[gl - 1] == GI_CLEAN;
-                const bool next_clean = gl < EPASS - 1 && sm.gi[gl + 1] == GI_CLEAN;
+                const bool next_clean = gl < EPASS - 1 && q + 1 < n_groups && sm.gi[gl + 1] == GI_CLEAN;   /* (classified in this pass) */
                 const u32 wn = sm.win[4 * q + 4];
                 const u32 sel = realign_selector(s);
                 dst[0] = __byte_perm(w.x, w.y, sel);
