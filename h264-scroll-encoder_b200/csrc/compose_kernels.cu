@@ -117,6 +117,14 @@ struct FrameGeo {
     int tma_seg0;         /* >= 0: the frame's tiles come by TMA; 64-byte segment index of its first hint in the map (even); -1: cp.async */
 };
 
+/* s / tpr == umulhi(s, magic[tpr]) for s < 2^25: magic[tpr] = floor((2^32 - 1) / tpr) + 1, tpr = segments per row <= (MAX_MB_W + 7) / 8 */
+constexpr int TPR_MAX = (COMPOSE_MAX_MB_W + MPT - 1) / MPT;
+struct TprMagic {
+    u32 v[TPR_MAX + 1];
+    constexpr TprMagic() : v() { v[0] = 0u; for (int t = 1; t <= TPR_MAX; t++) v[t] = 0xFFFFFFFFu / (u32)t + 1u; }
+};
+__constant__ TprMagic c_tpr_magic = TprMagic();
+
 __device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict__ descs, int f,
                                              const H264GpuMbHint *__restrict__ hints, unsigned long long tma_hints = 0) {
     const uint4 *dq = (const uint4 *)(descs + f);
@@ -128,7 +136,7 @@ __device__ __forceinline__ FrameGeo load_geo(const H264GpuFrameDesc *__restrict_
     g.tpr = (g.W + MPT - 1) / MPT;
     g.n_seg = g.tpr * g.H;
     g.seg_max = min(NT, HBS - g.tpr - 2);                    /* (one slot in reserve: a TMA tile starts on a 128-byte row) */
-    g.tpr_magic = 0xFFFFFFFFu / (u32)g.tpr + 1u;
+    g.tpr_magic = c_tpr_magic.v[g.tpr];                      /* 0xFFFFFFFF / tpr + 1 from constant memory: the division is ~25 instructions per warp and frame */
     /* TMA: the map's rows are 128 bytes = 16 hints; the frame must start on a row, tile the map with whole segments, and
        end inside the rows the tensor map covers (tma_hints: 0 when the launch has no tensor map) */
     const u64 h0 = (u64)d2.x | ((u64)d2.y << 32);
