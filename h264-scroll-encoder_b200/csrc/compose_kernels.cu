@@ -426,6 +426,8 @@ __device__ __forceinline__ bool frame_is_spec(const H264GpuFrameDesc *__restrict
 template <bool SPEC>
 __device__ __forceinline__ int next_own_frame(const H264GpuFrameDesc *__restrict__ descs, int f, int n_frames, int step) {
     const int lane = threadIdx.x & 31;
+    /* (a batch of one mode - the usual case - answers with the first candidate: one broadcast load instead of 32 scattered ones) */
+    if (f < n_frames && frame_is_spec(descs, f) == SPEC) return f;
     while (f < n_frames) {
         const long long mine = (long long)f + (long long)lane * step;
         const bool own = mine < n_frames && frame_is_spec(descs, (int)mine) == SPEC;
