@@ -166,7 +166,7 @@ def cpu_sample(po, args):
     payload | None, what)."""
     from h264_scroll_encoder_b200 import workloads, abi
     wl = args.workload
-    if wl == "compose":
+    if wl in ("compose", "config5spec"):                    # (the reference has one mode: skip OFF, its own predictor)
         b, what = workloads.make_config5(2, 8), "2 streams x 8 frames of the config-5 workload"
     elif wl == "config4":
         b, what = workloads.make_config4(4), "4 frames of config 4"
@@ -257,6 +257,9 @@ def build_batch(args, rank=0, world=1):
         return workloads.repeat_batch(workloads.make_config2(250), args.copies or DEFAULT_COPIES[wl])
     if wl == "config1":                                       # 248 frames x streams
         return workloads.make_config1(args.copies or DEFAULT_COPIES[wl], 248)
+    if wl == "config5spec":                                   # config-5 streams coded with spec P_Skip + the spec median predictor
+        from h264_scroll_encoder_b200 import abi
+        return workloads.make_config5(args.copies or DEFAULT_COPIES[wl], 64, flags=abi.SKIP_SPEC | abi.PRED_SPEC)
     raise SystemExit("unknown workload " + wl)
 
 
@@ -264,7 +267,7 @@ def build_batch(args, rank=0, world=1):
 # of the persistent compose grid (148 SMs x 2 CTAs, one frame per CTA at a time) - 64 x 37 = 8 x 296, 248 x 37 = 31 x 296,
 # 250 x 13 = 10.98 x 296 - so that the figure is the kernel's rate, not the last partial wave of a small batch
 # (64 x 8 frames of config 4 were 1.73 waves: 0.170 of the roofline against the 0.206 the same kernel does on 8 whole waves).
-DEFAULT_COPIES = {"config4": 37, "config2": 13, "config1": 37}
+DEFAULT_COPIES = {"config4": 37, "config2": 13, "config1": 37, "config5spec": 37}
 
 
 def workload_config(args, b=None):
@@ -279,7 +282,11 @@ def workload_config(args, b=None):
         "config1": "config1: experiments/scroll-encoder twin, 1280x720, 248 frames from offset 496 at speed 1 (first frame the "
                    "waypoint frame, num_refs 2 -> 3) x %d streams per GPU, skip OFF, reference predictor" % (args.copies or DEFAULT_COPIES["config1"]),
     }
+    names["config5spec"] = ("config5 streams in the SPEC modes (SURVEY 8f rank 3: mb_skip_run / P_Skip and the median predictor as H.264 "
+                            "8.4.1.1-8.4.1.3 have them - no counterpart in the reference; checked against the oracle port): %d streams x 64 "
+                            "frames of 1920x1088 per GPU with the 25x25-MB spliced region, num_refs 2" % (args.copies or DEFAULT_COPIES["config5spec"]))
     shape = {"compose": (args.streams * args.frames, 8160), "config4": (64 * (args.copies or DEFAULT_COPIES["config4"]), 32400),
+             "config5spec": (64 * (args.copies or DEFAULT_COPIES["config5spec"]), 8160),
              "config2": (250 * (args.copies or DEFAULT_COPIES["config2"]), 3600),
              "config1": (248 * (args.copies or DEFAULT_COPIES["config1"]), 3600)}[args.workload]
     cfg = {"workload": names[args.workload], "sharding": "streams block-partitioned over ranks, no collective",
@@ -308,7 +315,8 @@ def check_bit_exact(po, b, hints_of, frames_of, n_check=64, seed=11):
     """>= n_check frames of the timed run's output against the reference's own functions (oracle/_ref) or the port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
-    chk, kind = (po.Ref(), "reference") if po.have_ref() else (po.Oracle(), "port")
+    spec = bool((np.asarray(b.desc["flags"]) != 0).any())        # SPEC modes: the reference has none - the oracle port checks
+    chk, kind = (po.Ref(), "reference") if po.have_ref() and not spec else (po.Oracle(), "port")
     pick = np.random.default_rng(seed).choice(b.n_frames, min(n_check, b.n_frames), replace=False)
     for f in pick:
         f = int(f)
@@ -507,8 +515,13 @@ def main_ours(args):
                           "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
-            try:
-                line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            try:                                                  # (one ncu capture of this workload's full-size launch, not measured in this run)
+                t = json.load(open(tr))
+                t = t if args.workload == "compose" else t.get("other_workloads", {}).get(args.workload, {})
+                same_batch = args.workload != "compose" or (args.streams, args.frames) == (128, 64)
+                if same_batch and t.get("dram_bytes_per_launch"):
+                    line["roofline"]["traffic"] = t["dram_bytes_per_launch"]
+                    line["roofline"]["traffic_source"] = "profiles/traffic.json (ncu capture of this workload's launch; not measured in this run)"
             except Exception:
                 pass
         if world == 1 and not args.no_cpu:
@@ -566,7 +579,7 @@ def quick_kernel_fraction(gc, args, wl):
 def default_line_extras(args, gc):
     """What the default line carries beside the config-5 numbers, so that the driver records them too."""
     extras = {"other_configs": {}, "side_kernels": {}}
-    for wl in ("config4", "config2", "config1"):
+    for wl in ("config4", "config2", "config1", "config5spec"):
         extras["other_configs"][wl] = quick_kernel_fraction(gc, args, wl)
     a = argparse.Namespace(**vars(args))
     a.no_cpu, a.steps, a.warmup = True, 10, 3
@@ -789,7 +802,7 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=64, help="frames per stream per step")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="compose", choices=["compose", "config4", "config2", "config1", "rewrite", "unescape", "latency"],
+    ap.add_argument("--workload", default="compose", choices=["compose", "config4", "config2", "config1", "config5spec", "rewrite", "unescape", "latency"],
                     help="compose = the north-star metric on config 5 (default); config4 / config2 / config1 = the other named "
                          "resolutions; rewrite / unescape = side kernels (SURVEY 8f); latency = per-call latency of the frame writer")
     ap.add_argument("--copies", type=int, default=0, help="config4/2/1: copies of the configuration's frames per GPU (0 = enough to exceed L2)")
