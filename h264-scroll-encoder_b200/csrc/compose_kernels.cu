@@ -7,15 +7,18 @@
  * A frame is cut into segments of 8 consecutive macroblocks of one row; a thread owns one segment, a tile is up to 512
  * consecutive segments (4096 macroblocks).
  *
- *   stage    the hints of the tile plus the row above it are copied global -> shared with 16-byte cp.async into a
- *            swizzled layout (every thread later reads its own 64 bytes with conflict-free 128-bit loads); the copy of
- *            the next tile - of the next frame when this one ends - is in flight while the current tile is composed.
- *            The next frame's whole dense map is sent to L2 a frame ahead (cp.async.bulk.prefetch.L2), and the frame's
- *            pre-encoded payload comes to shared memory with ONE bulk copy through the TMA unit
+ *   stage    the hints of the tile plus the row above it come global -> shared through the TMA unit: the dense maps are one
+ *            2-D tensor of 128-byte rows, a tile is three boxes of 96 rows issued by ONE thread (cp.async.bulk.tensor.2d,
+ *            SWIZZLE_128B = the layout the readers use, completion on an mbarrier); frames that do not start on a 128-byte
+ *            row or are not a multiple of 8 macroblocks wide take the same tile with 16-byte cp.async.  The copy of the next
+ *            tile - of the next frame when this one ends - is in flight while the window is filled / emitted.  The first two
+ *            tiles of the next frame's map are sent to L2 a frame ahead, further tiles one tile ahead
+ *            (cp.async.bulk.prefetch.L2), and the frame's pre-encoded payload comes to shared memory with ONE bulk copy
  *            (cp.async.bulk.shared.global, completion counted on an mbarrier)
  *   decide   per MB: A/B/C(D) neighbours from shared memory, packed int16 predictor, P_Skip test, mvd, closed-form
  *            Exp-Golomb -> a <= 32-bit code + length in registers.  Where a whole warp sits in uniform motion the
- *            constant code is taken instead (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
+ *            constant code is taken instead; frames without a spliced region try one whole-warp "rows of one motion" vote
+ *            first (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
  *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
  *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
  *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word integer (picked per
@@ -24,9 +27,10 @@
  *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice trailer - becomes 16-byte
  *            work items that are spread over all lanes of the CTA: one lane splices one pre-encoded MB (copy_bits,
  *            src/h264_writer.c:228) with funnel shifts, whole words as plain stores, edge words with atomicOr
- *   emit     (emit_stage.cuh) emulation prevention (src/nal.c:24-50) on 16-byte groups: the rare groups - a zero byte
- *            inside, the frame's tail - are compacted into a list first and worked through densely; groups without
- *            insertions leave as re-aligned 32/128-bit words; the window is cleared with one st.bulk
+ *   emit     (emit_stage.cuh) emulation prevention (src/nal.c:24-50) on 16-byte groups: the rare groups - two neighbouring
+ *            zero bytes inside, the frame's tail - are compacted into a list first and worked through densely; groups
+ *            without insertions leave as re-aligned 32/128-bit words, a window without any straight from where it lies;
+ *            the window is cleared with one st.bulk
  *
  * The Annex-B start code, the NAL header byte and the host-written slice header are the first bits of the same bit
  * string, so the window image is the output image.
