@@ -62,7 +62,7 @@ class ClockSampler:
     (the region lasts tens of milliseconds: too short for nvidia-smi's 100 ms loop)."""
 
     def __init__(self, index):
-        self.index, self.sm, self.reasons, self.stop_flag, self.t, self.max = index, [], 0, False, None, None
+        self.index, self.sm, self.ts, self.reasons, self.stop_flag, self.t, self.max = index, [], [], 0, False, None, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -77,6 +77,7 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.ts.append(time.perf_counter())
                 self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:                        # noqa: BLE001
                 pass
@@ -372,19 +373,21 @@ def main_ours(args):
     def kernel_step():
         gc.compose_batch(d_desc, n, d_hints, d_dyn, d_tab, d_pay, d_out, d_sizes)
 
+    sampler = ClockSampler(local)                 # (started in front of the warm-up: its first NVML reads take milliseconds)
+    sampler.start()
     for _ in range(args.warmup):
         kernel_step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = gc.launch_count()
+    t_region0 = time.perf_counter()
     gc.check(L.h264gpu_event_record(ev0, None))
     for _ in range(args.steps):
         kernel_step()
     gc.check(L.h264gpu_event_record(ev1, None))
     ms = L.h264gpu_event_elapsed_ms(ev0, ev1)
+    t_region1 = time.perf_counter()
     launches = gc.launch_count() - launches0
-    samples_timed = len(sampler.sm)
+    samples_timed = sum(1 for t in list(sampler.ts) if t_region0 <= t <= t_region1)
     # the timed region is ~10 ms - one or two NVML reads; the same kernel keeps running (untimed) while the sampler goes on,
     # so that the median is taken over a few dozen samples under the very same load
     t_end = time.perf_counter() + 0.06
