@@ -139,8 +139,6 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                 const uint4 w = ((const uint4 *)sm.win)[q];
                 slow = group_zero_pair(w) || vb < 16 || !roomy;
                 if (!slow && (w.x >> 26) == 0u) slow = q == 0 || (sm.win[4 * q - 1] & 0xFFu) == 0u;
-                /* the holder of the window's last byte hands the zero run to the next window */
-                if (16 * (q + 1) >= chunk_bytes) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
             }
             sm.gi[gl] = (u32)vb << 8;
             const u32 m = __ballot_sync(FULL, slow);
@@ -151,6 +149,8 @@ __device__ __noinline__ u32 emit_window(Smem &sm, u32 chunk_byte0, int chunk_byt
                 if (slow) sm.elist[base + (u32)__popc(m & ((1u << lane) - 1u))] = (unsigned short)gl;
             }
         }
+        /* the zero run the window ends in goes to the next window (one thread, once: not a test in every round of the loop) */
+        if (tid == NT - 1 && q0 + EPASS >= n_groups && chunk_bytes > 0) sm.zrun[zpar ^ 1u] = zeros_before_win(sm.win, (u32)chunk_bytes, zrun_in);
         TRACE(30);
         __syncthreads();
         TRACE(31);
