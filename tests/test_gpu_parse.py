@@ -67,3 +67,41 @@ def test_parse_composed_stream(gpu, po):
         want = _cpu_units(gpu.lib, stream)[:max_nals]
         got = [(int(u["offset"]), int(u["size"]), int(u["nal_ref_idc"]), int(u["nal_unit_type"])) for u in units]
         assert got == want
+
+
+def _ref_parser_lib(gpu):
+    ref = os.path.join(helpers.ROOT, "oracle", "_ref", "libref_composer.so")
+    lib = C.CDLL(ref) if os.path.exists(ref) else gpu.lib          # (the reference's own parser where oracle/_ref is built)
+    lib.ebsp_to_rbsp.restype = C.c_size_t
+    lib.ebsp_to_rbsp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.rbsp_to_ebsp.restype = C.c_size_t
+    lib.rbsp_to_ebsp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    return lib
+
+
+@pytest.mark.parametrize("which", ["config2", "config3", "config4", "config5 spec modes", "config1"])
+def test_every_configuration_parses_cleanly_with_the_reference_parser(gpu, po, which):
+    """north_star: the output "must parse cleanly with the reference's nal_parser" - every named configuration, not only
+    config 5: nal_parser_next (src/nal_parser.c:14-65) finds one P-slice unit per frame exactly where the frames lie, and
+    ebsp_to_rbsp (:67-88) followed by rbsp_to_ebsp (src/nal.c:24-50) gives the unit's bytes back."""
+    b = {"config2": lambda: workloads.make_config2(12), "config3": lambda: workloads.make_config3(6),
+         "config4": lambda: workloads.make_config4(2),
+         "config5 spec modes": lambda: workloads.make_config5(2, 4, flags=abi.SKIP_SPEC | abi.PRED_SPEC),
+         "config1": lambda: workloads.make_config1(1, 24)}[which]()
+    hints = helpers.dense_hints(po, b)
+    frames, _ = gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload)
+    stream = np.ascontiguousarray(np.concatenate(frames), np.uint8)
+    lib = _ref_parser_lib(gpu)
+    units = _cpu_units(lib, stream)
+    assert len(units) == b.n_frames
+    starts = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    for f, (off, size, ref_idc, typ) in enumerate(units):
+        assert typ == 1 and off == starts[f] + 5 and size == len(frames[f]) - 5, "frame %d" % f      # 00 00 00 01 + header byte
+        assert ref_idc == (int(b.desc["nal_header"][f]) >> 5) & 3
+        ebsp = np.ascontiguousarray(stream[off:off + size])
+        rbsp = np.zeros(size + 8, np.uint8)
+        n = lib.ebsp_to_rbsp(rbsp.ctypes.data, ebsp.ctypes.data, size)
+        back = np.zeros(2 * size + 8, np.uint8)
+        m = lib.rbsp_to_ebsp(back.ctypes.data, len(back), rbsp.ctypes.data, n)
+        assert m == size and np.array_equal(back[:m], ebsp), "frame %d: escape round trip" % f
+        assert rbsp[n - 1] != 0                                                                         # rbsp_stop_one_bit in the last byte
