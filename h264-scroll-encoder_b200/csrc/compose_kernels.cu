@@ -21,7 +21,7 @@
  *            first (replaces src/h264_writer.c:595-641, :369-453, src/bitwriter.c:50-101)
  *   skiprun  SPEC mode only: block prefix-max of "last coded MB" -> mb_skip_run prefixes
  *   scan     block prefix sum of the threads' bit counts -> slice bit offsets
- *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/4/8-word integer (picked per
+ *   write    a thread whose 8 codes are all short concatenates them branch-free into a 2/3/4/8-word integer (picked per
  *            warp), shifts it to its slice bit offset and stores whole words into the shared-memory window (32 KB);
  *            partial first/last words of neighbouring threads are merged by shuffle
  *   queue    everything else - spliced MBs, long codes, separately prefixed codes, the slice trailer - becomes 16-byte
@@ -757,6 +757,8 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     bool has_t = false;
                     const u32 lmax = __reduce_max_sync(FULL, Lc);
                     if (lmax <= 64u) { if (Lc) simple_words<2>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
+                    /* (65..96 bits: a segment of 6-bit codes with one long mvd - the macroblock in front of a region edge) */
+                    else if (lmax <= 96u) { if (Lc) simple_words<3>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
                     else if (lmax <= 128u) { if (Lc) simple_words<4>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
                     else { if (Lc) simple_words<8>(code, len, O, Lc, sm.win, wbase, H, T, has_t); }
                     const u32 key = O >> 5;
