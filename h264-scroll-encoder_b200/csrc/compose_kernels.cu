@@ -637,13 +637,13 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                 abv[0] = staged_hint(hb, qa - 1, 7);
                 abv[MPT + 1] = staged_hint(hb, qa + 1, 0);
                 if (first) { own[0] = make_uint2(0u, HINT_Y_UNAVAIL); abv[0] = make_uint2(0u, HINT_Y_UNAVAIL); }
-                if (lastseg) {                                  /* C of the row's last MB is D (src/h264_writer.c:391-399) */
-                    if (kc == 7) abv[9] = abv[7];
-                    else {
+                /* C of the row's last MB is D (src/h264_writer.c:391-399).  (The frame-wide test outside: widths that are a multiple
+                   of 8 macroblocks - nearly all - branch over the chain for the other seven positions) */
+                if (kc == 7) { if (lastseg) abv[9] = abv[7]; }
+                else if (lastseg) {
 #pragma unroll
-                        for (int j = 0; j < MPT - 1; j++)
-                            if (kc == j) abv[j + 2] = abv[j];
-                    }
+                    for (int j = 0; j < MPT - 1; j++)
+                        if (kc == j) abv[j + 2] = abv[j];
                 }
             } else {
 #pragma unroll
