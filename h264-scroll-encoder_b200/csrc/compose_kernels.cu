@@ -622,11 +622,15 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             const int nmb = active ? min(MPT, W - MPT * col) : 0;
             const int g0 = row * W + MPT * col;                 /* raster index of the segment's first MB */
             const bool first = col == 0, lastseg = col == geo.tpr - 1;
-            const int qo = tid + geo.tpr + 1 + shift, qa = tid + 1 + shift;     /* slots of the own segment and of the one above */
+            /* slots of the own segment and of the one above.  (A thread past the tile's end reads thread 0's: what it holds is
+               never looked at - nmb = 0 keeps it out of every vote and every store - and filling its 38 registers with the
+               "unavailable" hint instead cost every thread 38 predicated moves per tile) */
+            const int tq = active ? tid : 0;
+            const int qo = tq + geo.tpr + 1 + shift, qa = tq + 1 + shift;
 
             uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
             uint2 abv[MPT + 2];                                 /* abv[j] = hint above-left of MB j */
-            if (active) {
+            {
 #pragma unroll
                 for (int k = 0; k < MPT / 2; k++) {
                     const uint4 v = staged_chunk(hb, qo, k), u = staged_chunk(hb, qa, k);
@@ -645,11 +649,6 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                     for (int j = 0; j < MPT - 1; j++)
                         if (kc == j) abv[j + 2] = abv[j];
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k <= MPT; k++) own[k] = make_uint2(0u, HINT_Y_UNAVAIL);
-#pragma unroll
-                for (int j = 0; j < MPT + 2; j++) abv[j] = make_uint2(0u, HINT_Y_UNAVAIL);
             }
 
             /* ---- decide + code ------------------------------------------------ */
@@ -813,7 +812,7 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
                                 u32 hx[MPT], key[2] = {0u, 0u};
 #pragma unroll
                                 for (int k = 0; k < MPT; k++) {
-                                    const uint2 h = staged_hint(hb, qo, k);
+                                    const uint2 h = staged_hint(hb, tid + geo.tpr + 1 + shift, k);   /* (its own slot: a queueing thread is inside the tile) */
                                     hx[k] = h.x;
                                     key[k >> 2] |= (h.y & 0xFFu) << (8 * (k & 3));
                                 }
