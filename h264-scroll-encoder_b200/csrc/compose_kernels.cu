@@ -383,11 +383,12 @@ __device__ __forceinline__ u32 decide_segment(const uint2 (&own)[MPT + 1], const
         if (skip_spec) {
             /* P_Skip looks at A and B themselves: all three neighbours must carry the MB's own hint */
             uni = ((h.x ^ a.x) | (h.y ^ a.y) | (h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
-        } else if (row0) {
-            /* top row: A alone decides (src/h264_writer.c:407-417); no neighbour at all predicts 0 */
-            uni = ((h.x ^ a.x) | (h.y ^ a.y)) == 0u;
         } else {
-            /* B == C == the MB's own hint: two refs match, and both medians of (a, h, h) are h whatever A is */
+            /* B == C == the MB's own hint: two refs match, and both medians of (a, h, h) are h whatever A is.  (The top row -
+               A alone decides, src/h264_writer.c:407-417 - has no shortcut of its own: its B and C are the "unavailable" hint,
+               the test fails, and the one warp that holds the row takes the predictor once per segment and the "same as the
+               macroblock before" path for the rest; a second test here cost every warp of every tile three instructions
+               per macroblock) */
             uni = ((h.x ^ b.x) | (h.y ^ b.y) | (h.x ^ c.x) | (h.y ^ c.y)) == 0u;
         }
         u32 kd = MBK_NONE;
