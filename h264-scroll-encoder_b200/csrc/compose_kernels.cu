@@ -632,9 +632,12 @@ compose_frames_kernel(const H264GpuFrameDesc *__restrict__ descs, int n_frames,
             uint2 own[MPT + 1];                                 /* own[0] = left neighbour of the first MB */
             uint2 abv[MPT + 2];                                 /* abv[j] = hint above-left of MB j */
             {
+                /* chunk 4 q + k of the tile lives at (4 q + k) ^ ((q >> 1) & 7) = ((4 q) ^ ((q >> 1) & 7)) ^ k: one swizzle term per
+                   slot, the chunk number folded in as a constant */
+                const u32 xo = (4u * (u32)qo) ^ (((u32)qo >> 1) & 7u), xa = (4u * (u32)qa) ^ (((u32)qa >> 1) & 7u);
 #pragma unroll
                 for (int k = 0; k < MPT / 2; k++) {
-                    const uint4 v = staged_chunk(hb, qo, k), u = staged_chunk(hb, qa, k);
+                    const uint4 v = hb[xo ^ (u32)k], u = hb[xa ^ (u32)k];
                     own[1 + 2 * k] = make_uint2(v.x, v.y); own[2 + 2 * k] = make_uint2(v.z, v.w);
                     abv[1 + 2 * k] = make_uint2(u.x, u.y); abv[2 + 2 * k] = make_uint2(u.z, u.w);
                 }
