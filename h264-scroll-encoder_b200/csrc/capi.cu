@@ -266,6 +266,7 @@ int h264gpu_compose_batch(const H264GpuFrameDesc *d_desc, int n_frames,
     H264GpuCtx *ctx = current();
     if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_desc || !d_hints || !d_out || !d_sizes) return fail(H264GPU_ERR_ARG, "null argument");
+    if (((uintptr_t)d_out | (uintptr_t)d_hints | (uintptr_t)d_desc) & 15u) return fail(H264GPU_ERR_ARG, "d_desc, d_hints and d_out must be 16-byte aligned");
     cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, 0, d_dyn, d_dyn_tab, d_payload,
                                                d_out, d_sizes, ctx->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);
@@ -280,6 +281,7 @@ int h264gpu_compose_batch_ex(const H264GpuFrameDesc *d_desc, int n_frames,
     H264GpuCtx *ctx = current();
     if (!ctx) return H264GPU_ERR_NO_DEVICE;
     if (n_frames < 0 || !d_desc || !d_hints || !d_out || !d_sizes) return fail(H264GPU_ERR_ARG, "null argument");
+    if (((uintptr_t)d_out | (uintptr_t)d_hints | (uintptr_t)d_desc) & 15u) return fail(H264GPU_ERR_ARG, "d_desc, d_hints and d_out must be 16-byte aligned");
     cudaError_t e = h264scroll::launch_compose(d_desc, n_frames, d_hints, n_hints, d_dyn, d_dyn_tab, d_payload,
                                                d_out, d_sizes, ctx->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(H264GPU_ERR_CUDA, "compose launch", e);

@@ -154,7 +154,8 @@ float h264gpu_event_elapsed_ms(void *ev_start, void *ev_stop); /* syncs on stop 
 /* ---- the hot path ------------------------------------------------------ */
 
 /*
- * Compose n_frames P-slices.  All pointers are DEVICE pointers.
+ * Compose n_frames P-slices.  All pointers are DEVICE pointers; d_desc, d_hints and d_out 16-byte aligned (the kernel
+ * moves descriptors, hints and output groups as 128-bit words; anything else is refused with H264GPU_ERR_ARG).
  *   d_desc      n_frames frame descriptors
  *   d_hints     dense hint maps, indexed by desc.hint_off
  *   d_dyn       dyn descriptors (may be NULL when no frame splices)
