@@ -91,3 +91,19 @@ def test_frames_without_a_spliced_region_in_every_mode(gpu, po, oracle, flags):
         frames, sizes = gpu.compose_host(b.desc, hints, b.dyn, b.dyn_tab, b.payload)
         for f in range(b.n_frames):
             assert np.array_equal(frames[f], helpers.checker_frame(oracle, b, hints, f)), "%s frame %d" % (b.name, f)
+
+
+def test_misaligned_device_pointers_are_refused(gpu):
+    """d_desc / d_hints / d_out travel as 128-bit words: h264gpu_compose_batch refuses pointers that are not 16-byte aligned
+    instead of launching a kernel that would fault (include/composer_gpu.h)."""
+    b = workloads.make_config4(1)
+    d_desc, d_h = gpu.to_device(b.desc), gpu.alloc(8 * b.hint_stride + 64)
+    d_out, d_sizes = gpu.alloc(b.slot_cap + 64), gpu.alloc(16)
+    L = gpu.lib
+    ok = L.h264gpu_compose_batch(d_desc.ptr, 0, d_h.ptr, None, None, None, d_out.ptr, d_sizes.ptr, None)
+    assert ok == 0
+    for args in ((d_desc.ptr, d_h.ptr, d_out.ptr + 4), (d_desc.ptr, d_h.ptr + 8, d_out.ptr), (d_desc.ptr + 4, d_h.ptr, d_out.ptr)):
+        rc = L.h264gpu_compose_batch(args[0], 1, args[1], None, None, None, args[2], d_sizes.ptr, None)
+        assert rc != 0 and b"16-byte aligned" in L.h264gpu_last_error()
+    for x in (d_desc, d_h, d_out, d_sizes):
+        x.free()
